@@ -1,0 +1,134 @@
+/* ysp.h -- C ABI of the B200-native YOLO-Seg++ inference hot path (libysp.so).
+ *
+ * The reference (Jhewu/YOLO-U) is 100% Python: its "plugin interface" for this path is a set of Python call
+ * signatures on torch.Tensors.  Each entry point below replaces one of them; the Python host side in
+ * `yolo-u_b200/` keeps the reference signatures and hands raw device pointers to these functions through ctypes.
+ *
+ *   reference interface (file:line under the reference tree)                     entry point here
+ *   ---------------------------------------------------------------------------  --------------------------------
+ *   dataset.py:53-68 + evaluate_model.py:136 (u8 HWC -> float CHW /255)          ysp_normalize_u8
+ *   evaluate_model.py:141  YOLO_predictor.model(img) -> [y, [P3,P4,P5]]          ysp_detector_forward
+ *   evaluate_model.py:142-144  logits = sigmoid(P3[:, -1:])                      ysp_bottleneck (and inside ysp_pipeline)
+ *   nms.py:13-166  non_max_suppression(...)                                      ysp_nms
+ *   nms.py:239-296 TorchNMS.nms(boxes, scores, thr)                              ysp_nms_core
+ *   YOLOSegPlusPlus.py:242-272  YOLOSegPlusPlus.forward(x, logits)               ysp_segpp_forward
+ *   evaluate_model.py:157-158,166-174  sigmoid>0.5, TP/FP/FN, Dice counts        ysp_mask_dice
+ *   evaluate_model.py:134-174  (the loop body = the de-facto predict())          ysp_pipeline
+ *   evaluate_model.py:234-243 / YOLOSegPlusPlus.py:150 (state_dict tensors)      ysp_load_weight / ysp_finalize
+ *
+ * Conventions: every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a HOST pointer.  Nothing
+ * is allocated per call: scratch comes from the caller-provided workspace (`d_ws`, at least
+ * ysp_workspace_bytes()).  All calls are asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant per
+ * handle+workspace, and return 0 on success or a negative YSP_E* code; ysp_last_error() gives the message.
+ * There is NO CPU fallback: without a CUDA device every compute entry returns YSP_ECUDA.
+ */
+#ifndef YSP_H_
+#define YSP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YSP_OK 0
+#define YSP_EINVAL (-1)   /* bad argument / shape (Python side raises ValueError / AssertionError) */
+#define YSP_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define YSP_ESTATE (-3)   /* call order: weights missing, not finalized, workspace too small */
+#define YSP_ENOWEIGHT (-4)/* a state_dict tensor the topology needs was never loaded (message names it) */
+
+/* arithmetic / storage mode of the conv path */
+#define YSP_MODE_FP32 0   /* "parity mode": fp32 activations, fp32 FFMA, bit-for-bit deterministic            */
+#define YSP_MODE_BF16 1   /* "throughput mode": bf16 activations, tcgen05 bf16 MMA with fp32 TMEM accumulators */
+
+typedef struct ysp_handle ysp_handle;
+
+int ysp_version(void);
+const char* ysp_last_error(void);
+
+/* -- lifetime / weights ------------------------------------------------------------------------------------------ */
+int ysp_create(ysp_handle** out, int device, int mode);
+void ysp_destroy(ysp_handle* h);
+/* One state_dict tensor (HOST fp32, contiguous, PyTorch layout).  `name` = "det." + DetectionModel key
+ * (e.g. det.model.0.conv.weight) or "seg." + YOLOSegPlusPlus key (seg.decoder.0.0.cv1.bn.running_var). */
+int ysp_load_weight(ysp_handle* h, const char* name, const float* h_data, int ndim, const int64_t* shape);
+/* Fold BatchNorm (eval; detector eps 1e-3 if it arrives unfused, decoder eps 1e-5), repack to the kernel layouts,
+ * upload.  `which`: bit0 = detector, bit1 = seg head. */
+int ysp_finalize(ysp_handle* h, int which);
+/* scratch bytes needed for a batch of B slices of HxW through ysp_pipeline (>= every other entry's need) */
+size_t ysp_workspace_bytes(ysp_handle* h, int B, int H, int W);
+
+/* -- a1: input normalisation -------------------------------------------------------------------------------------- */
+/* u8 [B,H,W,4] (channel order as stored) -> fp32 NCHW [B,4,H,W] = x/255 (ToTensor).  HBM-bound, 4 B in / 16 B out per pixel. */
+int ysp_normalize_u8(const uint8_t* d_u8, float* d_out_nchw, int B, int H, int W, void* stream);
+
+/* -- a2: detector ------------------------------------------------------------------------------------------------- */
+/* img fp32 NCHW [B,4,H,W]; H,W are zero-padded bottom/right to S=ceil32 (decision D1).  Outputs (fp32):
+ * y [B,5,A] (xywh px + sigmoid cls), raw maps NCHW [B,65,S/8,S/8], [B,65,S/16,..], [B,65,S/32,..] (any may be NULL). */
+int ysp_detector_forward(ysp_handle* h, const float* d_img, int B, int H, int W, float* d_y, float* d_p3, float* d_p4,
+                         float* d_p5, void* d_ws, size_t ws_bytes, void* stream);
+
+/* -- a3: bottleneck ---------------------------------------------------------------------------------------------- */
+/* logits[B,1,h,w] = sigmoid(P3_raw[:, C-1, :h, :w]) from NCHW raw map [B,C,Hs,Ws] */
+int ysp_bottleneck(const float* d_p3, int B, int C, int Hs, int Ws, float* d_logits, int h, int w, void* stream);
+
+/* -- a5..a8: seg head -------------------------------------------------------------------------------------------- */
+/* x fp32 NCHW [B,4,H,W] (H,W % 8 == 0), logits fp32 [B,1,H/8,W/8] -> out fp32 [B,1,H,W] mask logits (no sigmoid) */
+int ysp_segpp_forward(ysp_handle* h, const float* d_x, const float* d_logits, float* d_out, int B, int H, int W,
+                      void* d_ws, size_t ws_bytes, void* stream);
+
+/* -- a4: box suppression ------------------------------------------------------------------------------------------ */
+/* pred fp32 [B,C,A] (rows 0..3 xywh, 4..4+nc-1 class scores, rest extra; NOT modified).  Outputs padded:
+ * out_boxes [B,max_det,6+extra] (xyxy, conf, cls, extra), out_idx [B,max_det] int64 anchor indices, out_count [B] int32.
+ * Stable descending score order (ties -> lower anchor index), suppress iff IoU > iou_thres with separately
+ * rounded fp32 ops, conf strictly > conf_thres, class offset cls*max_wh unless agnostic, n > max_nms truncation,
+ * max_det truncation; no wall-clock limit.  classes: optional DEVICE int32[n_classes] filter (nms.py:127-131). */
+size_t ysp_nms_workspace_bytes(int B, int C, int A, int max_det);
+int ysp_nms(const float* d_pred, int B, int C, int A, int nc, float conf_thres, float iou_thres, int max_det,
+            int max_nms, float max_wh, int agnostic, const int32_t* d_classes, int n_classes, float* d_out_boxes,
+            int64_t* d_out_idx, int32_t* d_out_count, void* d_ws, size_t ws_bytes, void* stream);
+/* boxes [N,4] xyxy, scores [N] -> keep [N] int64 (score order), count [1] int32 */
+int ysp_nms_core(const float* d_boxes, const float* d_scores, int N, float iou_thres, int64_t* d_keep,
+                 int32_t* d_count, void* d_ws, size_t ws_bytes, void* stream);
+
+/* nms.py:84-86 side effect (the reference overwrites prediction[:, :4, :] with xyxy in place) */
+int ysp_xywh2xyxy_inplace(float* d_pred, int B, int C, int A, void* stream);
+
+/* -- a9: mask + Dice counters ------------------------------------------------------------------------------------ */
+/* counts[b] = (|P&T|, |P|, |T|), P = sigmoid(logit) > 0.5 (fp32), T = target > 0.5; optional u8 mask out [B,HW] */
+int ysp_mask_dice(const float* d_logits, const float* d_target, int B, int HW, int32_t* d_counts, uint8_t* d_mask,
+                  void* stream);
+
+/* -- fused pipeline (evaluate_model.py:134-174 with decision D1) -------------------------------------------------- */
+typedef struct ysp_pipeline_io {
+  const float* d_img;        /* fp32 NCHW [B,4,H,W]   (or NULL if d_img_u8 given) */
+  const uint8_t* d_img_u8;   /* u8 [B,H,W,4]          (normalised on the fly, a1) */
+  const float* d_target;     /* fp32 [B,1,H,W] or NULL (then counts' |P&T|,|T| are 0) */
+  float* d_mask_logits;      /* fp32 [B,1,H,W] */
+  float* d_y;                /* fp32 [B,5,A] or NULL */
+  float* d_bottleneck;       /* fp32 [B,1,H/8,W/8] or NULL */
+  float* d_det_boxes;        /* fp32 [B,max_det,6] */
+  int64_t* d_det_idx;        /* int64 [B,max_det] */
+  int32_t* d_det_count;      /* int32 [B] */
+  int32_t* d_counts;         /* int32 [B,3] */
+  uint8_t* d_mask;           /* u8 [B,H,W] or NULL */
+  float conf_thres, iou_thres;
+  int max_det;
+} ysp_pipeline_io;
+int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, void* d_ws, size_t ws_bytes,
+                 void* stream);
+
+/* -- introspection (tests / profiling) ---------------------------------------------------------------------------- */
+/* keep every intermediate alive (no workspace reuse) so ysp_debug_tensor can read them; affects plans built later */
+int ysp_set_keep_intermediates(ysp_handle* h, int on);
+/* number of kernels the last ysp_* call on this handle launched */
+int ysp_last_launch_count(ysp_handle* h);
+/* copy a named intermediate of the last plan run ("det:model.6", "seg:decoder.0", ...) to fp32 NCHW host-visible
+ * device buffer; returns dims via shape[4] = N,C,H,W.  d_out may be NULL to query the shape only. */
+int ysp_debug_tensor(ysp_handle* h, const char* name, void* d_ws, float* d_out, int64_t* shape, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YSP_H_ */

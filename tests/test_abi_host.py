@@ -1,0 +1,99 @@
+"""CPU: the C-ABI library loads and exports every symbol include/ysp.h declares; host-side logic (state_dict
+compatibility, sharding, metric aggregation, error behaviour without a GPU).  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import yolo_u_b200 as ysp
+from yolo_u_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ysp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ysp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = ysp.lib()
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), f"libysp.so does not export {n}"
+    assert set(names) == set(_lib.PROTOTYPES), "ctypes prototypes out of sync with include/ysp.h"
+    assert L.ysp_version() >= 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
+def test_no_cpu_fallback():
+    h = ctypes.c_void_p()
+    rc = ysp.lib().ysp_create(ctypes.byref(h), 0, 0)
+    assert rc == -2 and b"no CPU fallback" in ysp.lib().ysp_last_error()
+    with pytest.raises(ysp.YspError):
+        ysp.non_max_suppression(torch.zeros(1, 5, 10))
+    with pytest.raises(ysp.YspError):
+        ysp.TorchNMS.nms(torch.zeros(2, 4), torch.zeros(2), 0.5)
+    with pytest.raises(ysp.YspError):
+        ysp.mask_counts(torch.zeros(1, 1, 8, 8), None)
+    with pytest.raises(ysp.YspError):
+        ysp.Engine("cpu")
+
+
+def test_nms_argument_checks_match_reference():
+    # nms.py:59-60 are asserts and fire before anything touches the device
+    with pytest.raises(AssertionError, match="Invalid Confidence threshold"):
+        ysp.non_max_suppression(torch.zeros(1, 5, 10), conf_thres=1.5)
+    with pytest.raises(AssertionError, match="Invalid IoU"):
+        ysp.non_max_suppression(torch.zeros(1, 5, 10), iou_thres=-0.1)
+    assert ysp.TorchNMS.nms(torch.zeros(0, 4), torch.zeros(0), 0.5).shape == (0,)
+
+
+def test_state_dict_is_reference_compatible(models):
+    pred, seg = models
+    m = ysp.YOLOSegPlusPlus(pred)
+    ref_sd, sd = seg.state_dict(), m.state_dict()
+    assert list(ref_sd.keys()) == list(sd.keys())
+    assert all(ref_sd[k].shape == sd[k].shape for k in sd)
+    m.load_state_dict(ref_sd)                                  # evaluate_model.py:243
+    assert torch.equal(m.state_dict()["output.weight"], ref_sd["output.weight"])
+    assert all(not p.requires_grad for p in m.encoder.parameters())       # YOLOSegPlusPlus.py:151-153
+    head = sum(p.numel() for n, p in m.named_parameters() if not n.startswith("encoder."))
+    assert head == 63764
+
+
+def test_sharding_is_a_partition():
+    for nv, ws in [(64, 1), (64, 2), (64, 4), (64, 8), (7, 3), (2, 4)]:
+        got = [ysp.shard_volumes(nv, ws, r) for r in range(ws)]
+        assert got[0][0] == 0 and got[-1][1] == nv
+        assert all(got[i][1] == got[i + 1][0] for i in range(ws - 1))
+        sizes = [b - a for a, b in got]
+        assert max(sizes) - min(sizes) <= 1
+    assert ysp.shard_slices(64, 155, 8, 3) == (3 * 8 * 155, 4 * 8 * 155)
+    assert ysp.batches(0, 10, 4) == [(0, 4), (4, 8), (8, 10)]
+    with pytest.raises(ValueError):
+        ysp.shard_volumes(4, 2, 2)
+
+
+def test_dice_and_metrics_match_oracle():
+    from oracle.model import dice_from_counts as odice, tp_fp_fn
+    g = torch.Generator().manual_seed(0)
+    t = torch.randint(0, 50, (16,), generator=g)
+    p = torch.randint(0, 50, (16,), generator=g)
+    inter = torch.minimum(t, p) // 2
+    counts = torch.stack([inter, p, t], 1)
+    counts[0] = 0
+    counts[1] = torch.tensor([0, 7, 0])
+    assert torch.allclose(ysp.dice_from_counts(counts), odice(counts))
+    m = ysp.SegMetrics()
+    m.update(counts[:8].int())
+    m.update(counts[8:].int())
+    r = m.compute()
+    tp, fp, fn = tp_fp_fn(counts)
+    assert (r["TP"], r["FP"], r["FN"]) == (tp, fp, fn)
+    assert r["dice"] == pytest.approx(float(odice(counts).double().mean()), abs=1e-7)
+    assert r["slices"] == 16

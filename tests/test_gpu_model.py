@@ -1,0 +1,148 @@
+"""GPU parity of the conv path through the C ABI vs the PyTorch fp32 oracle on identical seeded synthetic inputs and
+weights.  Tolerances (north_star): fp32 parity mode max-abs <= 1e-3 on mask logits, Dice <= 1e-4; bf16 throughput
+mode is checked against looser, explicitly stated bounds (1e-3 is not reachable with bf16 storage)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL_LOGITS_FP32 = 1e-3
+TOL_DICE = 1e-4
+TOL_LOGITS_BF16 = 0.25          # absolute, logits calibrated to std 1.5
+TOL_FLIP_BF16 = 0.02            # fraction of mask pixels allowed to differ in bf16 mode
+TOL_DICE_BF16 = 5e-3
+
+
+@pytest.fixture(scope="module")
+def ysp():
+    import yolo_u_b200
+    assert torch.cuda.is_available()
+    return yolo_u_b200
+
+
+@pytest.fixture(scope="module")
+def ref240(models):
+    from oracle.model import synth_inputs, pipeline, mask_counts
+    from oracle import nms as onms
+    pred, seg = models
+    x, lg, tg = synth_inputs(4, 240)
+    with torch.no_grad():
+        out = seg(x, lg)
+        p_out, dets, keep, y, bott = pipeline(pred, seg, x, onms.non_max_suppression)
+    return dict(x=x, lg=lg, tg=tg, seg_out=out, pipe_out=p_out, dets=dets, keep=keep, y=y, bott=bott,
+                counts=mask_counts(p_out, tg))
+
+
+def test_normalize_u8(ysp):
+    import ctypes
+    g = torch.Generator().manual_seed(1)
+    u8 = torch.randint(0, 256, (3, 240, 240, 4), dtype=torch.uint8, generator=g)
+    want = u8.permute(0, 3, 1, 2).float().div(255)               # ToTensor (dataset.py:68)
+    d = u8.cuda()
+    out = torch.empty(3, 4, 240, 240, device="cuda")
+    rc = ysp.lib().ysp_normalize_u8(d.data_ptr(), out.data_ptr(), 3, 240, 240, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), want)
+
+
+def test_mask_dice_counts(ysp):
+    from oracle.model import mask_counts as omc
+    g = torch.Generator().manual_seed(3)
+    lg = torch.randn(5, 1, 240, 240, generator=g)
+    lg[0, 0, 0, :4] = torch.tensor([0.0, 5e-8, -5e-8, 1e-6])     # sigmoid == 0.5 band
+    tg = (torch.rand(5, 1, 240, 240, generator=g) > 0.5).float()
+    tg[3] = 0
+    lg[4] = -3.0
+    counts, mask = ysp.mask_counts(lg.cuda(), tg.cuda(), want_mask=True)
+    assert torch.equal(counts.cpu().long(), omc(lg, tg))
+    assert torch.equal(mask.cpu().bool(), torch.sigmoid(lg) > 0.5)
+    c2 = ysp.mask_counts(lg.cuda(), None)
+    assert torch.equal(c2[:, 1].cpu(), counts[:, 1].cpu()) and int(c2[:, 0].sum()) == 0
+
+
+def test_segpp_fp32_parity(ysp, models, ref240):
+    pred, seg = models
+    m = ysp.YOLOSegPlusPlus(pred, mode="fp32")
+    m.load_state_dict(seg.state_dict())
+    out = m(ref240["x"].cuda(), ref240["lg"].cuda())
+    assert out.shape == (4, 1, 240, 240) and out.dtype == torch.float32
+    err = (out.cpu() - ref240["seg_out"]).abs().max().item()
+    assert err <= TOL_LOGITS_FP32, f"max-abs logits error {err}"
+    # reference-native resolution (160) and a non-square multiple of 8
+    from oracle.model import synth_inputs
+    for (h, w) in ((160, 160), (64, 96)):
+        g = torch.Generator().manual_seed(h + w)
+        x = torch.rand(2, 4, h, w, generator=g)
+        lg = torch.sigmoid(torch.randn(2, 1, h // 8, w // 8, generator=g))
+        with torch.no_grad():
+            want = seg(x, lg)
+        got = m(x.cuda(), lg.cuda())
+        assert (got.cpu() - want).abs().max().item() <= TOL_LOGITS_FP32, (h, w)
+    with pytest.raises(RuntimeError):
+        m(torch.rand(1, 4, 100, 100).cuda(), torch.rand(1, 1, 12, 12).cuda())
+
+
+def test_detector_fp32_parity(ysp, models, ref240):
+    pred, _ = models
+    det = ysp.B200Detector.from_predictor(pred, mode="fp32")
+    from oracle.model import pad_to_multiple
+    with torch.no_grad():
+        y_ref, raws_ref = pred.model(pad_to_multiple(ref240["x"]))
+    y, raws = det(ref240["x"].cuda())
+    assert y.shape == (4, 5, 1344)
+    for r, rr in zip(raws, raws_ref):
+        assert r.shape == rr.shape
+        assert (r.cpu() - rr).abs().max().item() <= 1e-3
+    assert (y[:, 4:].cpu() - y_ref[:, 4:]).abs().max().item() <= 1e-4         # sigmoid cls
+    assert (y[:, :4].cpu() - y_ref[:, :4]).abs().max().item() <= 2e-2         # boxes in pixels (x stride 8..32)
+    # native %32 input, reference resolution
+    x160 = torch.rand(2, 4, 160, 160, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        y_ref, raws_ref = pred.model(x160)
+    y, raws = det(x160.cuda())
+    assert y.shape == (2, 5, 525)
+    assert (raws[0].cpu() - raws_ref[0]).abs().max().item() <= 1e-3
+
+
+def test_pipeline_fp32_parity(ysp, models, ref240):
+    from oracle.model import dice_from_counts
+    pred, seg = models
+    P = ysp.Predictor.from_modules(pred, seg, mode="fp32")
+    ml, dets, keep, counts = P.predict(ref240["x"].cuda(), ref240["tg"].cuda())
+    assert (ml.cpu() - ref240["pipe_out"]).abs().max().item() <= TOL_LOGITS_FP32
+    d_ref = dice_from_counts(ref240["counts"])
+    d = ysp.dice_from_counts(counts.cpu())
+    assert (d - d_ref).abs().max().item() <= TOL_DICE
+    # NMS inside the pipeline: bit-exactness is defined at the NMS boundary (same prediction tensor into both, SURVEY
+    # App. C); the pipeline's own y differs from the oracle's by fp32 rounding, so compare against NMS of OUR y.
+    o = P.predict_raw(ref240["x"].cuda(), ref240["tg"].cuda())
+    from oracle import cnms
+    want_d, want_k = cnms.nms_batched(o["y"].cpu(), 0.25, 0.45, 300)
+    for b in range(4):
+        assert torch.equal(keep[b].cpu(), want_k[b])
+        assert torch.equal(dets[b].cpu(), want_d[b])
+    assert (o["bottleneck"].cpu() - ref240["bott"]).abs().max().item() <= 1e-4
+    # u8 ingest path (a1) gives the same result as fp32 input of x/255
+    u8 = (ref240["x"] * 255).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    xf = u8.permute(0, 3, 1, 2).float() / 255
+    a = P.predict_raw(u8.cuda())["mask_logits"].clone()
+    b = P.predict_raw(xf.cuda())["mask_logits"].clone()
+    assert torch.equal(a, b)
+
+
+def test_bf16_mode_bounds(ysp, models, ref240):
+    from oracle.model import dice_from_counts, mask_counts
+    pred, seg = models
+    P = ysp.Predictor.from_modules(pred, seg, mode="bf16")
+    ml, dets, keep, counts = P.predict(ref240["x"].cuda(), ref240["tg"].cuda())
+    ml = ml.cpu()
+    err = (ml - ref240["pipe_out"]).abs().max().item()
+    flips = ((ml > 0) != (ref240["pipe_out"] > 0)).float().mean().item()
+    d = ysp.dice_from_counts(counts.cpu())
+    d_ref = dice_from_counts(ref240["counts"])
+    print(f"bf16: logits max-abs {err:.4f}, mask flips {flips:.5f}, dice err {(d - d_ref).abs().max().item():.2e}")
+    assert err <= TOL_LOGITS_BF16
+    assert flips <= TOL_FLIP_BF16
+    assert (d - d_ref).abs().max().item() <= TOL_DICE_BF16
+    assert torch.equal(counts.cpu().long(), mask_counts(ml, ref240["tg"]))   # counters exact on our own logits

@@ -1,0 +1,71 @@
+// common.cuh -- shared device helpers and kernel parameter blocks for libysp (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ysp {
+
+typedef __nv_bfloat16 bf16;
+
+enum { ACT_NONE = 0, ACT_SILU = 1 };
+
+// ---- scalar conversion ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- 4-wide vectors (16 B fp32 / 8 B bf16) -------------------------------------------------------------------------
+struct F4 { float v[4]; };
+template <typename T> __device__ __forceinline__ F4 load4(const T* p);
+template <> __device__ __forceinline__ F4 load4<float>(const float* p) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  F4 r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+template <> __device__ __forceinline__ F4 load4<bf16>(const bf16* p) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x), b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+  F4 r; r.v[0] = __low2float(a); r.v[1] = __high2float(a); r.v[2] = __low2float(b); r.v[3] = __high2float(b); return r;
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, const F4& r);
+template <> __device__ __forceinline__ void store4<float>(float* p, const F4& r) {
+  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+}
+template <> __device__ __forceinline__ void store4<bf16>(bf16* p, const F4& r) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(r.v[0], r.v[1]), b = __floats2bfloat162_rn(r.v[2], r.v[3]);
+  uint2 t; t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float apply_act(float x, int act) { return act == ACT_SILU ? silu_f(x) : x; }
+
+// ---- parameter blocks ----------------------------------------------------------------------------------------------
+// Activations are NHWC "views": base pointer already advanced to the first channel of the view, `cs` = pixel stride
+// in elements (>= C), so concatenations are formed by construction (producers write into channel slices).
+struct ConvP {
+  const void* in; void* out; const float* w; const float* bias; const void* res;
+  int N, H, W, Cin, in_cs;
+  int OH, OW, Cout, out_cs, res_cs;
+  int kh, kw, stride, pad, act;
+  int M, K, wld;            // M = N*OH*OW, K = kh*kw*Cin, weights [K][wld] fp32
+};
+
+struct DwP {
+  const void* in; void* out; const float* w; const float* bias; const void* res;
+  int N, H, W, C, in_cs, out_cs, res_cs;
+  int k, pad, act;
+  int grp, grp_stride;      // input channel c lives at (c / grp) * grp_stride + c % grp of the input view
+};
+
+struct EwP {                // generic elementwise / resampling ops over NHWC views
+  const void* a; const void* b; void* out;
+  int N, H, W, C, a_cs, b_cs, out_cs;
+  int OH, OW;
+};
+
+}  // namespace ysp

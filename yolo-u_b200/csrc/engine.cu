@@ -1,0 +1,844 @@
+// engine.cu -- handle, weight packing, static execution plans and the C ABI of libysp.so (see include/ysp.h).
+//
+// The network topology of the hot path is fixed (YOLOv12n detector 4-ch nc=1 + YOLO-Seg++ head, SURVEY App. A.3 /
+// 3.2), so it is written here once as a graph builder that emits a static list of kernel launches ("plan") per
+// (batch, H, W).  Activations live in a caller-provided workspace as NHWC views; concatenations are formed by
+// construction (producers write into channel slices of the consumer's buffer), buffers are packed by lifetime so
+// the working set of consecutive layers stays L2-resident.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ysp.h"
+#include "kernels.h"
+
+using namespace ysp;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+  return code;
+}
+#define CUDA_OK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(YSP_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
+
+namespace {
+
+struct HostT { std::vector<float> d; std::vector<int64_t> shape; };
+
+struct DevConv {           // packed weights of one conv (BN folded)
+  float* w = nullptr;      // dense: [K][wld] fp32; depthwise: [k*k][C]
+  float* bias = nullptr;   // [Cout]
+  void* w_tc = nullptr;    // bf16 [Cout_pad][K_pad] K-major (tensor-core path), or NULL
+  int Cout = 0, Cin = 0, kh = 0, kw = 0, wld = 0, K = 0, Ktc = 0;
+  bool dw = false;
+};
+
+struct TRef { int buf = -1; int N = 0, H = 0, W = 0, C = 0, cs = 0, co = 0, dt = 0; };
+struct BufInfo { size_t bytes = 0, off = 0; int first = 1 << 30, last = -1; };
+struct RunCtx { char* ws; void* ext[16]; cudaStream_t s; };
+
+static inline size_t esize(int dt) { return dt == DT_F32 ? 4 : 2; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Plan {
+  std::vector<std::function<void(RunCtx&)>> steps;
+  std::vector<BufInfo> bufs;
+  std::map<std::string, TRef> named;
+  std::vector<TcConvPlan*> tc_plans;
+  size_t ws_bytes = 0;
+  int launches = 0;
+  ~Plan() { for (auto* t : tc_plans) tc_conv_plan_destroy(t); }
+  void* ptr(const RunCtx& c, const TRef& t) const {
+    char* base = t.buf >= 0 ? c.ws + bufs[t.buf].off : reinterpret_cast<char*>(c.ext[-1 - t.buf]);
+    return base ? base + (size_t)t.co * esize(t.dt) : nullptr;
+  }
+};
+
+}  // namespace
+
+struct ysp_handle {
+  int device = 0, mode = YSP_MODE_FP32;
+  std::map<std::string, HostT> host;
+  std::map<std::string, DevConv> convs;
+  std::map<std::string, float*> vecs;        // small raw fp32 vectors (ECA conv1d weights)
+  bool det_ready = false, seg_ready = false;
+  bool keep_all = false;                     // disable buffer reuse so ysp_debug_tensor sees every intermediate
+  std::map<std::string, std::unique_ptr<Plan>> plans;
+  Plan* last_plan = nullptr;
+  int last_launches = 0;
+  std::string build_err;
+  int act_dt() const { return mode == YSP_MODE_BF16 ? DT_BF16 : DT_F32; }
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// weight packing
+// ---------------------------------------------------------------------------------------------------------------------
+static const HostT* find(ysp_handle* h, const std::string& k) {
+  auto it = h->host.find(k);
+  return it == h->host.end() ? nullptr : &it->second;
+}
+
+// `prefix` names either an ultralytics Conv module (prefix.conv.weight [+ prefix.conv.bias] [+ prefix.bn.*]) or a
+// plain nn.Conv2d (prefix.weight, prefix.bias).  BN folded in double precision with the module's eps.
+static int pack_conv(ysp_handle* h, const std::string& prefix, double bn_eps, DevConv** out) {
+  auto it = h->convs.find(prefix);
+  if (it != h->convs.end()) { *out = &it->second; return 0; }
+  const HostT* w = find(h, prefix + ".conv.weight");
+  const HostT* b = nullptr;
+  const HostT *g = nullptr, *be = nullptr, *mu = nullptr, *var = nullptr;
+  if (w) {
+    b = find(h, prefix + ".conv.bias");
+    g = find(h, prefix + ".bn.weight");
+    if (g) {
+      be = find(h, prefix + ".bn.bias"); mu = find(h, prefix + ".bn.running_mean"); var = find(h, prefix + ".bn.running_var");
+      if (!be || !mu || !var) return fail(YSP_ENOWEIGHT, "incomplete BatchNorm state for %s", prefix.c_str());
+    }
+  } else {
+    w = find(h, prefix + ".weight");
+    b = find(h, prefix + ".bias");
+  }
+  if (!w) return fail(YSP_ENOWEIGHT, "missing weight %s(.conv).weight", prefix.c_str());
+  if (w->shape.size() != 4) return fail(YSP_EINVAL, "%s: conv weight must be 4-d", prefix.c_str());
+  DevConv dc;
+  dc.Cout = (int)w->shape[0]; int cin_g = (int)w->shape[1]; dc.kh = (int)w->shape[2]; dc.kw = (int)w->shape[3];
+  dc.dw = (cin_g == 1 && dc.Cout > 1 && (dc.kh > 1));
+  // a [C,1,1,1] weight is ambiguous; 1x1 with Cin=1 does not occur on the path except as depthwise-free convs
+  std::vector<double> scale(dc.Cout, 1.0), shift(dc.Cout, 0.0);
+  for (int co = 0; co < dc.Cout; ++co) {
+    double bb = b ? b->d[co] : 0.0;
+    if (g) {
+      double sc = (double)g->d[co] / std::sqrt((double)var->d[co] + bn_eps);
+      scale[co] = sc;
+      shift[co] = (double)be->d[co] + (bb - (double)mu->d[co]) * sc;
+    } else {
+      shift[co] = bb;
+    }
+  }
+  std::vector<float> hw, hb(dc.Cout);
+  for (int co = 0; co < dc.Cout; ++co) hb[co] = (float)shift[co];
+  const int taps = dc.kh * dc.kw;
+  if (dc.dw) {
+    dc.Cin = dc.Cout; dc.K = taps; dc.wld = dc.Cout;
+    hw.assign((size_t)taps * dc.Cout, 0.f);
+    for (int c = 0; c < dc.Cout; ++c)
+      for (int t = 0; t < taps; ++t) hw[(size_t)t * dc.Cout + c] = (float)(w->d[(size_t)c * taps + t] * scale[c]);
+  } else {
+    dc.Cin = cin_g; dc.K = taps * dc.Cin; dc.wld = (dc.Cout + 3) / 4 * 4;
+    hw.assign((size_t)dc.K * dc.wld, 0.f);
+    for (int co = 0; co < dc.Cout; ++co)
+      for (int ci = 0; ci < dc.Cin; ++ci)
+        for (int t = 0; t < taps; ++t)
+          hw[(size_t)(t * dc.Cin + ci) * dc.wld + co] = (float)(w->d[((size_t)co * dc.Cin + ci) * taps + t] * scale[co]);
+  }
+  CUDA_OK(cudaMalloc(&dc.w, hw.size() * 4));
+  CUDA_OK(cudaMemcpy(dc.w, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&dc.bias, hb.size() * 4));
+  CUDA_OK(cudaMemcpy(dc.bias, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
+  if (!dc.dw && h->mode == YSP_MODE_BF16) {
+    // tensor-core layout: [Cout_pad16][Ktc] bf16, K-major, k = tap*Cin_pad + ci with Cin padded to a multiple of 16
+    int cin_pad = (dc.Cin + 15) / 16 * 16;
+    int cout_pad = (dc.Cout + 15) / 16 * 16;
+    dc.Ktc = taps * cin_pad;
+    std::vector<uint16_t> hbf((size_t)cout_pad * dc.Ktc, 0);
+    for (int co = 0; co < dc.Cout; ++co)
+      for (int ci = 0; ci < dc.Cin; ++ci)
+        for (int t = 0; t < taps; ++t) {
+          float v = (float)(w->d[((size_t)co * dc.Cin + ci) * taps + t] * scale[co]);
+          uint32_t u; memcpy(&u, &v, 4);
+          uint32_t r = u + 0x7fffu + ((u >> 16) & 1u);          // round-to-nearest-even to bf16
+          hbf[(size_t)co * dc.Ktc + (size_t)t * cin_pad + ci] = (uint16_t)(r >> 16);
+        }
+    CUDA_OK(cudaMalloc(&dc.w_tc, hbf.size() * 2));
+    CUDA_OK(cudaMemcpy(dc.w_tc, hbf.data(), hbf.size() * 2, cudaMemcpyHostToDevice));
+  }
+  auto res = h->convs.emplace(prefix, dc);
+  *out = &res.first->second;
+  return 0;
+}
+
+static int pack_vec(ysp_handle* h, const std::string& key, float** out) {
+  auto it = h->vecs.find(key);
+  if (it != h->vecs.end()) { *out = it->second; return 0; }
+  const HostT* t = find(h, key);
+  if (!t) return fail(YSP_ENOWEIGHT, "missing weight %s", key.c_str());
+  float* d = nullptr;
+  CUDA_OK(cudaMalloc(&d, t->d.size() * 4));
+  CUDA_OK(cudaMemcpy(d, t->d.data(), t->d.size() * 4, cudaMemcpyHostToDevice));
+  h->vecs[key] = d;
+  *out = d;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// graph builder
+// ---------------------------------------------------------------------------------------------------------------------
+struct Builder {
+  ysp_handle* h; Plan* plan; int dt; std::string ns; double bn_eps; int rc = 0;
+  Builder(ysp_handle* h_, Plan* p_, const std::string& ns_, double eps) : h(h_), plan(p_), dt(h_->act_dt()), ns(ns_), bn_eps(eps) {}
+
+  TRef alloc(int N, int H, int W, int C, int dtype = -1, int cs = 0) {
+    if (dtype < 0) dtype = dt;
+    int align = dtype == DT_F32 ? 4 : 8;                       // 16-byte pixel rows
+    if (cs == 0) cs = (C + align - 1) / align * align;
+    BufInfo b; b.bytes = align_up((size_t)N * H * W * cs * esize(dtype), 256);
+    plan->bufs.push_back(b);
+    TRef t; t.buf = (int)plan->bufs.size() - 1; t.N = N; t.H = H; t.W = W; t.C = C; t.cs = cs; t.co = 0; t.dt = dtype;
+    return t;
+  }
+  static TRef ext(int slot, int N, int H, int W, int C, int cs, int dtype) {
+    TRef t; t.buf = -1 - slot; t.N = N; t.H = H; t.W = W; t.C = C; t.cs = cs; t.co = 0; t.dt = dtype; return t;
+  }
+  static TRef slice(TRef t, int c0, int c) { t.co += c0; t.C = c; return t; }
+  void name(const std::string& n, const TRef& t) { plan->named[ns + ":" + n] = t; }
+
+  void touch(const TRef& t) {
+    if (t.buf < 0) return;
+    BufInfo& b = plan->bufs[t.buf];
+    int step = (int)plan->steps.size();
+    b.first = std::min(b.first, step); b.last = std::max(b.last, step);
+  }
+  void emit(std::function<void(RunCtx&)> f, std::initializer_list<const TRef*> uses, int nlaunch = 1) {
+    for (auto* t : uses) if (t) touch(*t);
+    plan->steps.push_back(std::move(f));
+    plan->launches += nlaunch;
+  }
+
+  // dense conv (ultralytics Conv / nn.Conv2d); OH/OW default to 'same'/stride arithmetic on (padH, padW)
+  void conv(const std::string& prefix, TRef in, TRef out, int k, int s, int act, const TRef* res = nullptr,
+            int padH = 0, int padW = 0) {
+    if (rc) return;
+    DevConv* dc = nullptr;
+    if ((rc = pack_conv(h, ns + "." + prefix, bn_eps, &dc))) return;
+    if (dc->dw || dc->Cin != in.C || dc->Cout != out.C || dc->kh != k) {
+      rc = fail(YSP_EINVAL, "conv %s: weight [%d,%d,%d,%d] does not match in C=%d out C=%d k=%d", prefix.c_str(), dc->Cout,
+                dc->Cin, dc->kh, dc->kw, in.C, out.C, k);
+      return;
+    }
+    ConvP p = {};
+    p.w = dc->w; p.bias = dc->bias;
+    p.N = in.N; p.H = in.H; p.W = in.W; p.Cin = in.C; p.in_cs = in.cs;
+    p.OH = out.H; p.OW = out.W; p.Cout = out.C; p.out_cs = out.cs; p.res_cs = res ? res->cs : 0;
+    p.kh = k; p.kw = k; p.stride = s; p.pad = k / 2; p.act = act;
+    p.M = out.N * out.H * out.W; p.K = dc->K; p.wld = dc->wld;
+    (void)padH; (void)padW;
+    Plan* pl = plan;
+    TRef rres = res ? *res : TRef();
+    bool has_res = res != nullptr;
+    int in_dt = in.dt, out_dt = out.dt;
+    TcConvPlan* tcp = nullptr;
+    if (h->mode == YSP_MODE_BF16 && dc->w_tc && in_dt == DT_BF16 && getenv("YSP_NO_TC") == nullptr) {
+      ConvP q = p; q.K = dc->Ktc;
+      if (tc_conv_supported(q)) {
+        tcp = tc_conv_plan_create(q, dc->w_tc, out_dt);
+        if (tcp) pl->tc_plans.push_back(tcp);
+      }
+    }
+    emit([=](RunCtx& c) {
+      ConvP q = p;
+      q.in = pl->ptr(c, in); q.out = pl->ptr(c, out); q.res = has_res ? pl->ptr(c, rres) : nullptr;
+      if (tcp) launch_conv_tc(tcp, q, c.s);
+      else launch_conv_dense(q, in_dt, out_dt, c.s);
+    }, {&in, &out, res});
+  }
+
+  void dw(const std::string& prefix, TRef in, TRef out, int k, int act, const TRef* res = nullptr, int grp = 0,
+          int grp_stride = 0) {
+    if (rc) return;
+    DevConv* dc = nullptr;
+    if ((rc = pack_conv(h, ns + "." + prefix, bn_eps, &dc))) return;
+    if (!dc->dw || dc->Cout != out.C || dc->kh != k || (out.C & 3)) {
+      rc = fail(YSP_EINVAL, "dwconv %s: weight [%d,%d,%d,%d] does not match C=%d k=%d", prefix.c_str(), dc->Cout, dc->Cin,
+                dc->kh, dc->kw, out.C, k);
+      return;
+    }
+    DwP p = {};
+    p.w = dc->w; p.bias = dc->bias;
+    p.N = out.N; p.H = out.H; p.W = out.W; p.C = out.C; p.in_cs = in.cs; p.out_cs = out.cs; p.res_cs = res ? res->cs : 0;
+    p.k = k; p.pad = k / 2; p.act = act;
+    p.grp = grp ? grp : out.C; p.grp_stride = grp ? grp_stride : out.C;
+    Plan* pl = plan; TRef rres = res ? *res : TRef(); bool has_res = res != nullptr; int d = dt;
+    emit([=](RunCtx& c) {
+      DwP q = p;
+      q.in = pl->ptr(c, in); q.out = pl->ptr(c, out); q.res = has_res ? pl->ptr(c, rres) : nullptr;
+      launch_conv_dw(q, d, c.s);
+    }, {&in, &out, res});
+  }
+
+  void ew(int mode, TRef a, const TRef* b, TRef out) {
+    if (rc) return;
+    EwP p = {};
+    p.N = out.N; p.H = a.H; p.W = a.W; p.C = out.C; p.a_cs = a.cs; p.b_cs = b ? b->cs : 0; p.out_cs = out.cs;
+    p.OH = out.H; p.OW = out.W;
+    Plan* pl = plan; TRef rb = b ? *b : TRef(); bool has_b = b != nullptr; int d = dt;
+    emit([=](RunCtx& c) {
+      EwP q = p;
+      q.a = pl->ptr(c, a); q.b = has_b ? pl->ptr(c, rb) : nullptr; q.out = pl->ptr(c, out);
+      if (mode == 0) launch_add(q, d, c.s);
+      else if (mode == 1) launch_up_nearest2(q, d, c.s);
+      else launch_up_bilinear2(q, d, c.s);
+    }, {&a, b, &out});
+  }
+
+  void eca(const std::string& key, TRef x) {
+    if (rc) return;
+    float* w3 = nullptr;
+    if ((rc = pack_vec(h, ns + "." + key, &w3))) return;
+    TRef mean = alloc(x.N, 1, 1, x.C, DT_F32);
+    Plan* pl = plan; int d = dt;
+    emit([=](RunCtx& c) {
+      launch_eca(pl->ptr(c, x), x.N, x.H * x.W, x.C, x.cs, w3, (float*)pl->ptr(c, mean), d, c.s);
+    }, {&x, &mean}, 2);
+  }
+
+  void attention(TRef qkv, TRef out, int heads, int area) {
+    if (rc) return;
+    Plan* pl = plan; int d = dt;
+    emit([=](RunCtx& c) {
+      launch_attention(pl->ptr(c, qkv), pl->ptr(c, out), qkv.N, qkv.H * qkv.W, out.C, heads, area, qkv.cs, out.cs, d, c.s);
+    }, {&qkv, &out});
+  }
+
+  // ---- ultralytics blocks, concat-by-construction -------------------------------------------
+  void bottleneck(const std::string& p, TRef x, TRef out, bool shortcut, int k0, int k1, double e) {
+    int c_ = (int)(out.C * e);
+    TRef t = alloc(x.N, x.H, x.W, c_);
+    conv(p + ".cv1", x, t, k0, 1, ACT_SILU);
+    bool add = shortcut && x.C == out.C;
+    conv(p + ".cv2", t, out, k1, 1, ACT_SILU, add ? &x : nullptr);
+  }
+  void c3k(const std::string& p, TRef x, TRef out, int n, bool shortcut) {
+    int c_ = (int)(out.C * 0.5);
+    TRef cat = alloc(x.N, x.H, x.W, 2 * c_);
+    TRef a = alloc(x.N, x.H, x.W, c_);
+    conv(p + ".cv1", x, a, 1, 1, ACT_SILU);
+    conv(p + ".cv2", x, slice(cat, c_, c_), 1, 1, ACT_SILU);
+    TRef cur = a;
+    for (int i = 0; i < n; ++i) {
+      TRef dst = (i == n - 1) ? slice(cat, 0, c_) : alloc(x.N, x.H, x.W, c_);
+      bottleneck(p + ".m." + std::to_string(i), cur, dst, shortcut, 3, 3, 1.0);
+      cur = dst;
+    }
+    conv(p + ".cv3", cat, out, 1, 1, ACT_SILU);
+  }
+  void c3k2(const std::string& p, TRef x, TRef out, bool is_c3k, double e, bool shortcut) {
+    int c = (int)(out.C * e);
+    TRef cat = alloc(x.N, x.H, x.W, 3 * c);
+    conv(p + ".cv1", x, slice(cat, 0, 2 * c), 1, 1, ACT_SILU);
+    if (is_c3k) c3k(p + ".m.0", slice(cat, c, c), slice(cat, 2 * c, c), 2, shortcut);
+    else bottleneck(p + ".m.0", slice(cat, c, c), slice(cat, 2 * c, c), shortcut, 3, 3, 0.5);
+    conv(p + ".cv2", cat, out, 1, 1, ACT_SILU);
+  }
+  void ablock(const std::string& p, TRef x, TRef out, int area) {
+    const int dim = x.C, heads = dim / 32;
+    TRef qkv = alloc(x.N, x.H, x.W, 3 * dim);
+    conv(p + ".attn.qkv", x, qkv, 1, 1, ACT_NONE);
+    TRef xa = alloc(x.N, x.H, x.W, dim);
+    attention(qkv, xa, heads, area);
+    TRef xpe = alloc(x.N, x.H, x.W, dim);
+    dw(p + ".attn.pe", slice(qkv, 64, dim), xpe, 7, ACT_NONE, &xa, 32, 96);   // v channels: head*96 + 64 + d
+    TRef x1 = alloc(x.N, x.H, x.W, dim);
+    conv(p + ".attn.proj", xpe, x1, 1, 1, ACT_NONE, &x);
+    TRef hid = alloc(x.N, x.H, x.W, 2 * dim);
+    conv(p + ".mlp.0", x1, hid, 1, 1, ACT_SILU);
+    conv(p + ".mlp.1", hid, out, 1, 1, ACT_NONE, &x1);
+  }
+  void a2c2f(const std::string& p, TRef x, TRef out, int n, bool a2, int area) {
+    int c_ = (int)(out.C * 0.5);
+    TRef cat = alloc(x.N, x.H, x.W, (1 + n) * c_);
+    conv(p + ".cv1", x, slice(cat, 0, c_), 1, 1, ACT_SILU);
+    for (int i = 0; i < n; ++i) {
+      TRef src = slice(cat, i * c_, c_), dst = slice(cat, (i + 1) * c_, c_);
+      std::string m = p + ".m." + std::to_string(i);
+      if (a2) {
+        TRef tmp = alloc(x.N, x.H, x.W, c_);
+        ablock(m + ".0", src, tmp, area);
+        ablock(m + ".1", tmp, dst, area);
+      } else {
+        c3k(m, src, dst, 2, true);
+      }
+    }
+    conv(p + ".cv2", cat, out, 1, 1, ACT_SILU);
+  }
+  // GhostConv: y = Conv(c1, c_/2, 1); out = cat(y, DW5x5(y)); optional residual (GhostBottleneck identity shortcut)
+  void ghostconv(const std::string& p, TRef x, TRef out, int act, const TRef* res) {
+    int hc = out.C / 2;
+    if (!res) {
+      conv(p + ".cv1", x, slice(out, 0, hc), 1, 1, act);
+      dw(p + ".cv2", slice(out, 0, hc), slice(out, hc, hc), 5, act);
+    } else {
+      TRef y = alloc(x.N, x.H, x.W, hc);
+      conv(p + ".cv1", x, y, 1, 1, act);
+      TRef r0 = slice(*res, 0, hc), r1 = slice(*res, hc, hc);
+      dw(p + ".cv2", y, slice(out, hc, hc), 5, act, &r1);
+      ew(0, y, &r0, slice(out, 0, hc));
+    }
+  }
+  void c3ghost(const std::string& p, TRef x, TRef out) {
+    int c_ = (int)(out.C * 0.5);
+    TRef cat = alloc(x.N, x.H, x.W, 2 * c_);
+    TRef a = alloc(x.N, x.H, x.W, c_);
+    conv(p + ".cv1", x, a, 1, 1, ACT_SILU);
+    conv(p + ".cv2", x, slice(cat, c_, c_), 1, 1, ACT_SILU);
+    // GhostBottleneck(c_, c_), stride 1: GhostConv(c_, c_/2) -> Identity -> GhostConv(c_/2, c_, act=False); + x
+    TRef g1 = alloc(x.N, x.H, x.W, c_ / 2);
+    ghostconv(p + ".m.0.conv.0", a, g1, ACT_SILU, nullptr);
+    TRef dst = slice(cat, 0, c_);
+    ghostconv(p + ".m.0.conv.2", g1, dst, ACT_NONE, &a);
+    conv(p + ".cv3", cat, out, 1, 1, ACT_SILU);
+  }
+  // DoubleLightConv (YOLOSegPlusPlus.py:33-58) on an already-upsampled input
+  void doublelight(const std::string& p, TRef x, TRef out) {
+    TRef r = alloc(x.N, x.H, x.W, out.C);
+    conv(p + ".residual_conv", x, r, 1, 1, ACT_NONE);
+    TRef a = alloc(x.N, x.H, x.W, out.C);
+    conv(p + ".conv.0.conv1", x, a, 1, 1, ACT_NONE);
+    TRef b = alloc(x.N, x.H, x.W, out.C);
+    dw(p + ".conv.0.conv2", a, b, 3, ACT_SILU);
+    TRef c = alloc(x.N, x.H, x.W, out.C);
+    conv(p + ".conv.1.conv1", b, c, 1, 1, ACT_NONE);
+    dw(p + ".conv.1.conv2", c, out, 3, ACT_SILU, &r);
+  }
+};
+
+// pack buffers by lifetime (greedy first-fit over a timeline); keep_all => no reuse
+static void assign_offsets(Plan* plan, bool keep_all) {
+  struct Live { size_t off, bytes; int last; };
+  std::vector<int> order(plan->bufs.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return plan->bufs[a].first < plan->bufs[b].first; });
+  std::vector<Live> live;
+  size_t top = 0;
+  for (int id : order) {
+    BufInfo& b = plan->bufs[id];
+    if (b.last < 0) { b.off = 0; continue; }   // never used
+    if (!keep_all)
+      live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.last < b.first; }), live.end());
+    std::sort(live.begin(), live.end(), [](const Live& x, const Live& y) { return x.off < y.off; });
+    size_t off = 0;
+    for (const Live& l : live) {
+      if (off + b.bytes <= l.off) break;
+      off = std::max(off, l.off + l.bytes);
+    }
+    b.off = off;
+    live.push_back({off, b.bytes, b.last});
+    top = std::max(top, off + b.bytes);
+  }
+  plan->ws_bytes = top;
+}
+
+// ext slots
+enum { X_IMG = 0, X_Y = 1, X_P3 = 2, X_P4 = 3, X_P5 = 4, X_LOGITS = 5, X_OUT = 6, X_BOTT = 7, X_IMG_U8 = 8 };
+
+static void input_step(Builder& g, TRef x, int B, int H, int W) {
+  Plan* pl = g.plan; int dt = g.dt;
+  g.emit([=](RunCtx& c) {
+    if (c.ext[X_IMG_U8]) launch_u8_to_nhwc((const uint8_t*)c.ext[X_IMG_U8], pl->ptr(c, x), B, H, W, x.cs, dt, c.s);
+    else launch_nchw_to_nhwc((const float*)c.ext[X_IMG], pl->ptr(c, x), B, 4, H, W, x.cs, dt, c.s);
+  }, {&x});
+}
+
+// Detector: YOLOv12n, 4-ch, nc=1.  Input HxW is zero-padded (virtually) to S = ceil32.
+static int build_detector(ysp_handle* h, Plan* plan, int B, int H, int W) {
+  Builder g(h, plan, "det", 1e-3);
+  const int SH = (H + 31) / 32 * 32, SW = (W + 31) / 32 * 32;
+  auto dims = [&](int s, int& oh, int& ow) { oh = SH / s; ow = SW / s; };
+  int h2, w2, h4, w4, h8, w8, h16, w16, h32, w32;
+  dims(2, h2, w2); dims(4, h4, w4); dims(8, h8, w8); dims(16, h16, w16); dims(32, h32, w32);
+  TRef x = g.alloc(B, H, W, 4);
+  input_step(g, x, B, H, W);
+  // backbone
+  TRef t0 = g.alloc(B, h2, w2, 16);  g.conv("model.0", x, t0, 3, 2, ACT_SILU);              g.name("model.0", t0);
+  TRef t1 = g.alloc(B, h4, w4, 32);  g.conv("model.1", t0, t1, 3, 2, ACT_SILU);             g.name("model.1", t1);
+  TRef t2 = g.alloc(B, h4, w4, 64);  g.c3k2("model.2", t1, t2, false, 0.25, true);          g.name("model.2", t2);
+  TRef t3 = g.alloc(B, h8, w8, 64);  g.conv("model.3", t2, t3, 3, 2, ACT_SILU);             g.name("model.3", t3);
+  TRef cat13 = g.alloc(B, h8, w8, 256);        // [up(L11) 128 | L4 128]
+  TRef t4 = Builder::slice(cat13, 128, 128);   g.c3k2("model.4", t3, t4, false, 0.25, true);          g.name("model.4", t4);
+  TRef t5 = g.alloc(B, h16, w16, 128); g.conv("model.5", t4, t5, 3, 2, ACT_SILU);           g.name("model.5", t5);
+  TRef cat10 = g.alloc(B, h16, w16, 384);      // [up(L8) 256 | L6 128]
+  TRef t6 = Builder::slice(cat10, 256, 128);   g.a2c2f("model.6", t5, t6, 2, true, 4);      g.name("model.6", t6);
+  TRef t7 = g.alloc(B, h32, w32, 256); g.conv("model.7", t6, t7, 3, 2, ACT_SILU);           g.name("model.7", t7);
+  TRef cat19 = g.alloc(B, h32, w32, 384);      // [L18 128 | L8 256]
+  TRef t8 = Builder::slice(cat19, 128, 256);   g.a2c2f("model.8", t7, t8, 2, true, 1);      g.name("model.8", t8);
+  // neck
+  g.ew(1, t8, nullptr, Builder::slice(cat10, 0, 256));                                       // 9, 10
+  TRef cat16 = g.alloc(B, h16, w16, 192);      // [L15 64 | L11 128]
+  TRef t11 = Builder::slice(cat16, 64, 128);   g.a2c2f("model.11", cat10, t11, 1, false, -1); g.name("model.11", t11);
+  g.ew(1, t11, nullptr, Builder::slice(cat13, 0, 128));                                      // 12, 13
+  TRef t14 = g.alloc(B, h8, w8, 64);   g.a2c2f("model.14", cat13, t14, 1, false, -1);       g.name("model.14", t14);
+  g.conv("model.15", t14, Builder::slice(cat16, 0, 64), 3, 2, ACT_SILU);                     // 15, 16
+  TRef t17 = g.alloc(B, h16, w16, 128); g.a2c2f("model.17", cat16, t17, 1, false, -1);      g.name("model.17", t17);
+  g.conv("model.18", t17, Builder::slice(cat19, 0, 128), 3, 2, ACT_SILU);                    // 18, 19
+  TRef t20 = g.alloc(B, h32, w32, 256); g.c3k2("model.20", cat19, t20, true, 0.5, true);    g.name("model.20", t20);
+  // Detect (nc=1): raw maps NHWC fp32 [.., 65] (row stride 68)
+  TRef feats[3] = {t14, t17, t20};
+  TRef raws[3];
+  for (int i = 0; i < 3; ++i) {
+    TRef f = feats[i];
+    std::string s = std::to_string(i);
+    TRef raw = g.alloc(B, f.H, f.W, 65, DT_F32, 68);
+    raws[i] = raw;
+    TRef a = g.alloc(B, f.H, f.W, 64), b = g.alloc(B, f.H, f.W, 64);
+    g.conv("model.21.cv2." + s + ".0", f, a, 3, 1, ACT_SILU);
+    g.conv("model.21.cv2." + s + ".1", a, b, 3, 1, ACT_SILU);
+    g.conv("model.21.cv2." + s + ".2", b, Builder::slice(raw, 0, 64), 1, 1, ACT_NONE);
+    TRef d1 = g.alloc(B, f.H, f.W, f.C), p1 = g.alloc(B, f.H, f.W, 64), d2 = g.alloc(B, f.H, f.W, 64),
+         p2 = g.alloc(B, f.H, f.W, 64);
+    g.dw("model.21.cv3." + s + ".0.0", f, d1, 3, ACT_SILU);
+    g.conv("model.21.cv3." + s + ".0.1", d1, p1, 1, 1, ACT_SILU);
+    g.dw("model.21.cv3." + s + ".1.0", p1, d2, 3, ACT_SILU);
+    g.conv("model.21.cv3." + s + ".1.1", d2, p2, 1, 1, ACT_SILU);
+    g.conv("model.21.cv3." + s + ".2", p2, Builder::slice(raw, 64, 1), 1, 1, ACT_NONE);
+  }
+  if (g.rc) return g.rc;
+  DecodeP dp = {};
+  dp.B = B; dp.nc = 1; dp.cs = 68;
+  dp.A = 0;
+  for (int i = 0; i < 3; ++i) { dp.h[i] = raws[i].H; dp.w[i] = raws[i].W; dp.A += raws[i].H * raws[i].W; }
+  dp.stride[0] = 8.f; dp.stride[1] = 16.f; dp.stride[2] = 32.f;
+  dp.bh = H / 8; dp.bw = W / 8;
+  Plan* pl = plan;
+  TRef r0 = raws[0], r1 = raws[1], r2 = raws[2];
+  g.emit([=](RunCtx& c) {
+    DecodeP q = dp;
+    q.raw[0] = (const float*)pl->ptr(c, r0); q.raw[1] = (const float*)pl->ptr(c, r1); q.raw[2] = (const float*)pl->ptr(c, r2);
+    q.y = (float*)c.ext[X_Y]; q.p[0] = (float*)c.ext[X_P3]; q.p[1] = (float*)c.ext[X_P4]; q.p[2] = (float*)c.ext[X_P5];
+    q.bott = (float*)c.ext[X_BOTT];
+    launch_detect_decode(q, c.s);
+  }, {&r0, &r1, &r2});
+  assign_offsets(plan, h->keep_all);
+  return 0;
+}
+
+// YOLO-Seg++ head (YOLOSegPlusPlus.py:150-178, :242-272)
+static int build_seg(ysp_handle* h, Plan* plan, int B, int H, int W) {
+  Builder g(h, plan, "seg", 1e-5);
+  const int h2 = (H + 1) / 2, w2 = (W + 1) / 2, h4 = (h2 + 1) / 2, w4 = (w2 + 1) / 2, h8 = (h4 + 1) / 2, w8 = (w4 + 1) / 2;
+  TRef x = g.alloc(B, H, W, 4);
+  input_step(g, x, B, H, W);
+  // encoder = detector layers 0..4 (frozen, BN already folded; falls back to eps 1e-3 when it arrives unfused)
+  g.bn_eps = 1e-3;
+  TRef e0 = g.alloc(B, h2, w2, 16);  g.conv("encoder.0", x, e0, 3, 2, ACT_SILU);            g.name("encoder.0", e0);
+  TRef e1 = g.alloc(B, h4, w4, 32);  g.conv("encoder.1", e0, e1, 3, 2, ACT_SILU);           g.name("encoder.1", e1);
+  TRef cat2 = g.alloc(B, h4, w4, 128);          // dec2 input: [dec1 out 64 | skipA 64]
+  TRef skipA = Builder::slice(cat2, 64, 64);    g.c3k2("encoder.2", e1, skipA, false, 0.25, true);   g.name("encoder.2", skipA);
+  TRef e3 = g.alloc(B, h8, w8, 64);  g.conv("encoder.3", skipA, e3, 3, 2, ACT_SILU);        g.name("encoder.3", e3);
+  const int c0 = 129, c0s = g.dt == DT_F32 ? 132 : 144;
+  TRef cat0 = g.alloc(B, h8, w8, c0, -1, c0s);  // dec0 input: [skipB 128 | logits 1 | zero pad]
+  TRef skipB = Builder::slice(cat0, 0, 128);    g.c3k2("encoder.4", e3, skipB, false, 0.25, true);   g.name("encoder.4", skipB);
+  g.bn_eps = 1e-5;
+  {
+    TRef lg = Builder::slice(cat0, 128, 1);
+    Plan* pl = plan; int dt = g.dt; int zp = c0s - 129;
+    g.emit([=](RunCtx& c) {
+      launch_logits_to_nhwc((const float*)c.ext[X_LOGITS], pl->ptr(c, lg), B, h8, w8, lg.cs, zp, dt, c.s);
+    }, {&lg});
+  }
+  // decoder
+  TRef d0 = g.alloc(B, h8, w8, 96);
+  g.c3ghost("decoder.0.0", cat0, d0);
+  g.eca("decoder.0.1.conv.weight", d0);                                                       g.name("decoder.0", d0);
+  TRef u1 = g.alloc(B, h4, w4, 96);   g.ew(2, d0, nullptr, u1);
+  TRef d1 = Builder::slice(cat2, 0, 64);
+  g.doublelight("decoder.1.1", u1, d1);                                                       g.name("decoder.1", d1);
+  TRef d2 = g.alloc(B, h4, w4, 64);
+  g.c3ghost("decoder.2.0", cat2, d2);
+  g.eca("decoder.2.1.conv.weight", d2);                                                       g.name("decoder.2", d2);
+  TRef u3 = g.alloc(B, h2, w2, 64);   g.ew(2, d2, nullptr, u3);
+  TRef d3 = g.alloc(B, h2, w2, 32);   g.doublelight("decoder.3.1", u3, d3);                  g.name("decoder.3", d3);
+  TRef u4 = g.alloc(B, H, W, 32);     g.ew(2, d3, nullptr, u4);
+  TRef d4 = g.alloc(B, H, W, 16);     g.doublelight("decoder.4.1", u4, d4);                  g.name("decoder.4", d4);
+  TRef out = Builder::ext(X_OUT, B, H, W, 1, 1, DT_F32);
+  g.conv("output", d4, out, 1, 1, ACT_NONE);
+  if (g.rc) return g.rc;
+  assign_offsets(plan, h->keep_all);
+  return 0;
+}
+
+static int get_plan(ysp_handle* h, const char* kind, int B, int H, int W, Plan** out) {
+  char key[96];
+  snprintf(key, sizeof(key), "%s:%d:%d:%d:%d", kind, B, H, W, (int)h->keep_all);
+  auto it = h->plans.find(key);
+  if (it != h->plans.end()) { *out = it->second.get(); return 0; }
+  std::unique_ptr<Plan> p(new Plan());
+  int rc = (kind[0] == 'd') ? build_detector(h, p.get(), B, H, W) : build_seg(h, p.get(), B, H, W);
+  if (rc) return rc;
+  *out = p.get();
+  h->plans[key] = std::move(p);
+  return 0;
+}
+
+static int run_plan(ysp_handle* h, Plan* p, RunCtx& c) {
+  for (auto& f : p->steps) f(c);
+  h->last_plan = p;
+  h->last_launches += p->launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(YSP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static int check_device(ysp_handle* h) {
+  if (!h) return fail(YSP_EINVAL, "null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+extern "C" {
+
+int ysp_version(void) { return 100; }
+const char* ysp_last_error(void) { return g_err; }
+
+int ysp_create(ysp_handle** out, int device, int mode) {
+  if (!out || (mode != YSP_MODE_FP32 && mode != YSP_MODE_BF16)) return fail(YSP_EINVAL, "ysp_create: bad arguments");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail(YSP_ECUDA, "no CUDA device (%s); libysp has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(YSP_EINVAL, "device %d out of range (%d devices)", device, n);
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(YSP_ECUDA, "device %d is sm_%d%d; libysp is built for sm_100a only", device, prop.major, prop.minor);
+  ysp_handle* h = new ysp_handle();
+  h->device = device; h->mode = mode;
+  h->keep_all = getenv("YSP_KEEP_INTERMEDIATES") != nullptr;
+  *out = h;
+  return 0;
+}
+
+void ysp_destroy(ysp_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  h->plans.clear();
+  for (auto& kv : h->convs) { cudaFree(kv.second.w); cudaFree(kv.second.bias); if (kv.second.w_tc) cudaFree(kv.second.w_tc); }
+  for (auto& kv : h->vecs) cudaFree(kv.second);
+  delete h;
+}
+
+int ysp_set_keep_intermediates(ysp_handle* h, int on) {
+  if (!h) return fail(YSP_EINVAL, "null handle");
+  h->keep_all = on != 0;
+  return 0;
+}
+
+int ysp_load_weight(ysp_handle* h, const char* name, const float* h_data, int ndim, const int64_t* shape) {
+  if (!h || !name || !h_data || ndim < 0 || ndim > 8) return fail(YSP_EINVAL, "ysp_load_weight: bad arguments");
+  HostT t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.d.assign(h_data, h_data + n);
+  h->host[name] = std::move(t);
+  return 0;
+}
+
+int ysp_finalize(ysp_handle* h, int which) {
+  int rc = check_device(h);
+  if (rc) return rc;
+  // dry-run both graphs at a nominal shape: touches (packs + uploads) every weight the topology needs
+  if (which & 1) {
+    Plan p;
+    if ((rc = build_detector(h, &p, 1, 64, 64))) return rc;
+    h->det_ready = true;
+  }
+  if (which & 2) {
+    Plan p;
+    if ((rc = build_seg(h, &p, 1, 64, 64))) return rc;
+    h->seg_ready = true;
+  }
+  CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+
+size_t ysp_workspace_bytes(ysp_handle* h, int B, int H, int W) {
+  if (!h || B <= 0 || H <= 0 || W <= 0) return 0;
+  if (cudaSetDevice(h->device) != cudaSuccess) return 0;
+  size_t total = 0;
+  Plan* p = nullptr;
+  if (h->det_ready && get_plan(h, "det", B, H, W, &p) == 0) total += align_up(p->ws_bytes, 256);
+  if (h->seg_ready && (H % 8 == 0) && (W % 8 == 0) && get_plan(h, "seg", B, H, W, &p) == 0) total += align_up(p->ws_bytes, 256);
+  const int SH = (H + 31) / 32 * 32, SW = (W + 31) / 32 * 32;
+  const int A = (SH / 8) * (SW / 8) + (SH / 16) * (SW / 16) + (SH / 32) * (SW / 32);
+  total += align_up((size_t)B * 5 * A * 4, 256);                 // y when the caller does not want it
+  total += align_up((size_t)B * (H / 8) * (W / 8) * 4, 256);     // bottleneck logits
+  total += nms_workspace_bytes(B, 5, A, 300) + 256;
+  return total;
+}
+
+int ysp_normalize_u8(const uint8_t* d_u8, float* d_out, int B, int H, int W, void* stream) {
+  if (!d_u8 || !d_out || B < 0 || H <= 0 || W <= 0) return fail(YSP_EINVAL, "ysp_normalize_u8: bad arguments");
+  if (B == 0) return 0;
+  launch_normalize_u8(d_u8, d_out, B, H, W, (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int ysp_detector_forward(ysp_handle* h, const float* d_img, int B, int H, int W, float* d_y, float* d_p3, float* d_p4,
+                         float* d_p5, void* d_ws, size_t ws_bytes, void* stream) {
+  int rc = check_device(h);
+  if (rc) return rc;
+  if (!h->det_ready) return fail(YSP_ESTATE, "detector weights not finalized");
+  if (!d_img || B <= 0 || H <= 0 || W <= 0) return fail(YSP_EINVAL, "ysp_detector_forward: bad arguments");
+  Plan* p = nullptr;
+  if ((rc = get_plan(h, "det", B, H, W, &p))) return rc;
+  if (ws_bytes < p->ws_bytes || !d_ws) return fail(YSP_ESTATE, "workspace too small: need %zu bytes, got %zu", p->ws_bytes, ws_bytes);
+  RunCtx c = {};
+  c.ws = (char*)d_ws; c.s = (cudaStream_t)stream;
+  c.ext[X_IMG] = (void*)d_img; c.ext[X_Y] = d_y; c.ext[X_P3] = d_p3; c.ext[X_P4] = d_p4; c.ext[X_P5] = d_p5;
+  h->last_launches = 0;
+  return run_plan(h, p, c);
+}
+
+int ysp_bottleneck(const float* d_p3, int B, int C, int Hs, int Ws, float* d_logits, int hh, int ww, void* stream) {
+  if (!d_p3 || !d_logits || B < 0 || C <= 0 || hh > Hs || ww > Ws) return fail(YSP_EINVAL, "ysp_bottleneck: bad arguments");
+  if (B == 0) return 0;
+  launch_bottleneck(d_p3, B, C, Hs, Ws, d_logits, hh, ww, (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int ysp_segpp_forward(ysp_handle* h, const float* d_x, const float* d_logits, float* d_out, int B, int H, int W,
+                      void* d_ws, size_t ws_bytes, void* stream) {
+  int rc = check_device(h);
+  if (rc) return rc;
+  if (!h->seg_ready) return fail(YSP_ESTATE, "seg head weights not finalized");
+  if (!d_x || !d_logits || !d_out || B <= 0) return fail(YSP_EINVAL, "ysp_segpp_forward: bad arguments");
+  if (H % 8 || W % 8 || H <= 0 || W <= 0) return fail(YSP_EINVAL, "H and W must be positive multiples of 8 (got %dx%d)", H, W);
+  Plan* p = nullptr;
+  if ((rc = get_plan(h, "seg", B, H, W, &p))) return rc;
+  if (ws_bytes < p->ws_bytes || !d_ws) return fail(YSP_ESTATE, "workspace too small: need %zu bytes, got %zu", p->ws_bytes, ws_bytes);
+  RunCtx c = {};
+  c.ws = (char*)d_ws; c.s = (cudaStream_t)stream;
+  c.ext[X_IMG] = (void*)d_x; c.ext[X_LOGITS] = (void*)d_logits; c.ext[X_OUT] = d_out;
+  h->last_launches = 0;
+  return run_plan(h, p, c);
+}
+
+size_t ysp_nms_workspace_bytes(int B, int C, int A, int max_det) { return nms_workspace_bytes(B, C, A, max_det); }
+
+int ysp_nms(const float* d_pred, int B, int C, int A, int nc, float conf_thres, float iou_thres, int max_det,
+            int max_nms, float max_wh, int agnostic, const int32_t* d_classes, int n_classes, float* d_out_boxes,
+            int64_t* d_out_idx, int32_t* d_out_count, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!(conf_thres >= 0.f && conf_thres <= 1.f)) return fail(YSP_EINVAL, "Invalid Confidence threshold %g, valid values are between 0.0 and 1.0", conf_thres);
+  if (!(iou_thres >= 0.f && iou_thres <= 1.f)) return fail(YSP_EINVAL, "Invalid IoU %g, valid values are between 0.0 and 1.0", iou_thres);
+  if (nc <= 0) nc = C - 4;
+  if (B < 0 || A < 0 || C < 5 || nc < 1 || 4 + nc > C || max_det < 0 || max_nms < 0) return fail(YSP_EINVAL, "ysp_nms: bad shape B=%d C=%d A=%d nc=%d", B, C, A, nc);
+  if (B == 0) return 0;
+  if (!d_pred || !d_out_idx || !d_out_count || !d_out_boxes) return fail(YSP_EINVAL, "ysp_nms: null pointer");
+  if (max_det == 0 || A == 0) { CUDA_OK(cudaMemsetAsync(d_out_count, 0, 4 * (size_t)B, (cudaStream_t)stream)); return 0; }
+  int rc = launch_nms(d_pred, B, C, A, nc, conf_thres, iou_thres, max_det, max_nms, max_wh, agnostic, d_classes, n_classes,
+                      d_out_boxes, d_out_idx, d_out_count, d_ws, ws_bytes, (cudaStream_t)stream);
+  if (rc) return fail(YSP_ESTATE, "ysp_nms: workspace too small (need %zu bytes)", nms_workspace_bytes(B, C, A, max_det));
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int ysp_nms_core(const float* d_boxes, const float* d_scores, int N, float iou_thres, int64_t* d_keep, int32_t* d_count,
+                 void* d_ws, size_t ws_bytes, void* stream) {
+  if (N < 0 || !d_count) return fail(YSP_EINVAL, "ysp_nms_core: bad arguments");
+  int rc = launch_nms_core(d_boxes, d_scores, N, iou_thres, d_keep, d_count, d_ws, ws_bytes, (cudaStream_t)stream);
+  if (rc) return fail(YSP_ESTATE, "ysp_nms_core: workspace too small (need %zu bytes)", nms_workspace_bytes(1, 5, N, N));
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int ysp_xywh2xyxy_inplace(float* d_pred, int B, int C, int A, void* stream) {
+  if (!d_pred || C < 4) return fail(YSP_EINVAL, "ysp_xywh2xyxy_inplace: bad arguments");
+  launch_xywh2xyxy_inplace(d_pred, B, C, A, (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int ysp_mask_dice(const float* d_logits, const float* d_target, int B, int HW, int32_t* d_counts, uint8_t* d_mask,
+                  void* stream) {
+  if (!d_logits || !d_counts || B < 0 || HW < 0) return fail(YSP_EINVAL, "ysp_mask_dice: bad arguments");
+  if (B == 0) return 0;
+  launch_mask_dice(d_logits, d_target, B, HW, d_counts, d_mask, (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, void* d_ws, size_t ws_bytes,
+                 void* stream) {
+  int rc = check_device(h);
+  if (rc) return rc;
+  if (!h->det_ready || !h->seg_ready) return fail(YSP_ESTATE, "weights not finalized");
+  if (!io || B <= 0 || (!io->d_img && !io->d_img_u8) || !io->d_mask_logits || !io->d_det_boxes || !io->d_det_idx ||
+      !io->d_det_count || !io->d_counts)
+    return fail(YSP_EINVAL, "ysp_pipeline: bad arguments");
+  if (H % 8 || W % 8) return fail(YSP_EINVAL, "H and W must be multiples of 8 (got %dx%d)", H, W);
+  if (!(io->conf_thres >= 0.f && io->conf_thres <= 1.f) || !(io->iou_thres >= 0.f && io->iou_thres <= 1.f))
+    return fail(YSP_EINVAL, "invalid thresholds");
+  Plan *pd = nullptr, *ps = nullptr;
+  if ((rc = get_plan(h, "det", B, H, W, &pd))) return rc;
+  if ((rc = get_plan(h, "seg", B, H, W, &ps))) return rc;
+  const int SH = (H + 31) / 32 * 32, SW = (W + 31) / 32 * 32;
+  const int A = (SH / 8) * (SW / 8) + (SH / 16) * (SW / 16) + (SH / 32) * (SW / 32);
+  const int max_det = io->max_det > 0 ? io->max_det : 300;
+  // workspace carve-up: [det | seg] share one region? No: the seg head starts while nothing of det is live, but the
+  // y / bottleneck tensors cross the two plans, so they get their own slots after the larger of the two arenas.
+  size_t arena = std::max(align_up(pd->ws_bytes, 256), align_up(ps->ws_bytes, 256));
+  size_t off_y = arena;
+  size_t off_b = off_y + align_up((size_t)B * 5 * A * 4, 256);
+  size_t off_n = off_b + align_up((size_t)B * (H / 8) * (W / 8) * 4, 256);
+  size_t need = off_n + nms_workspace_bytes(B, 5, A, max_det);
+  if (!d_ws || ws_bytes < need) return fail(YSP_ESTATE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+  char* ws = (char*)d_ws;
+  float* y = io->d_y ? io->d_y : (float*)(ws + off_y);
+  float* bott = io->d_bottleneck ? io->d_bottleneck : (float*)(ws + off_b);
+  cudaStream_t s = (cudaStream_t)stream;
+  h->last_launches = 0;
+  RunCtx c = {};
+  c.ws = ws; c.s = s;
+  c.ext[X_IMG] = (void*)io->d_img; c.ext[X_IMG_U8] = (void*)io->d_img_u8; c.ext[X_Y] = y; c.ext[X_BOTT] = bott;
+  if ((rc = run_plan(h, pd, c))) return rc;                                             // evaluate_model.py:141-144
+  if (launch_nms(y, B, 5, A, 1, io->conf_thres, io->iou_thres, max_det, 30000, 7680.f, 0, nullptr, 0, io->d_det_boxes,
+                 io->d_det_idx, io->d_det_count, ws + off_n, ws_bytes - off_n, s))       // :147
+    return fail(YSP_ESTATE, "nms workspace");
+  h->last_launches += 2;
+  RunCtx c2 = {};
+  c2.ws = ws; c2.s = s;
+  c2.ext[X_IMG] = (void*)io->d_img; c2.ext[X_IMG_U8] = (void*)io->d_img_u8; c2.ext[X_LOGITS] = bott;
+  c2.ext[X_OUT] = io->d_mask_logits;
+  if ((rc = run_plan(h, ps, c2))) return rc;                                            // :156
+  launch_mask_dice(io->d_mask_logits, io->d_target, B, H * W, io->d_counts, io->d_mask, s);   // :157-174
+  h->last_launches += 1;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int ysp_last_launch_count(ysp_handle* h) { return h ? h->last_launches : 0; }
+
+int ysp_debug_tensor(ysp_handle* h, const char* name, void* d_ws, float* d_out, int64_t* shape, void* stream) {
+  if (!h || !name || !shape) return fail(YSP_EINVAL, "ysp_debug_tensor: bad arguments");
+  for (auto& kv : h->plans) {
+    Plan* p = kv.second.get();
+    if (p != h->last_plan) continue;
+    auto it = p->named.find(name);
+    if (it == p->named.end()) continue;
+    const TRef& t = it->second;
+    shape[0] = t.N; shape[1] = t.C; shape[2] = t.H; shape[3] = t.W;
+    if (d_out) {
+      RunCtx c = {}; c.ws = (char*)d_ws;
+      launch_nhwc_to_nchw_f32(p->ptr(c, t), d_out, t.N, t.H, t.W, t.C, t.cs, t.dt, (cudaStream_t)stream);
+      CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+  }
+  return fail(YSP_EINVAL, "no tensor named %s in the last plan", name);
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// kernels.h -- host-callable launchers (one per kernel family).  dtype: 0 = fp32 activations, 1 = bf16 activations.
+#pragma once
+#include "common.cuh"
+
+namespace ysp {
+
+enum { DT_F32 = 0, DT_BF16 = 1 };
+
+// kernels_simt.cu
+void launch_conv_dense(const ConvP& p, int in_dt, int out_dt, cudaStream_t s);
+void launch_conv_dw(const DwP& p, int dt, cudaStream_t s);
+void launch_add(const EwP& p, int dt, cudaStream_t s);                       // out = a + b
+void launch_up_nearest2(const EwP& p, int dt, cudaStream_t s);               // out[oy,ox] = a[oy/2,ox/2]
+void launch_up_bilinear2(const EwP& p, int dt, cudaStream_t s);              // torch bilinear x2, align_corners=False
+void launch_eca(void* x, int N, int HW, int C, int cs, const float* w3, float* mean_ws, int dt, cudaStream_t s);
+void launch_attention(const void* qkv, void* out, int B, int Ntok, int C, int heads, int area, int qkv_cs,
+                      int out_cs, int dt, cudaStream_t s);
+void launch_nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, int out_cs, int dt, cudaStream_t s);
+void launch_u8_to_nhwc(const uint8_t* in, void* out, int N, int H, int W, int out_cs, int dt, cudaStream_t s);
+void launch_normalize_u8(const uint8_t* in, float* out_nchw, int N, int H, int W, cudaStream_t s);
+// writes logits (fp32 [B,1,h,w]) into channel slice of an NHWC view and zero-fills `zero_pad` following channels
+void launch_logits_to_nhwc(const float* logits, void* out, int N, int h, int w, int out_cs, int zero_pad, int dt,
+                           cudaStream_t s);
+// raw head maps NHWC fp32 [B,hw,cs] x3 -> y [B,4+nc,A] + NCHW raw copies (nullable) + optional bottleneck logits
+struct DecodeP {
+  const float* raw[3]; int h[3], w[3]; int cs; int nc; int B; int A;
+  float stride[3];
+  float* y; float* p[3];
+  float* bott; int bh, bw;     // sigmoid(raw0[..., 64+nc-1]) cropped to bh x bw (fp32 [B,1,bh,bw]) or NULL
+};
+void launch_detect_decode(const DecodeP& p, cudaStream_t s);
+void launch_bottleneck(const float* p3, int B, int C, int Hs, int Ws, float* logits, int h, int w, cudaStream_t s);
+void launch_mask_dice(const float* logits, const float* target, int B, int HW, int32_t* counts, uint8_t* mask,
+                      cudaStream_t s);
+void launch_nhwc_to_nchw_f32(const void* in, float* out, int N, int H, int W, int C, int in_cs, int dt, cudaStream_t s);
+
+// nms.cu
+size_t nms_workspace_bytes(int B, int C, int A, int max_det);
+int launch_nms(const float* pred, int B, int C, int A, int nc, float conf, float iou, int max_det, int max_nms,
+               float max_wh, int agnostic, const int32_t* classes, int n_classes, float* out_boxes, int64_t* out_idx,
+               int32_t* out_count, void* ws, size_t ws_bytes, cudaStream_t s);
+int launch_nms_core(const float* boxes, const float* scores, int N, float iou, int64_t* keep, int32_t* count, void* ws,
+                    size_t ws_bytes, cudaStream_t s);
+void launch_xywh2xyxy_inplace(float* pred, int B, int C, int A, cudaStream_t s);
+
+// conv_tc.cu (tcgen05 + TMA implicit GEMM, bf16)
+struct TcConvPlan;   // opaque: tensor maps + tiling, built once per (layer, shape)
+TcConvPlan* tc_conv_plan_create(const ConvP& p, const void* w_bf16_kmajor, int out_dt);
+void tc_conv_plan_destroy(TcConvPlan*);
+void launch_conv_tc(const TcConvPlan* plan, const ConvP& p, cudaStream_t s);
+bool tc_conv_supported(const ConvP& p);
+
+}  // namespace ysp
