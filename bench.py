@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the YOLO-Seg++ inference hot path (BASELINE.json: "4-ch 240x240 slices/sec
+(fwd+NMS) at 1/2/4/8 B200; % of roofline").
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--batch 256] [--mode bf16]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (one rank per GPU)
+
+One "step" = one pass of the whole pipeline (detector@256-padded + NMS + seg head@240 + mask/Dice counters,
+evaluate_model.py:134-174) over one batch of B synthetic slices per GPU (BASELINE configs[1]: bf16, B=256, 1xB200).
+Slices are independent, so N GPUs run N shards with no data-path collective ("weak" scaling; the only collective is
+the 5-counter metric all-reduce, done once outside the step loop like the reference's aggregate at :177-187).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = host u8 buffers -> H2D -> pipeline -> D2H
+of detections + counters, through the Python API a user calls (Predictor.predict_raw).  `--impl reference` times the
+CPU restatement of the reference path (oracle/, the reference itself needs ultralytics+monai which are absent) on the
+host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 240
+METRIC = "slices_per_sec_fwd_nms"
+UNIT = "slices/s"
+GFLOP_PER_SLICE = 1.8608          # detector@256 1.0407 + seg@240 0.8201
+IO_BYTES_PER_SLICE = {"fp32_in": 4 * H * W * 4 + H * W * 4 + 5 * 1344 * 4}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_setup(seed=0):
+    """Oracle (CPU restatement of the reference graph + nms.py semantics) loaded with the SAME synthetic checkpoint."""
+    import torch
+    from oracle import nms as onms
+    from oracle.model import DetectionModel, Predictor as OPredictor, YOLOSegPlusPlus as OSeg, mask_counts, pipeline
+    from yolo_u_b200.synth import synth_state_dicts
+    det_sd, seg_sd = synth_state_dicts(seed)
+    det = DetectionModel().fuse().eval()
+    det.load_state_dict(det_sd)
+    pred = OPredictor(det)
+    seg = OSeg(pred).eval()
+    seg.load_state_dict(seg_sd)
+
+    def run(x, tg):
+        with torch.no_grad():
+            out, dets, keep, y, bott = pipeline(pred, seg, x, onms.non_max_suppression)
+            return mask_counts(out, tg)
+    return run
+
+
+def time_cpu(run, batch, seconds, min_iters=2):
+    import torch
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(batch, 4, H, W, generator=g)
+    tg = (torch.rand(batch, 1, H, W, generator=g) > 0.5).float()
+    run(x, tg)                                    # warm-up
+    t0, n = time.perf_counter(), 0
+    while True:
+        run(x, tg)
+        n += 1
+        dt = time.perf_counter() - t0
+        if n >= min_iters and dt >= seconds:
+            break
+    return n * batch / dt, n, dt
+
+
+def main_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    run = cpu_reference_setup()
+    g = torch.Generator().manual_seed(1)
+    cb = 4                                        # BASELINE configs[0]: batch 4 on CPU
+    per_step = 2                                  # batches of 4 per step -> bounded sample of the B=256 workload
+    x = torch.rand(cb, 4, H, W, generator=g)
+    tg = (torch.rand(cb, 1, H, W, generator=g) > 0.5).float()
+    for _ in range(max(args.warmup, 1)):
+        run(x, tg)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(per_step):
+            run(x, tg)
+    dt = time.perf_counter() - t0
+    val = args.steps * per_step * cb / dt
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "YOLO-Seg++ pipeline 4x240x240: detector@256pad + NMS(.25/.45) + seg head + mask/Dice",
+                       "batch_per_step": per_step * cb, "note": "CPU restatement of the reference graph (oracle/), host cores only"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps x {per_step * cb} slices (batches of {cb}), torch {torch.__version__} CPU fp32, os.cpu_count={os.cpu_count()}"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    import yolo_u_b200 as ysp
+    from yolo_u_b200.synth import calibrate, synth_state_dicts
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, Wm = args.batch, args.steps, args.warmup
+    peaks = load_peaks()
+
+    det_sd, seg_sd = synth_state_dicts(0)
+    det_sd, seg_sd = calibrate(det_sd, seg_sd, device=dev)
+    P = ysp.Predictor(det_sd, seg_sd, device=dev, mode=args.mode)
+    eng = P.engine
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    nbuf = 3                                      # 3 x 236 MB fp32 inputs: every step reads inputs that cannot be L2-resident
+    xs = [torch.rand(B, 4, H, W, generator=g).to(dev) for _ in range(nbuf)]
+    tg = (torch.rand(B, 1, H, W, generator=g) > 0.5).float().to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident throughput (`value`) ----------------------------------------------------------------------
+    for i in range(Wm):
+        P.predict_raw(xs[i % nbuf], tg)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launches_total
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        P.predict_raw(xs[i % nbuf], tg)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launches_total - l0
+    ms = max_over_ranks(ms)
+    value = world * B * K / (ms / 1e3)
+    counts = P._out["counts"].clone()
+
+    # ---- metric all-reduce (the only collective of the path), outside the step loop like evaluate_model.py:177-187 ----
+    met = ysp.SegMetrics()
+    met.update(counts)
+    met.reduce(device=dev)
+    dice = met.compute()["dice"]
+
+    # ---- end to end through the public API with HOST buffers ----------------------------------------------------------
+    hx = [torch.randint(0, 256, (B, H, W, 4), dtype=torch.uint8, generator=g).pin_memory() for _ in range(2)]
+    dx = [torch.empty(B, H, W, 4, dtype=torch.uint8, device=dev) for _ in range(2)]
+    o = P.predict_raw(dx[0], tg)
+    h_out = {k: torch.empty(o[k].shape, dtype=o[k].dtype).pin_memory() for k in ("counts", "det_count", "det_boxes", "det_idx")}
+    h2d = hx[0].numel()
+    d2h = sum(t.numel() * t.element_size() for t in h_out.values())
+
+    def e2e_step(i):
+        dx[i % 2].copy_(hx[i % 2], non_blocking=True)
+        out = P.predict_raw(dx[i % 2], tg)
+        for k, t in h_out.items():
+            t.copy_(out[k], non_blocking=True)
+
+    for i in range(Wm):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(K):
+        e2e_step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    e2e_val = world * B * K / (ms_e2e / 1e3)
+
+    # ---- per-kernel device times (extra pass, CUDA events around every launch inside libysp) -> roofline ----------------
+    roof, top = None, []
+    if rank == 0:
+        eng.profile(2)
+        nprof = 3
+        for i in range(nprof):
+            P.predict_raw(xs[i % nbuf], tg)
+        eng.profile(0)
+        rep = eng.profile_report()
+        kinds = {}
+        for r in rep:
+            a = kinds.setdefault(r["kind"], {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "launches": 0})
+            a["ms"] += r["ms"]; a["bytes"] += r["bytes"]; a["flops"] += r["flops"]; a["launches"] += r["launches"]
+        tot = sum(a["ms"] for a in kinds.values())
+        top = sorted(({"kernel": k, "share": a["ms"] / tot, "ms_per_step": a["ms"] / nprof,
+                       "GBps": a["bytes"] / a["ms"] / 1e6 if a["ms"] else 0, "TFLOPs": a["flops"] / a["ms"] / 1e9 if a["ms"] else 0}
+                      for k, a in kinds.items()), key=lambda d: -d["share"])[:8]
+        dom = max(rep, key=lambda r: r["ms"])                      # dominant single kernel (one layer's launches)
+        per_launch_ms = dom["ms"] / max(dom["launches"], 1)
+        bytes_per_launch = dom["bytes"] / max(dom["launches"], 1)
+        flops_per_launch = dom["flops"] / max(dom["launches"], 1)
+        intensity = flops_per_launch / max(bytes_per_launch, 1)
+        ridge = peaks["bf16_tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom["name"])
+        if intensity < ridge:
+            ach = bytes_per_launch / per_launch_ms / 1e6
+            roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic}
+        else:
+            ach = flops_per_launch / per_launch_ms / 1e9
+            roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": traffic}
+        roof.update({"kernel": dom["name"], "kind": dom["kind"], "us_per_launch": per_launch_ms * 1e3,
+                     "share_of_step": dom["ms"] / tot, "peak_source": peaks["src"],
+                     "pipeline_tensor_frac": value / world * GFLOP_PER_SLICE * 1e9 / (peaks["bf16_tflops_sustained"] * 1e12),
+                     "pipeline_hbm_frac_compulsory": value / world * IO_BYTES_PER_SLICE["fp32_in"] / (peaks["hbm_gbs"] * 1e9)})
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on the box's host cores, bounded sample ---------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        run = cpu_reference_setup()
+        v, n, dt = time_cpu(run, 4, args.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n} batches of 4 slices in {dt:.1f}s (oracle/ CPU restatement, torch CPU fp32, os.cpu_count={os.cpu_count()})"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.mode == "bf16" else "fp32", "data": "synthetic",
+                "config": {"workload": "YOLO-Seg++ pipeline 4x240x240: detector@256pad + NMS(.25/.45,max_det 300) + seg head + mask/Dice (BASELINE configs[1])",
+                           "batch_per_gpu": B, "global_batch": B * world, "H": H, "W": W, "parallelism": f"shard{world}",
+                           "l2": f"inputs larger than L2: {nbuf} rotating fp32 input buffers of {B * 4 * H * W * 4 / 1e6:.0f} MB",
+                           "weights": "random-init synthetic checkpoint (yolo_u_b200.synth, seed 0, calibrated heads)"},
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / K, "note": "pinned u8 HWC host input (a1 fused on device), D2H of padded detections + counters"},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "top_kernels": top, "mean_dice_vs_random_target": dice}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return main_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        import random
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(random.randint(20000, 40000)), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -124,6 +124,12 @@ int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, 
 int ysp_set_keep_intermediates(ysp_handle* h, int on);
 /* number of kernels the last ysp_* call on this handle launched */
 int ysp_last_launch_count(ysp_handle* h);
+/* per-step device timing: enable=1 start/continue, 2 = clear and start, 0 = stop.  While on, every plan step is
+ * bracketed by CUDA events on the launching stream and the call synchronises at its end (NOT for timed regions).
+ * ysp_profile_report writes a JSON array [{name,kind,ms,calls,launches,bytes,flops}] (bytes/flops = ALGORITHMIC
+ * per-step totals accumulated over calls) and returns its length, or <0. */
+int ysp_profile(ysp_handle* h, int enable);
+int ysp_profile_report(ysp_handle* h, char* buf, size_t cap);
 /* copy a named intermediate of the last plan run ("det:model.6", "seg:decoder.0", ...) to fp32 NCHW host-visible
  * device buffer; returns dims via shape[4] = N,C,H,W.  d_out may be NULL to query the shape only. */
 int ysp_debug_tensor(ysp_handle* h, const char* name, void* d_ws, float* d_out, int64_t* shape, void* stream);

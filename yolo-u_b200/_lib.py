@@ -42,6 +42,8 @@ PROTOTYPES = {
     "ysp_pipeline": (i32, [vp, C.POINTER(PipelineIO), i32, i32, i32, vp, sz, vp]),
     "ysp_last_launch_count": (i32, [vp]),
     "ysp_set_keep_intermediates": (i32, [vp, i32]),
+    "ysp_profile": (i32, [vp, i32]),
+    "ysp_profile_report": (i32, [vp, C.c_char_p, sz]),
     "ysp_debug_tensor": (i32, [vp, C.c_char_p, vp, vp, C.POINTER(i64), vp]),
 }
 

@@ -50,8 +50,12 @@ struct RunCtx { char* ws; void* ext[16]; cudaStream_t s; };
 static inline size_t esize(int dt) { return dt == DT_F32 ? 4 : 2; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+struct StepInfo { std::string name; std::string kind; double bytes = 0, flops = 0; int launches = 1; };
+struct ProfAgg { std::string kind; double ms = 0, bytes = 0, flops = 0; long calls = 0; long launches = 0; };
+
 struct Plan {
   std::vector<std::function<void(RunCtx&)>> steps;
+  std::vector<StepInfo> infos;
   std::vector<BufInfo> bufs;
   std::map<std::string, TRef> named;
   std::vector<TcConvPlan*> tc_plans;
@@ -76,6 +80,9 @@ struct ysp_handle {
   std::map<std::string, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   int last_launches = 0;
+  bool profiling = false;
+  std::map<std::string, ProfAgg> prof;
+  std::vector<cudaEvent_t> prof_events;
   std::string build_err;
   int act_dt() const { return mode == YSP_MODE_BF16 ? DT_BF16 : DT_F32; }
 };
@@ -209,10 +216,17 @@ struct Builder {
     int step = (int)plan->steps.size();
     b.first = std::min(b.first, step); b.last = std::max(b.last, step);
   }
-  void emit(std::function<void(RunCtx&)> f, std::initializer_list<const TRef*> uses, int nlaunch = 1) {
+  static double tbytes(const TRef& t) { return (double)t.N * t.H * t.W * t.C * esize(t.dt); }
+  void emit(std::function<void(RunCtx&)> f, std::initializer_list<const TRef*> uses, int nlaunch = 1,
+            StepInfo info = StepInfo()) {
     for (auto* t : uses) if (t) touch(*t);
     plan->steps.push_back(std::move(f));
     plan->launches += nlaunch;
+    info.launches = nlaunch;
+    if (info.name.empty()) info.name = "misc";
+    if (info.kind.empty()) info.kind = "misc";
+    info.name = ns + ":" + info.name;
+    plan->infos.push_back(info);
   }
 
   // dense conv (ultralytics Conv / nn.Conv2d); OH/OW default to 'same'/stride arithmetic on (padH, padW)
@@ -250,7 +264,10 @@ struct Builder {
       q.in = pl->ptr(c, in); q.out = pl->ptr(c, out); q.res = has_res ? pl->ptr(c, rres) : nullptr;
       if (tcp) launch_conv_tc(tcp, q, c.s);
       else launch_conv_dense(q, in_dt, out_dt, c.s);
-    }, {&in, &out, res});
+    }, {&in, &out, res}, 1,
+    StepInfo{prefix, std::string(tcp ? "tc_conv" : "conv") + std::to_string(k) + "x" + std::to_string(k) + (s == 2 ? "s2" : ""),
+             tbytes(in) + tbytes(out) + (res ? tbytes(*res) : 0.0) + (double)dc->K * dc->Cout * (tcp ? 2 : 4),
+             2.0 * p.M * (double)dc->K * dc->Cout, 1});
   }
 
   void dw(const std::string& prefix, TRef in, TRef out, int k, int act, const TRef* res = nullptr, int grp = 0,
@@ -273,7 +290,10 @@ struct Builder {
       DwP q = p;
       q.in = pl->ptr(c, in); q.out = pl->ptr(c, out); q.res = has_res ? pl->ptr(c, rres) : nullptr;
       launch_conv_dw(q, d, c.s);
-    }, {&in, &out, res});
+    }, {&in, &out, res}, 1,
+    StepInfo{prefix, "dwconv" + std::to_string(k) + "x" + std::to_string(k),
+             2.0 * tbytes(out) + (res ? tbytes(*res) : 0.0) + (double)k * k * out.C * 4,
+             2.0 * out.N * out.H * out.W * (double)out.C * k * k, 1});
   }
 
   void ew(int mode, TRef a, const TRef* b, TRef out) {
@@ -288,7 +308,9 @@ struct Builder {
       if (mode == 0) launch_add(q, d, c.s);
       else if (mode == 1) launch_up_nearest2(q, d, c.s);
       else launch_up_bilinear2(q, d, c.s);
-    }, {&a, b, &out});
+    }, {&a, b, &out}, 1,
+    StepInfo{mode == 0 ? "add" : (mode == 1 ? "up_nearest" : "up_bilinear"), mode == 0 ? "add" : (mode == 1 ? "up_nearest" : "up_bilinear"),
+             tbytes(a) + (b ? tbytes(*b) : 0.0) + tbytes(out), mode == 2 ? 8.0 * out.N * out.H * out.W * out.C : 0.0, 1});
   }
 
   void eca(const std::string& key, TRef x) {
@@ -299,7 +321,7 @@ struct Builder {
     Plan* pl = plan; int d = dt;
     emit([=](RunCtx& c) {
       launch_eca(pl->ptr(c, x), x.N, x.H * x.W, x.C, x.cs, w3, (float*)pl->ptr(c, mean), d, c.s);
-    }, {&x, &mean}, 2);
+    }, {&x, &mean}, 2, StepInfo{key, "eca", 3.0 * tbytes(x), 2.0 * x.N * x.H * x.W * x.C, 2});
   }
 
   void attention(TRef qkv, TRef out, int heads, int area) {
@@ -307,7 +329,9 @@ struct Builder {
     Plan* pl = plan; int d = dt;
     emit([=](RunCtx& c) {
       launch_attention(pl->ptr(c, qkv), pl->ptr(c, out), qkv.N, qkv.H * qkv.W, out.C, heads, area, qkv.cs, out.cs, d, c.s);
-    }, {&qkv, &out});
+    }, {&qkv, &out}, 1,
+    StepInfo{"attention", "attention", tbytes(qkv) + tbytes(out),
+             4.0 * qkv.N * (double)(qkv.H * qkv.W) * (qkv.H * qkv.W / (area > 0 ? area : 1)) * out.C, 1});
   }
 
   // ---- ultralytics blocks, concat-by-construction -------------------------------------------
@@ -446,7 +470,7 @@ static void input_step(Builder& g, TRef x, int B, int H, int W) {
   g.emit([=](RunCtx& c) {
     if (c.ext[X_IMG_U8]) launch_u8_to_nhwc((const uint8_t*)c.ext[X_IMG_U8], pl->ptr(c, x), B, H, W, x.cs, dt, c.s);
     else launch_nchw_to_nhwc((const float*)c.ext[X_IMG], pl->ptr(c, x), B, 4, H, W, x.cs, dt, c.s);
-  }, {&x});
+  }, {&x}, 1, StepInfo{"input", "input_layout", (double)B * H * W * 4 * 4 + Builder::tbytes(x), 0.0, 1});
 }
 
 // Detector: YOLOv12n, 4-ch, nc=1.  Input HxW is zero-padded (virtually) to S = ceil32.
@@ -516,7 +540,7 @@ static int build_detector(ysp_handle* h, Plan* plan, int B, int H, int W) {
     q.y = (float*)c.ext[X_Y]; q.p[0] = (float*)c.ext[X_P3]; q.p[1] = (float*)c.ext[X_P4]; q.p[2] = (float*)c.ext[X_P5];
     q.bott = (float*)c.ext[X_BOTT];
     launch_detect_decode(q, c.s);
-  }, {&r0, &r1, &r2});
+  }, {&r0, &r1, &r2}, 1, StepInfo{"detect_decode", "detect_decode", (double)B * dp.A * (65 * 4 * 2 + 5 * 4), (double)B * dp.A * 200.0, 1});
   assign_offsets(plan, h->keep_all);
   return 0;
 }
@@ -543,7 +567,7 @@ static int build_seg(ysp_handle* h, Plan* plan, int B, int H, int W) {
     Plan* pl = plan; int dt = g.dt; int zp = c0s - 129;
     g.emit([=](RunCtx& c) {
       launch_logits_to_nhwc((const float*)c.ext[X_LOGITS], pl->ptr(c, lg), B, h8, w8, lg.cs, zp, dt, c.s);
-    }, {&lg});
+    }, {&lg}, 1, StepInfo{"logits_in", "input_layout", (double)B * h8 * w8 * 8, 0.0, 1});
   }
   // decoder
   TRef d0 = g.alloc(B, h8, w8, 96);
@@ -579,8 +603,29 @@ static int get_plan(ysp_handle* h, const char* kind, int B, int H, int W, Plan**
   return 0;
 }
 
+static void prof_add(ysp_handle* h, const StepInfo& in, float ms) {
+  ProfAgg& a = h->prof[in.name + "|" + in.kind];
+  a.kind = in.kind; a.ms += ms; a.bytes += in.bytes; a.flops += in.flops; a.calls += 1; a.launches += in.launches;
+}
+
 static int run_plan(ysp_handle* h, Plan* p, RunCtx& c) {
-  for (auto& f : p->steps) f(c);
+  if (h->profiling) {
+    size_t need = 2 * p->steps.size();
+    while (h->prof_events.size() < need) { cudaEvent_t e; cudaEventCreate(&e); h->prof_events.push_back(e); }
+    for (size_t i = 0; i < p->steps.size(); ++i) {
+      cudaEventRecord(h->prof_events[2 * i], c.s);
+      p->steps[i](c);
+      cudaEventRecord(h->prof_events[2 * i + 1], c.s);
+    }
+    cudaStreamSynchronize(c.s);
+    for (size_t i = 0; i < p->steps.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]);
+      prof_add(h, p->infos[i], ms);
+    }
+  } else {
+    for (auto& f : p->steps) f(c);
+  }
   h->last_plan = p;
   h->last_launches += p->launches;
   cudaError_t e = cudaGetLastError();
@@ -805,22 +850,63 @@ int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, 
   c.ws = ws; c.s = s;
   c.ext[X_IMG] = (void*)io->d_img; c.ext[X_IMG_U8] = (void*)io->d_img_u8; c.ext[X_Y] = y; c.ext[X_BOTT] = bott;
   if ((rc = run_plan(h, pd, c))) return rc;                                             // evaluate_model.py:141-144
+  cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (h->profiling) { for (auto& e : pe) cudaEventCreate(&e); cudaEventRecord(pe[0], s); }
   if (launch_nms(y, B, 5, A, 1, io->conf_thres, io->iou_thres, max_det, 30000, 7680.f, 0, nullptr, 0, io->d_det_boxes,
                  io->d_det_idx, io->d_det_count, ws + off_n, ws_bytes - off_n, s))       // :147
     return fail(YSP_ESTATE, "nms workspace");
+  if (h->profiling) cudaEventRecord(pe[1], s);
   h->last_launches += 2;
   RunCtx c2 = {};
   c2.ws = ws; c2.s = s;
   c2.ext[X_IMG] = (void*)io->d_img; c2.ext[X_IMG_U8] = (void*)io->d_img_u8; c2.ext[X_LOGITS] = bott;
   c2.ext[X_OUT] = io->d_mask_logits;
   if ((rc = run_plan(h, ps, c2))) return rc;                                            // :156
+  if (h->profiling) cudaEventRecord(pe[2], s);
   launch_mask_dice(io->d_mask_logits, io->d_target, B, H * W, io->d_counts, io->d_mask, s);   // :157-174
   h->last_launches += 1;
+  if (h->profiling) {
+    cudaEventRecord(pe[3], s);
+    cudaStreamSynchronize(s);
+    float m0 = 0.f, m1 = 0.f;
+    cudaEventElapsedTime(&m0, pe[0], pe[1]);
+    cudaEventElapsedTime(&m1, pe[2], pe[3]);
+    StepInfo a{"pipe:nms", "nms", (double)B * A * 5 * 4 + (double)B * max_det * 32, 0.0, 2};
+    StepInfo b{"pipe:mask_dice", "mask_dice", (double)B * H * W * (io->d_target ? 8 : 4) + (io->d_mask ? (double)B * H * W : 0.0), 0.0, 1};
+    prof_add(h, a, m0); prof_add(h, b, m1);
+    for (auto& e : pe) cudaEventDestroy(e);
+  }
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int ysp_last_launch_count(ysp_handle* h) { return h ? h->last_launches : 0; }
+
+int ysp_profile(ysp_handle* h, int enable) {
+  if (!h) return fail(YSP_EINVAL, "null handle");
+  h->profiling = enable != 0;
+  if (enable == 2) h->prof.clear();
+  return 0;
+}
+
+int ysp_profile_report(ysp_handle* h, char* buf, size_t cap) {
+  if (!h || !buf || cap < 3) return fail(YSP_EINVAL, "ysp_profile_report: bad arguments");
+  std::string o = "[";
+  bool first = true;
+  for (auto& kv : h->prof) {
+    char line[512];
+    std::string nm = kv.first.substr(0, kv.first.find('|'));
+    snprintf(line, sizeof(line), "%s{\"name\":\"%s\",\"kind\":\"%s\",\"ms\":%.6f,\"calls\":%ld,\"launches\":%ld,\"bytes\":%.1f,\"flops\":%.1f}",
+             first ? "" : ",", nm.c_str(), kv.second.kind.c_str(), kv.second.ms, kv.second.calls, kv.second.launches,
+             kv.second.bytes, kv.second.flops);
+    o += line;
+    first = false;
+  }
+  o += "]";
+  if (o.size() + 1 > cap) return fail(YSP_EINVAL, "ysp_profile_report: buffer too small (need %zu)", o.size() + 1);
+  memcpy(buf, o.c_str(), o.size() + 1);
+  return (int)o.size();
+}
 
 int ysp_debug_tensor(ysp_handle* h, const char* name, void* d_ws, float* d_out, int64_t* shape, void* stream) {
   if (!h || !name || !shape) return fail(YSP_EINVAL, "ysp_debug_tensor: bad arguments");

@@ -165,6 +165,18 @@ class Engine:
         self._count()
         return o
 
+    def profile(self, enable: int):
+        """1 = on, 2 = clear + on, 0 = off (per-step CUDA-event timing inside libysp; not for timed regions)."""
+        check(lib().ysp_profile(self._h, int(enable)))
+
+    def profile_report(self):
+        import json
+        buf = C.create_string_buffer(1 << 20)
+        n = lib().ysp_profile_report(self._h, buf, len(buf))
+        if n < 0:
+            check(n)
+        return json.loads(buf.value.decode())
+
     def debug_tensor(self, name: str) -> torch.Tensor:
         shape = (C.c_int64 * 4)()
         ws = self._ws
