@@ -254,7 +254,8 @@ struct Builder {
     TcConvPlan* tcp = nullptr;
     if (h->mode == YSP_MODE_BF16 && dc->w_tc && in_dt == DT_BF16 && getenv("YSP_NO_TC") == nullptr) {
       ConvP q = p; q.K = dc->Ktc;
-      if (tc_conv_supported(q)) {
+      const char* only = getenv("YSP_TC_ONLY");       // debugging aid: tensor-core path only for matching layers
+      if ((!only || prefix.find(only) != std::string::npos) && tc_conv_supported(q)) {
         tcp = tc_conv_plan_create(q, dc->w_tc, out_dt);
         if (tcp) pl->tc_plans.push_back(tcp);
       }
