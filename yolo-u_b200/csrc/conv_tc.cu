@@ -10,9 +10,9 @@
 // * Both land in 128B/64B/32B-swizzled shared memory (swizzle = Kc*2 bytes) and are consumed by
 //   tcgen05.mma.cta_group::1.kind::f16 (M=128, N=N_tile, K=16) issued by one thread; accumulators are double-buffered
 //   in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-// * Epilogue (4 warps): tcgen05.ld 32x32b -> +bias (BN folded) -> SiLU -> +residual -> bf16/fp32 NHWC store, written
+// * Epilogue (8 warps): tcgen05.ld 32x32b -> +bias (BN folded) -> SiLU -> +residual -> bf16/fp32 NHWC store, written
 //   into a channel slice of the consumer's buffer (concat by construction).
-// * Persistent grid (<= #SMs CTAs), warp-specialised: warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps2-5 epilogue.
+// * Persistent grid (<= #SMs CTAs), warp-specialised: warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps2-9 epilogue.
 #include <cuda.h>
 
 #include <cstdio>
@@ -101,11 +101,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint
 
 constexpr int kMaxStages = 8;
 
-__global__ void __launch_bounds__(192, 1)
+constexpr int kTcThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue
+
+__global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[528];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
@@ -113,13 +116,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < 528; i += kTcThreads) s_bias[i] = i < p.Cout ? p.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -181,8 +185,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===== epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) =====
+    // ===== epilogue: 8 warps.  Warp w owns TMEM lanes [32q, 32q+32), q = w & 3 (hardware lane-quarter rule); the two
+    // warps sharing a quarter split the 16-column chunks of the tile between them (even / odd chunk index). =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -202,22 +208,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.N_tile);
-      for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
+      for (int c0 = half * 16; c0 < p.N_tile; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         tmem_ld_wait();
         const int cg = n_base + c0;               // first global output channel of this chunk
         if (valid && cg < p.Cout) {
-          const int nvalid = min(16, p.Cout - cg);
+          const int nvalid = p.Cout - cg;         // >= 16 means the whole chunk is real
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float x = __uint_as_float(v[j]) + (j < nvalid ? p.bias[cg + j] : 0.f);
-            f[j] = p.act == ACT_SILU ? x / (1.0f + __expf(-x)) : x;
+            float x = __uint_as_float(v[j]) + s_bias[cg + j];
+            f[j] = p.act == ACT_SILU ? __fdividef(x, 1.0f + __expf(-x)) : x;
           }
           if (p.res) {
             const bf16* rp = p.res + (size_t)pix * p.res_cs + cg;
-            if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+            if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
               uint4 r0 = *reinterpret_cast<const uint4*>(rp), r1 = *reinterpret_cast<const uint4*>(rp + 8);
               const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
               const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
@@ -227,21 +233,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 f[8 + 2 * j] += __low2float(h1[j]); f[8 + 2 * j + 1] += __high2float(h1[j]);
               }
             } else {
-              for (int j = 0; j < nvalid; ++j) f[j] += __bfloat162float(rp[j]);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (j < nvalid) f[j] += __bfloat162float(rp[j]);
             }
           }
           if (p.out_f32) {
             float* op = reinterpret_cast<float*>(p.out) + (size_t)pix * p.out_cs + cg;
-            if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+            if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 reinterpret_cast<float4*>(op)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             } else {
-              for (int j = 0; j < nvalid; ++j) op[j] = f[j];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (j < nvalid) op[j] = f[j];
             }
           } else {
             bf16* op = reinterpret_cast<bf16*>(p.out) + (size_t)pix * p.out_cs + cg;
-            if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+            if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
               uint32_t w[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -251,7 +259,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               reinterpret_cast<uint4*>(op)[0] = make_uint4(w[0], w[1], w[2], w[3]);
               reinterpret_cast<uint4*>(op)[1] = make_uint4(w[4], w[5], w[6], w[7]);
             } else {
-              for (int j = 0; j < nvalid; ++j) op[j] = __float2bfloat16_rn(f[j]);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (j < nvalid) op[j] = __float2bfloat16_rn(f[j]);
             }
           }
         }
@@ -402,7 +411,7 @@ void launch_conv_tc(const TcConvPlan* pl, const ConvP& c, cudaStream_t s) {
   if (pl->last_in != c.in && !encode_A(pl, c.in)) return;
   TcParams p = pl->p;
   p.res = reinterpret_cast<const bf16*>(c.res); p.out = c.out;
-  conv_tc_kernel<<<pl->grid, 192, pl->smem, s>>>(pl->tmA, pl->tmB, p);
+  conv_tc_kernel<<<pl->grid, kTcThreads, pl->smem, s>>>(pl->tmA, pl->tmB, p);
 }
 
 }  // namespace ysp

@@ -97,11 +97,12 @@ static const HostT* find(ysp_handle* h, const std::string& k) {
   return it == h->host.end() ? nullptr : &it->second;
 }
 
+// One conv with BN folded, still in PyTorch layout [Cout][Cin/g][kh][kw] (double-rounded to fp32 at upload).
+struct Folded { int Cout = 0, Cin = 0, kh = 0, kw = 0; bool dw = false; std::vector<double> w; std::vector<double> b; };
+
 // `prefix` names either an ultralytics Conv module (prefix.conv.weight [+ prefix.conv.bias] [+ prefix.bn.*]) or a
 // plain nn.Conv2d (prefix.weight, prefix.bias).  BN folded in double precision with the module's eps.
-static int pack_conv(ysp_handle* h, const std::string& prefix, double bn_eps, DevConv** out) {
-  auto it = h->convs.find(prefix);
-  if (it != h->convs.end()) { *out = &it->second; return 0; }
+static int fold_conv(ysp_handle* h, const std::string& prefix, double bn_eps, Folded& f) {
   const HostT* w = find(h, prefix + ".conv.weight");
   const HostT* b = nullptr;
   const HostT *g = nullptr, *be = nullptr, *mu = nullptr, *var = nullptr;
@@ -118,36 +119,56 @@ static int pack_conv(ysp_handle* h, const std::string& prefix, double bn_eps, De
   }
   if (!w) return fail(YSP_ENOWEIGHT, "missing weight %s(.conv).weight", prefix.c_str());
   if (w->shape.size() != 4) return fail(YSP_EINVAL, "%s: conv weight must be 4-d", prefix.c_str());
-  DevConv dc;
-  dc.Cout = (int)w->shape[0]; int cin_g = (int)w->shape[1]; dc.kh = (int)w->shape[2]; dc.kw = (int)w->shape[3];
-  dc.dw = (cin_g == 1 && dc.Cout > 1 && (dc.kh > 1));
-  // a [C,1,1,1] weight is ambiguous; 1x1 with Cin=1 does not occur on the path except as depthwise-free convs
-  std::vector<double> scale(dc.Cout, 1.0), shift(dc.Cout, 0.0);
-  for (int co = 0; co < dc.Cout; ++co) {
-    double bb = b ? b->d[co] : 0.0;
+  f.Cout = (int)w->shape[0]; f.Cin = (int)w->shape[1]; f.kh = (int)w->shape[2]; f.kw = (int)w->shape[3];
+  f.dw = (f.Cin == 1 && f.Cout > 1 && f.kh > 1);
+  const size_t per = (size_t)f.Cin * f.kh * f.kw;
+  f.w.resize((size_t)f.Cout * per); f.b.resize(f.Cout);
+  for (int co = 0; co < f.Cout; ++co) {
+    double bb = b ? b->d[co] : 0.0, sc = 1.0, sh = bb;
     if (g) {
-      double sc = (double)g->d[co] / std::sqrt((double)var->d[co] + bn_eps);
-      scale[co] = sc;
-      shift[co] = (double)be->d[co] + (bb - (double)mu->d[co]) * sc;
-    } else {
-      shift[co] = bb;
+      sc = (double)g->d[co] / std::sqrt((double)var->d[co] + bn_eps);
+      sh = (double)be->d[co] + (bb - (double)mu->d[co]) * sc;
     }
+    f.b[co] = sh;
+    for (size_t i = 0; i < per; ++i) f.w[co * per + i] = (double)w->d[co * per + i] * sc;
   }
+  return 0;
+}
+
+// Pack one conv, or several convs that read the same input concatenated along Cout (one GEMM instead of several).
+static int pack_conv_cat(ysp_handle* h, const std::string& key, const std::vector<std::string>& prefixes, double bn_eps,
+                         DevConv** out) {
+  auto it = h->convs.find(key);
+  if (it != h->convs.end()) { *out = &it->second; return 0; }
+  Folded f;
+  for (size_t i = 0; i < prefixes.size(); ++i) {
+    Folded g;
+    int rc = fold_conv(h, prefixes[i], bn_eps, g);
+    if (rc) return rc;
+    if (i == 0) { f = std::move(g); continue; }
+    if (g.Cin != f.Cin || g.kh != f.kh || g.kw != f.kw || g.dw || f.dw)
+      return fail(YSP_EINVAL, "cannot concatenate %s with %s", prefixes[i].c_str(), prefixes[0].c_str());
+    f.w.insert(f.w.end(), g.w.begin(), g.w.end());
+    f.b.insert(f.b.end(), g.b.begin(), g.b.end());
+    f.Cout += g.Cout;
+  }
+  DevConv dc;
+  dc.Cout = f.Cout; dc.kh = f.kh; dc.kw = f.kw; dc.dw = f.dw;
   std::vector<float> hw, hb(dc.Cout);
-  for (int co = 0; co < dc.Cout; ++co) hb[co] = (float)shift[co];
+  for (int co = 0; co < dc.Cout; ++co) hb[co] = (float)f.b[co];
   const int taps = dc.kh * dc.kw;
   if (dc.dw) {
     dc.Cin = dc.Cout; dc.K = taps; dc.wld = dc.Cout;
     hw.assign((size_t)taps * dc.Cout, 0.f);
     for (int c = 0; c < dc.Cout; ++c)
-      for (int t = 0; t < taps; ++t) hw[(size_t)t * dc.Cout + c] = (float)(w->d[(size_t)c * taps + t] * scale[c]);
+      for (int t = 0; t < taps; ++t) hw[(size_t)t * dc.Cout + c] = (float)f.w[(size_t)c * taps + t];
   } else {
-    dc.Cin = cin_g; dc.K = taps * dc.Cin; dc.wld = (dc.Cout + 3) / 4 * 4;
+    dc.Cin = f.Cin; dc.K = taps * dc.Cin; dc.wld = (dc.Cout + 3) / 4 * 4;
     hw.assign((size_t)dc.K * dc.wld, 0.f);
     for (int co = 0; co < dc.Cout; ++co)
       for (int ci = 0; ci < dc.Cin; ++ci)
         for (int t = 0; t < taps; ++t)
-          hw[(size_t)(t * dc.Cin + ci) * dc.wld + co] = (float)(w->d[((size_t)co * dc.Cin + ci) * taps + t] * scale[co]);
+          hw[(size_t)(t * dc.Cin + ci) * dc.wld + co] = (float)f.w[((size_t)co * dc.Cin + ci) * taps + t];
   }
   CUDA_OK(cudaMalloc(&dc.w, hw.size() * 4));
   CUDA_OK(cudaMemcpy(dc.w, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
@@ -162,7 +183,7 @@ static int pack_conv(ysp_handle* h, const std::string& prefix, double bn_eps, De
     for (int co = 0; co < dc.Cout; ++co)
       for (int ci = 0; ci < dc.Cin; ++ci)
         for (int t = 0; t < taps; ++t) {
-          float v = (float)(w->d[((size_t)co * dc.Cin + ci) * taps + t] * scale[co]);
+          float v = (float)f.w[((size_t)co * dc.Cin + ci) * taps + t];
           uint32_t u; memcpy(&u, &v, 4);
           uint32_t r = u + 0x7fffu + ((u >> 16) & 1u);          // round-to-nearest-even to bf16
           hbf[(size_t)co * dc.Ktc + (size_t)t * cin_pad + ci] = (uint16_t)(r >> 16);
@@ -170,9 +191,13 @@ static int pack_conv(ysp_handle* h, const std::string& prefix, double bn_eps, De
     CUDA_OK(cudaMalloc(&dc.w_tc, hbf.size() * 2));
     CUDA_OK(cudaMemcpy(dc.w_tc, hbf.data(), hbf.size() * 2, cudaMemcpyHostToDevice));
   }
-  auto res = h->convs.emplace(prefix, dc);
+  auto res = h->convs.emplace(key, dc);
   *out = &res.first->second;
   return 0;
+}
+
+static int pack_conv(ysp_handle* h, const std::string& prefix, double bn_eps, DevConv** out) {
+  return pack_conv_cat(h, prefix, {prefix}, bn_eps, out);
 }
 
 static int pack_vec(ysp_handle* h, const std::string& key, float** out) {
@@ -234,7 +259,13 @@ struct Builder {
             int padH = 0, int padW = 0) {
     if (rc) return;
     DevConv* dc = nullptr;
-    if ((rc = pack_conv(h, ns + "." + prefix, bn_eps, &dc))) return;
+    {   // "a+b" = convs a and b (same input) concatenated along Cout into one GEMM
+      std::vector<std::string> parts;
+      size_t st = 0, pos;
+      while ((pos = prefix.find('+', st)) != std::string::npos) { parts.push_back(ns + "." + prefix.substr(st, pos - st)); st = pos + 1; }
+      parts.push_back(ns + "." + prefix.substr(st));
+      if ((rc = pack_conv_cat(h, ns + "." + prefix, parts, bn_eps, &dc))) return;
+    }
     if (dc->dw || dc->Cin != in.C || dc->Cout != out.C || dc->kh != k) {
       rc = fail(YSP_EINVAL, "conv %s: weight [%d,%d,%d,%d] does not match in C=%d out C=%d k=%d", prefix.c_str(), dc->Cout,
                 dc->Cin, dc->kh, dc->kw, in.C, out.C, k);
@@ -423,6 +454,38 @@ struct Builder {
     ghostconv(p + ".m.0.conv.2", g1, dst, ACT_NONE, &a);
     conv(p + ".cv3", cat, out, 1, 1, ACT_SILU);
   }
+  // bilinear x2 + DoubleLightConv [+ output head] fused (kernels_fused.cu): the two 1x1 convs that read the upsampled
+  // tensor are linear, so they run at LOW resolution as one GEMM (P = [conv.0.conv1 | residual_conv]); one kernel does
+  // the rest per hi-res tile.  `out` is the hi-res NHWC result, or (head_prefix != "") the fp32 [N,1,2h,2w] logits.
+  void doublelight_fused(const std::string& p, TRef xlow, TRef out, const std::string& head_prefix) {
+    if (rc) return;
+    const int C = head_prefix.empty() ? out.C : 16;
+    TRef P = alloc(xlow.N, xlow.H, xlow.W, 2 * C);
+    conv(p + ".conv.0.conv1+" + p + ".residual_conv", xlow, P, 1, 1, ACT_NONE);
+    DevConv *d1 = nullptr, *c2 = nullptr, *d2 = nullptr, *hd = nullptr;
+    if ((rc = pack_conv(h, ns + "." + p + ".conv.0.conv2", bn_eps, &d1))) return;
+    if ((rc = pack_conv(h, ns + "." + p + ".conv.1.conv1", bn_eps, &c2))) return;
+    if ((rc = pack_conv(h, ns + "." + p + ".conv.1.conv2", bn_eps, &d2))) return;
+    if (!head_prefix.empty() && (rc = pack_conv(h, ns + "." + head_prefix, bn_eps, &hd))) return;
+    if (!d1->dw || !d2->dw || d1->Cout != C || d2->Cout != C || c2->Cin != C || c2->Cout != C || c2->kh != 1 || d1->kh != 3 ||
+        d2->kh != 3 || (hd && (hd->Cin != C || hd->Cout != 1))) {
+      rc = fail(YSP_EINVAL, "doublelight %s: unexpected weight shapes", p.c_str());
+      return;
+    }
+    DlcP q = {};
+    q.dw1 = d1->w; q.b1 = d1->bias; q.w2 = c2->w; q.b2 = c2->bias; q.w2ld = c2->wld; q.dw2 = d2->w; q.b3 = d2->bias;
+    q.wo = hd ? hd->w : nullptr; q.bo = hd ? hd->bias : nullptr; q.wo_ld = hd ? hd->wld : 0;
+    q.N = xlow.N; q.h = xlow.H; q.w = xlow.W; q.C = C; q.p_cs = P.cs; q.out_cs = out.cs;
+    Plan* pl = plan; int d = dt;
+    const double hi = (double)xlow.N * xlow.H * xlow.W * 4;
+    emit([=](RunCtx& c) {
+      DlcP r = q;
+      r.P = pl->ptr(c, P); r.out = pl->ptr(c, out);
+      launch_dlc_fused(r, d, c.s);
+    }, {&P, &out}, 1,
+    StepInfo{p + ".fused", "dlc_fused", tbytes(P) + (hd ? hi * 4 : tbytes(out)), 2.0 * hi * C * (9 + C + 9 + (hd ? 1 : 0)) + 16.0 * hi * C, 1});
+  }
+
   // DoubleLightConv (YOLOSegPlusPlus.py:33-58) on an already-upsampled input
   void doublelight(const std::string& p, TRef x, TRef out) {
     TRef r = alloc(x.N, x.H, x.W, out.C);
@@ -574,18 +637,26 @@ static int build_seg(ysp_handle* h, Plan* plan, int B, int H, int W) {
   TRef d0 = g.alloc(B, h8, w8, 96);
   g.c3ghost("decoder.0.0", cat0, d0);
   g.eca("decoder.0.1.conv.weight", d0);                                                       g.name("decoder.0", d0);
-  TRef u1 = g.alloc(B, h4, w4, 96);   g.ew(2, d0, nullptr, u1);
+  const bool fuse = getenv("YSP_NO_FUSE") == nullptr;
   TRef d1 = Builder::slice(cat2, 0, 64);
-  g.doublelight("decoder.1.1", u1, d1);                                                       g.name("decoder.1", d1);
+  if (fuse) g.doublelight_fused("decoder.1.1", d0, d1, "");
+  else { TRef u1 = g.alloc(B, h4, w4, 96); g.ew(2, d0, nullptr, u1); g.doublelight("decoder.1.1", u1, d1); }
+  g.name("decoder.1", d1);
   TRef d2 = g.alloc(B, h4, w4, 64);
   g.c3ghost("decoder.2.0", cat2, d2);
   g.eca("decoder.2.1.conv.weight", d2);                                                       g.name("decoder.2", d2);
-  TRef u3 = g.alloc(B, h2, w2, 64);   g.ew(2, d2, nullptr, u3);
-  TRef d3 = g.alloc(B, h2, w2, 32);   g.doublelight("decoder.3.1", u3, d3);                  g.name("decoder.3", d3);
-  TRef u4 = g.alloc(B, H, W, 32);     g.ew(2, d3, nullptr, u4);
-  TRef d4 = g.alloc(B, H, W, 16);     g.doublelight("decoder.4.1", u4, d4);                  g.name("decoder.4", d4);
+  TRef d3 = g.alloc(B, h2, w2, 32);
   TRef out = Builder::ext(X_OUT, B, H, W, 1, 1, DT_F32);
-  g.conv("output", d4, out, 1, 1, ACT_NONE);
+  if (fuse) {
+    g.doublelight_fused("decoder.3.1", d2, d3, "");                                           g.name("decoder.3", d3);
+    g.doublelight_fused("decoder.4.1", d3, out, "output");
+  } else {
+    TRef u3 = g.alloc(B, h2, w2, 64);   g.ew(2, d2, nullptr, u3);
+    g.doublelight("decoder.3.1", u3, d3);                                                     g.name("decoder.3", d3);
+    TRef u4 = g.alloc(B, H, W, 32);     g.ew(2, d3, nullptr, u4);
+    TRef d4 = g.alloc(B, H, W, 16);     g.doublelight("decoder.4.1", u4, d4);                g.name("decoder.4", d4);
+    g.conv("output", d4, out, 1, 1, ACT_NONE);
+  }
   if (g.rc) return g.rc;
   assign_offsets(plan, h->keep_all);
   return 0;

@@ -51,3 +51,17 @@ void launch_conv_tc(const TcConvPlan* plan, const ConvP& p, cudaStream_t s);
 bool tc_conv_supported(const ConvP& p);
 
 }  // namespace ysp
+
+namespace ysp {
+// kernels_fused.cu -- fused DoubleLightConv tail (everything after the two low-resolution 1x1 convs)
+struct DlcP {
+  const void* P;            // low-res NHWC [N, h, w, 2C] : [0,C) = conv.0.conv1 (BN folded, linear), [C,2C) = residual_conv
+  void* out;                // hi-res NHWC [N, 2h, 2w, C] (activation dtype) or, with head, fp32 [N, 2h, 2w]
+  const float *dw1, *b1;    // conv.0.conv2 depthwise 3x3 [9][C] + bias (SiLU)
+  const float *w2, *b2;     // conv.1.conv1 1x1 [K=C][C] + bias (linear)
+  const float *dw2, *b3;    // conv.1.conv2 depthwise 3x3 [9][C] + bias (SiLU)
+  const float *wo, *bo;     // optional head: 1x1 C -> 1 (+bias); NULL otherwise
+  int N, h, w, C, p_cs, out_cs, w2ld, wo_ld;
+};
+void launch_dlc_fused(const DlcP& p, int dt, cudaStream_t s);
+}  // namespace ysp
