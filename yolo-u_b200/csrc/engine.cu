@@ -216,6 +216,9 @@ static int pack_vec(ysp_handle* h, const std::string& key, float** out) {
 // ---------------------------------------------------------------------------------------------------------------------
 // graph builder
 // ---------------------------------------------------------------------------------------------------------------------
+// ext slots
+enum { X_IMG = 0, X_Y = 1, X_P3 = 2, X_P4 = 3, X_P5 = 4, X_LOGITS = 5, X_OUT = 6, X_BOTT = 7, X_IMG_U8 = 8 };
+
 struct Builder {
   ysp_handle* h; Plan* plan; int dt; std::string ns; double bn_eps; int rc = 0;
   Builder(ysp_handle* h_, Plan* p_, const std::string& ns_, double eps) : h(h_), plan(p_), dt(h_->act_dt()), ns(ns_), bn_eps(eps) {}
@@ -252,6 +255,20 @@ struct Builder {
     if (info.kind.empty()) info.kind = "misc";
     info.name = ns + ":" + info.name;
     plan->infos.push_back(info);
+  }
+
+  // 4-channel stem conv reading the caller's tensor directly (fp32 NCHW or u8 HWC4): kernels_stem_attn.cu
+  void stem(const std::string& prefix, TRef out, int B, int H, int W) {
+    if (rc) return;
+    DevConv* dc = nullptr;
+    if ((rc = pack_conv(h, ns + "." + prefix, bn_eps, &dc))) return;
+    if (dc->dw || dc->Cin != 4 || dc->Cout != 16 || dc->kh != 3) { rc = fail(YSP_EINVAL, "stem %s: expected a 3x3 4->16 conv", prefix.c_str()); return; }
+    Plan* pl = plan; int d = dt; const float* w = dc->w; const float* bias = dc->bias; int wld = dc->wld;
+    emit([=](RunCtx& c) {
+      const bool u8 = c.ext[X_IMG_U8] != nullptr;
+      launch_stem_conv(u8 ? c.ext[X_IMG_U8] : c.ext[X_IMG], u8, pl->ptr(c, out), w, bias, B, H, W, out.H, out.W, out.cs, wld, d, c.s);
+    }, {&out}, 1,
+    StepInfo{prefix, "stem_conv", (double)B * H * W * 16 + tbytes(out), 2.0 * B * out.H * out.W * 36.0 * 16.0, 1});
   }
 
   // dense conv (ultralytics Conv / nn.Conv2d); OH/OW default to 'same'/stride arithmetic on (padH, padW)
@@ -360,7 +377,11 @@ struct Builder {
     if (rc) return;
     Plan* pl = plan; int d = dt;
     emit([=](RunCtx& c) {
-      launch_attention(pl->ptr(c, qkv), pl->ptr(c, out), qkv.N, qkv.H * qkv.W, out.C, heads, area, qkv.cs, out.cs, d, c.s);
+      const int ntok = qkv.H * qkv.W, ar = area > 0 ? area : 1;
+      if (d == DT_BF16 && ntok % ar == 0 && ntok / ar == 64)
+        launch_attention64_bf16(pl->ptr(c, qkv), pl->ptr(c, out), qkv.N, ntok, heads, ar, qkv.cs, out.cs, c.s);
+      else
+        launch_attention(pl->ptr(c, qkv), pl->ptr(c, out), qkv.N, ntok, out.C, heads, ar, qkv.cs, out.cs, d, c.s);
     }, {&qkv, &out}, 1,
     StepInfo{"attention", "attention", tbytes(qkv) + tbytes(out),
              4.0 * qkv.N * (double)(qkv.H * qkv.W) * (qkv.H * qkv.W / (area > 0 ? area : 1)) * out.C, 1});
@@ -526,9 +547,6 @@ static void assign_offsets(Plan* plan, bool keep_all) {
   plan->ws_bytes = top;
 }
 
-// ext slots
-enum { X_IMG = 0, X_Y = 1, X_P3 = 2, X_P4 = 3, X_P5 = 4, X_LOGITS = 5, X_OUT = 6, X_BOTT = 7, X_IMG_U8 = 8 };
-
 static void input_step(Builder& g, TRef x, int B, int H, int W) {
   Plan* pl = g.plan; int dt = g.dt;
   g.emit([=](RunCtx& c) {
@@ -544,10 +562,8 @@ static int build_detector(ysp_handle* h, Plan* plan, int B, int H, int W) {
   auto dims = [&](int s, int& oh, int& ow) { oh = SH / s; ow = SW / s; };
   int h2, w2, h4, w4, h8, w8, h16, w16, h32, w32;
   dims(2, h2, w2); dims(4, h4, w4); dims(8, h8, w8); dims(16, h16, w16); dims(32, h32, w32);
-  TRef x = g.alloc(B, H, W, 4);
-  input_step(g, x, B, H, W);
   // backbone
-  TRef t0 = g.alloc(B, h2, w2, 16);  g.conv("model.0", x, t0, 3, 2, ACT_SILU);              g.name("model.0", t0);
+  TRef t0 = g.alloc(B, h2, w2, 16);  g.stem("model.0", t0, B, H, W);                        g.name("model.0", t0);
   TRef t1 = g.alloc(B, h4, w4, 32);  g.conv("model.1", t0, t1, 3, 2, ACT_SILU);             g.name("model.1", t1);
   TRef t2 = g.alloc(B, h4, w4, 64);  g.c3k2("model.2", t1, t2, false, 0.25, true);          g.name("model.2", t2);
   TRef t3 = g.alloc(B, h8, w8, 64);  g.conv("model.3", t2, t3, 3, 2, ACT_SILU);             g.name("model.3", t3);
@@ -613,11 +629,9 @@ static int build_detector(ysp_handle* h, Plan* plan, int B, int H, int W) {
 static int build_seg(ysp_handle* h, Plan* plan, int B, int H, int W) {
   Builder g(h, plan, "seg", 1e-5);
   const int h2 = (H + 1) / 2, w2 = (W + 1) / 2, h4 = (h2 + 1) / 2, w4 = (w2 + 1) / 2, h8 = (h4 + 1) / 2, w8 = (w4 + 1) / 2;
-  TRef x = g.alloc(B, H, W, 4);
-  input_step(g, x, B, H, W);
   // encoder = detector layers 0..4 (frozen, BN already folded; falls back to eps 1e-3 when it arrives unfused)
   g.bn_eps = 1e-3;
-  TRef e0 = g.alloc(B, h2, w2, 16);  g.conv("encoder.0", x, e0, 3, 2, ACT_SILU);            g.name("encoder.0", e0);
+  TRef e0 = g.alloc(B, h2, w2, 16);  g.stem("encoder.0", e0, B, H, W);                      g.name("encoder.0", e0);
   TRef e1 = g.alloc(B, h4, w4, 32);  g.conv("encoder.1", e0, e1, 3, 2, ACT_SILU);           g.name("encoder.1", e1);
   TRef cat2 = g.alloc(B, h4, w4, 128);          // dec2 input: [dec1 out 64 | skipA 64]
   TRef skipA = Builder::slice(cat2, 64, 64);    g.c3k2("encoder.2", e1, skipA, false, 0.25, true);   g.name("encoder.2", skipA);

@@ -34,6 +34,12 @@ void launch_mask_dice(const float* logits, const float* target, int B, int HW, i
                       cudaStream_t s);
 void launch_nhwc_to_nchw_f32(const void* in, float* out, int N, int H, int W, int C, int in_cs, int dt, cudaStream_t s);
 
+// kernels_stem_attn.cu
+void launch_stem_conv(const void* in, int in_u8, void* out, const float* w, const float* bias, int N, int H, int W, int OH,
+                      int OW, int out_cs, int wld, int dt, cudaStream_t s);
+void launch_attention64_bf16(const void* qkv, void* out, int B, int Ntok, int heads, int area, int qkv_cs, int out_cs,
+                             cudaStream_t s);
+
 // nms.cu
 size_t nms_workspace_bytes(int B, int C, int A, int max_det);
 int launch_nms(const float* pred, int B, int C, int A, int nc, float conf, float iou, int max_det, int max_nms,
