@@ -103,7 +103,7 @@ constexpr int kMaxStages = 8;
 
 constexpr int kTcThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
@@ -373,18 +373,20 @@ TcConvPlan* tc_conv_plan_create(const ConvP& c, const void* w_bf16, int out_dt) 
   p.a_bytes = (128u * p.Kc * 2u + 1023u) & ~1023u;
   p.b_bytes = ((uint32_t)p.N_tile * p.Kc * 2u + 1023u) & ~1023u;
   p.stage_bytes = p.a_bytes + p.b_bytes;
-  int st = (int)((200u * 1024u) / p.stage_bytes);
-  p.stages = st > kMaxStages ? kMaxStages : (st < 2 ? 2 : st);
   int cols = 32;
   while (cols < 2 * p.N_tile) cols <<= 1;
   p.tmem_cols = cols;
+  // two CTAs share an SM (TMEM <= 256 columns and <= ~105 KB smem each) unless the tile needs all 512 TMEM columns
+  int st = (int)(((cols <= 256 ? 104u : 200u) * 1024u) / p.stage_bytes);
+  p.stages = st > kMaxStages ? kMaxStages : (st < 2 ? 2 : st);
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=BF16, K-major both, N>>3 @17, M>>4 @24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.bias = c.bias; p.res_cs = c.res_cs; p.out_cs = c.out_cs; p.out_f32 = out_dt == DT_F32; p.act = c.act;
   pl->in_cs = c.in_cs; pl->H = c.H; pl->W = c.W; pl->NB = c.N;
   pl->smem = (size_t)p.stages * p.stage_bytes + 1024;
   const int total = p.n_tiles_m * p.n_tiles_n;
-  pl->grid = total < num_sms() ? total : num_sms();
+  const int ctas_per_sm = (p.tmem_cols <= 256 && pl->smem <= 110 * 1024) ? 2 : 1;
+  pl->grid = total < ctas_per_sm * num_sms() ? total : ctas_per_sm * num_sms();
   // weights: [cout_pad][Ktc] bf16
   {
     cuuint64_t dims[2] = {(cuuint64_t)p.ntaps * cin_pad, (cuuint64_t)cout_pad};

@@ -53,7 +53,7 @@ __device__ __forceinline__ void dw_strip(const float* src, int RW, int SC, const
 // FAST = bf16 "throughput mode": fast SiLU, pointwise conv on mma.sync bf16 tensor-core tiles (b and W2 rounded to
 // bf16, exactly what the unfused bf16 path stores); !FAST = fp32 parity mode: everything in fp32 FFMA.
 template <typename T, int C, int TH, int TW, int S2, int S4, bool FAST>
-__global__ void __launch_bounds__(256) dlc_fused_kernel(DlcP p) {
+__global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
   constexpr int C4 = C / 4;
   constexpr int PH = TH / 2 + 4, PW = TW / 2 + 4;      // low-res tile incl. halo
   constexpr int AH = TH + 4, AW = TW + 4;              // a: tile + 2
