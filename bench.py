@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 H = W = 240
 METRIC = "slices_per_sec_fwd_nms"
 UNIT = "slices/s"
+WORKLOAD = "YOLO-Seg++ pipeline 4x240x240: detector@256pad + NMS(.25/.45,max_det 300) + seg head + mask/Dice (BASELINE configs[1])"
 GFLOP_PER_SLICE = 1.8608          # detector@256 1.0407 + seg@240 0.8201
 IO_BYTES_PER_SLICE = {"fp32_in": 4 * H * W * 4 + H * W * 4 + 5 * 1344 * 4}
 
@@ -145,8 +146,9 @@ def main_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "YOLO-Seg++ pipeline 4x240x240: detector@256pad + NMS(.25/.45) + seg head + mask/Dice",
-                       "batch_per_step": per_step * cb, "note": "CPU restatement of the reference graph (oracle/), host cores only"},
+            "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus, "H": H, "W": W,
+                       "parallelism": f"shard{args.gpus}",
+                       "sample_per_step": per_step * cb, "note": "CPU restatement of the reference graph (oracle/) on the host cores; each step is a bounded sample of the workload"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{args.steps} steps x {per_step * cb} slices (batches of {cb}), torch {torch.__version__} CPU fp32, os.cpu_count={os.cpu_count()}"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -221,31 +223,33 @@ def main_ours(args):
     met.reduce(device=dev)
     dice = met.compute()["dice"]
 
-    # ---- end to end through the public API with HOST buffers ----------------------------------------------------------
+    # ---- end to end through the public API with HOST buffers (HostPipeline: double-buffered H2D / run / D2H streams) ------
     hx = [torch.randint(0, 256, (B, H, W, 4), dtype=torch.uint8, generator=g).pin_memory() for _ in range(2)]
-    dx = [torch.empty(B, H, W, 4, dtype=torch.uint8, device=dev) for _ in range(2)]
-    o = P.predict_raw(dx[0], tg)
-    h_out = {k: torch.empty(o[k].shape, dtype=o[k].dtype).pin_memory() for k in ("counts", "det_count", "det_boxes", "det_idx")}
-    h2d = hx[0].numel()
-    d2h = sum(t.numel() * t.element_size() for t in h_out.values())
-
-    def e2e_step(i):
-        dx[i % 2].copy_(hx[i % 2], non_blocking=True)
-        out = P.predict_raw(dx[i % 2], tg)
-        for k, t in h_out.items():
-            t.copy_(out[k], non_blocking=True)
-
+    htg = tg.cpu().pin_memory()
+    hp = ysp.HostPipeline(P, B, H, W)
     for i in range(Wm):
-        e2e_step(i)
+        hp.submit(hx[i % 2], htg)
+    hp.synchronize()
     barrier()
-    e0.record()
+    t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream(dev)
+    for st in (hp.s_in, hp.s_run, hp.s_out):
+        st.wait_stream(cur)
+    t_e0.record(cur)
+    for st in (hp.s_in, hp.s_run, hp.s_out):
+        st.wait_stream(cur)                      # every pipeline stream starts after the start event
     for i in range(K):
-        e2e_step(i)
-    e1.record()
+        slot = hp.submit(hx[i % 2], htg)
+    for st in (hp.s_in, hp.s_run, hp.s_out):
+        cur.wait_stream(st)                      # the end event waits for the last D2H
+    t_e1.record(cur)
     torch.cuda.synchronize()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    res = hp.results(slot)
+    assert int(res["counts"][:, 1].sum()) >= 0
+    ms_e2e = max_over_ranks(t_e0.elapsed_time(t_e1))
     barrier()
     e2e_val = world * B * K / (ms_e2e / 1e3)
+    h2d, d2h = hp.h2d_bytes, hp.d2h_bytes
 
     # ---- per-kernel device times (extra pass, CUDA events around every launch inside libysp) -> roofline ----------------
     roof, top = None, []
@@ -297,12 +301,12 @@ def main_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.mode == "bf16" else "fp32", "data": "synthetic",
-                "config": {"workload": "YOLO-Seg++ pipeline 4x240x240: detector@256pad + NMS(.25/.45,max_det 300) + seg head + mask/Dice (BASELINE configs[1])",
+                "config": {"workload": WORKLOAD,
                            "batch_per_gpu": B, "global_batch": B * world, "H": H, "W": W, "parallelism": f"shard{world}",
                            "l2": f"inputs larger than L2: {nbuf} rotating fp32 input buffers of {B * 4 * H * W * 4 / 1e6:.0f} MB",
                            "weights": "random-init synthetic checkpoint (yolo_u_b200.synth, seed 0, calibrated heads)"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / K, "note": "pinned u8 HWC host input (a1 fused on device), D2H of padded detections + counters"},
+                        "ms_per_step": ms_e2e / K, "note": "HostPipeline.submit: pinned u8 HWC host batch + fp32 target masks -> H2D -> ysp_pipeline -> D2H of padded detections + Dice counters, every step, double-buffered over 3 streams"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "top_kernels": top, "mean_dice_vs_random_target": dice}
         if cpu is not None:
             line["cpu_baseline"] = cpu

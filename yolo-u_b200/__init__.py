@@ -6,6 +6,6 @@ from .engine import Engine  # noqa: F401
 from .YOLOSegPlusPlus import YOLOSegPlusPlus, DoubleLightConv, ECA  # noqa: F401
 from .detector import B200Detector  # noqa: F401
 from .nms import non_max_suppression, TorchNMS  # noqa: F401
-from .predictor import Predictor, predict  # noqa: F401
+from .predictor import Predictor, HostPipeline, predict  # noqa: F401
 from .metrics import mask_counts, dice_from_counts, SegMetrics  # noqa: F401
 from .sharding import shard_volumes, shard_slices, batches  # noqa: F401

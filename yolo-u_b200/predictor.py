@@ -48,5 +48,72 @@ class Predictor:
         return o["mask_logits"], dets, keep, o["counts"]
 
 
+class HostPipeline:
+    """End-to-end driver for HOST batches: pinned u8 [B,H,W,4] slices in, padded detections + Dice counters out (host).
+
+    Double-buffered over three CUDA streams so the H2D copy of batch i+1 and the D2H read of batch i-1 overlap the
+    kernels of batch i (PCIe moves 59 MB per 256 slices; the step itself is ~10 ms).  `submit` is asynchronous;
+    `results(i)` returns the host tensors of slot i after `synchronize()` (or after the slot's event completed)."""
+
+    KEYS = ("counts", "det_count", "det_boxes", "det_idx")
+
+    def __init__(self, predictor: "Predictor", B: int, H: int, W: int, max_det: int = 300, conf_thres: float = 0.25,
+                 iou_thres: float = 0.45):
+        self.P, self.B, self.H, self.W = predictor, B, H, W
+        self.kw = dict(conf_thres=conf_thres, iou_thres=iou_thres, max_det=max_det)
+        dev = predictor.engine.device
+        self.dev = dev
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.d_img = [torch.empty(B, H, W, 4, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.d_tgt = [None, None]
+        self.d_out = [dict(), dict()]
+        self.h_out = [None, None]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_run = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.n = 0
+        self.h2d_bytes = B * H * W * 4
+        self.d2h_bytes = 0
+
+    def submit(self, h_img_u8: torch.Tensor, h_target: Optional[torch.Tensor] = None) -> int:
+        """h_img_u8: pinned uint8 [B,H,W,4]; h_target: optional pinned fp32 [B,1,H,W] ground-truth masks (both HOST).
+        Returns the slot (0/1) holding this batch's results."""
+        k = self.n % 2
+        self.n += 1
+        d_target = None
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_run[k])          # slot's previous compute has consumed d_img[k] / d_tgt[k]
+            self.d_img[k].copy_(h_img_u8, non_blocking=True)
+            if h_target is not None:
+                if self.d_tgt[k] is None:
+                    self.d_tgt[k] = torch.empty(h_target.shape, dtype=torch.float32, device=self.dev)
+                self.d_tgt[k].copy_(h_target, non_blocking=True)
+                d_target = self.d_tgt[k]
+            self.ev_in[k].record(self.s_in)
+        self.h2d_bytes = h_img_u8.numel() + (h_target.numel() * 4 if h_target is not None else 0)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(self.ev_in[k])
+            self.s_run.wait_event(self.ev_out[k])         # slot's previous results have left the device buffers
+            o = self.P.engine.pipeline(self.d_img[k], d_target, out=self.d_out[k], **self.kw)
+            self.ev_run[k].record(self.s_run)
+        if self.h_out[k] is None:
+            self.h_out[k] = {key: torch.empty(o[key].shape, dtype=o[key].dtype).pin_memory() for key in self.KEYS}
+            self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.h_out[k].values())
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_run[k])
+            for key in self.KEYS:
+                self.h_out[k][key].copy_(o[key], non_blocking=True)
+            self.ev_out[k].record(self.s_out)
+        return k
+
+    def results(self, slot: int):
+        self.ev_out[slot].synchronize()
+        return self.h_out[slot]
+
+    def synchronize(self):
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.synchronize()
+
+
 def predict(engine_or_predictor, img, **kw):
     return engine_or_predictor.predict(img, **kw)
