@@ -163,6 +163,10 @@ def main_ours(args):
     import yolo_u_b200 as ysp
     from yolo_u_b200.synth import calibrate, synth_state_dicts
 
+    # keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, ...) write to fd 1
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -310,7 +314,8 @@ def main_ours(args):
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "top_kernels": top, "mean_dice_vs_random_target": dice}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
