@@ -53,6 +53,8 @@ struct ConvP {
   int OH, OW, Cout, out_cs, res_cs;
   int kh, kw, stride, pad, act;
   int M, K, wld;            // M = N*OH*OW, K = kh*kw*Cin, weights [K][wld] fp32
+  int cout_store;           // >= Cout: channels [Cout, cout_store) are written as act(0) = 0 (zero channel padding)
+  int in_zpad;              // input view has zero-filled channels up to a multiple of 16 (tensor-core K padding)
 };
 
 struct DwP {

@@ -25,7 +25,7 @@ namespace ysp {
 struct TcParams {
   int kw, ntaps, stride, pad, kchunks, Kc, cin_pad;
   int TW, TH, TN, tiles_w, tiles_h, tiles_n, n_tiles_m, n_tiles_n, N_tile, flat;
-  int OH, OW, NB, Cout;
+  int OH, OW, NB, Cout, Cout_st;
   long long M;
   const float* bias; const bf16* res; void* out;
   int res_cs, out_cs, out_f32, act;
@@ -213,8 +213,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld16(taddr + c0, v);
         tmem_ld_wait();
         const int cg = n_base + c0;               // first global output channel of this chunk
-        if (valid && cg < p.Cout) {
-          const int nvalid = p.Cout - cg;         // >= 16 means the whole chunk is real
+        if (valid && cg < p.Cout_st) {
+          const int nvalid = p.Cout_st - cg;      // >= 16 means the whole chunk is stored (zero-padded channels included)
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -304,7 +304,7 @@ static int num_sms() {
 bool tc_conv_supported(const ConvP& p) {
   if (p.kh != p.kw || (p.kh != 1 && p.kh != 3) || (p.stride != 1 && p.stride != 2)) return false;
   const int cin_pad = (p.Cin + 15) / 16 * 16;
-  if (p.Cin % 16 != 0 && !(p.in_cs >= cin_pad && p.Cin > 64)) return false;   // padded-K only for the zero-padded concat buffer
+  if (p.Cin % 16 != 0 && !(p.in_zpad && p.in_cs >= cin_pad)) return false;   // padded K only over zero-filled channels
   if (p.in_cs % 8 != 0) return false;
   if (p.M < 128) return false;
   return get_encode() != nullptr;
@@ -342,7 +342,7 @@ TcConvPlan* tc_conv_plan_create(const ConvP& c, const void* w_bf16, int out_dt) 
   p.kw = c.kw; p.ntaps = c.kh * c.kw; p.stride = c.stride; p.pad = c.pad; p.cin_pad = cin_pad;
   p.Kc = cin_pad % 64 == 0 ? 64 : (cin_pad % 32 == 0 ? 32 : 16);
   p.kchunks = cin_pad / p.Kc;
-  p.OH = c.OH; p.OW = c.OW; p.NB = c.N; p.Cout = c.Cout; p.M = c.M;
+  p.OH = c.OH; p.OW = c.OW; p.NB = c.N; p.Cout = c.Cout; p.Cout_st = c.cout_store > c.Cout ? c.cout_store : c.Cout; p.M = c.M;
   p.n_tiles_n = (cout_pad + 255) / 256;
   p.N_tile = ((cout_pad + p.n_tiles_n - 1) / p.n_tiles_n + 15) / 16 * 16;
   p.flat = (c.kh == 1 && c.stride == 1 && c.OH == c.H && c.OW == c.W) ? 1 : 0;

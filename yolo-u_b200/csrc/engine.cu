@@ -43,8 +43,8 @@ struct DevConv {           // packed weights of one conv (BN folded)
   bool dw = false;
 };
 
-struct TRef { int buf = -1; int N = 0, H = 0, W = 0, C = 0, cs = 0, co = 0, dt = 0; };
-struct BufInfo { size_t bytes = 0, off = 0; int first = 1 << 30, last = -1; };
+struct TRef { int buf = -1; int N = 0, H = 0, W = 0, C = 0, cs = 0, co = 0, dt = 0; bool zpad = false; };
+struct BufInfo { size_t bytes = 0, off = 0; int first = 1 << 30, last = -1; std::vector<int> regions; };
 struct RunCtx { char* ws; void* ext[16]; cudaStream_t s; };
 
 static inline size_t esize(int dt) { return dt == DT_F32 ? 4 : 2; }
@@ -56,6 +56,9 @@ struct ProfAgg { std::string kind; double ms = 0, bytes = 0, flops = 0; long cal
 struct Plan {
   std::vector<std::function<void(RunCtx&)>> steps;
   std::vector<StepInfo> infos;
+  std::vector<int> lane, region;             // per step: stream lane (0 = caller's stream) and fork-join region (0 = none)
+  std::vector<std::pair<int, int>> region_span = {{0, 0}};   // [first step, last step] per region id
+  int split = -1;                            // seg plan: first step that needs the detector's bottleneck
   std::vector<BufInfo> bufs;
   std::map<std::string, TRef> named;
   std::vector<TcConvPlan*> tc_plans;
@@ -83,6 +86,9 @@ struct ysp_handle {
   bool profiling = false;
   std::map<std::string, ProfAgg> prof;
   std::vector<cudaEvent_t> prof_events;
+  std::vector<cudaStream_t> lanes;           // extra streams for independent branches (lane k -> lanes[k-1])
+  std::vector<cudaEvent_t> sync_events;      // fork/join events (timing disabled)
+  cudaStream_t aux = nullptr;                // pipeline: seg encoder / NMS run here, concurrently with the detector
   std::string build_err;
   int act_dt() const { return mode == YSP_MODE_BF16 ? DT_BF16 : DT_F32; }
 };
@@ -221,6 +227,11 @@ enum { X_IMG = 0, X_Y = 1, X_P3 = 2, X_P4 = 3, X_P5 = 4, X_LOGITS = 5, X_OUT = 6
 
 struct Builder {
   ysp_handle* h; Plan* plan; int dt; std::string ns; double bn_eps; int rc = 0;
+  int cur_lane = 0, cur_region = 0;
+  // independent branches: fork(); lane(k); ...; lane(j); ...; join();  -- steps in different lanes may run concurrently
+  void fork() { plan->region_span.push_back({(int)plan->steps.size(), (int)plan->steps.size()}); cur_region = (int)plan->region_span.size() - 1; }
+  void lane(int k) { cur_lane = k; }
+  void join() { cur_region = 0; cur_lane = 0; }
   Builder(ysp_handle* h_, Plan* p_, const std::string& ns_, double eps) : h(h_), plan(p_), dt(h_->act_dt()), ns(ns_), bn_eps(eps) {}
 
   TRef alloc(int N, int H, int W, int C, int dtype = -1, int cs = 0) {
@@ -243,12 +254,16 @@ struct Builder {
     BufInfo& b = plan->bufs[t.buf];
     int step = (int)plan->steps.size();
     b.first = std::min(b.first, step); b.last = std::max(b.last, step);
+    if (cur_region && (b.regions.empty() || b.regions.back() != cur_region)) b.regions.push_back(cur_region);
   }
   static double tbytes(const TRef& t) { return (double)t.N * t.H * t.W * t.C * esize(t.dt); }
   void emit(std::function<void(RunCtx&)> f, std::initializer_list<const TRef*> uses, int nlaunch = 1,
             StepInfo info = StepInfo()) {
     for (auto* t : uses) if (t) touch(*t);
     plan->steps.push_back(std::move(f));
+    plan->lane.push_back(cur_region ? cur_lane : 0);
+    plan->region.push_back(cur_region);
+    if (cur_region) plan->region_span[cur_region].second = (int)plan->steps.size() - 1;
     plan->launches += nlaunch;
     info.launches = nlaunch;
     if (info.name.empty()) info.name = "misc";
@@ -294,6 +309,8 @@ struct Builder {
     p.OH = out.H; p.OW = out.W; p.Cout = out.C; p.out_cs = out.cs; p.res_cs = res ? res->cs : 0;
     p.kh = k; p.kw = k; p.stride = s; p.pad = k / 2; p.act = act;
     p.M = out.N * out.H * out.W; p.K = dc->K; p.wld = dc->wld;
+    p.cout_store = out.zpad ? std::min((out.C + 15) / 16 * 16, out.cs) : out.C;
+    p.in_zpad = in.zpad ? 1 : 0;
     (void)padH; (void)padW;
     Plan* pl = plan;
     TRef rres = res ? *res : TRef();
@@ -391,6 +408,10 @@ struct Builder {
   void bottleneck(const std::string& p, TRef x, TRef out, bool shortcut, int k0, int k1, double e) {
     int c_ = (int)(out.C * e);
     TRef t = alloc(x.N, x.H, x.W, c_);
+    if (dt == DT_BF16 && c_ % 16 != 0) {       // zero-pad the hidden channels to 16 so cv2 is a tensor-core conv too
+      t = alloc(x.N, x.H, x.W, c_, -1, (c_ + 15) / 16 * 16);
+      t.zpad = true;
+    }
     conv(p + ".cv1", x, t, k0, 1, ACT_SILU);
     bool add = shortcut && x.C == out.C;
     conv(p + ".cv2", t, out, k1, 1, ACT_SILU, add ? &x : nullptr);
@@ -524,6 +545,9 @@ struct Builder {
 // pack buffers by lifetime (greedy first-fit over a timeline); keep_all => no reuse
 static void assign_offsets(Plan* plan, bool keep_all) {
   struct Live { size_t off, bytes; int last; };
+  // steps of a fork-join region may execute in any order: a buffer touched inside one is live for the whole region
+  for (auto& b : plan->bufs)
+    for (int r : b.regions) { b.first = std::min(b.first, plan->region_span[r].first); b.last = std::max(b.last, plan->region_span[r].second); }
   std::vector<int> order(plan->bufs.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
   std::sort(order.begin(), order.end(), [&](int a, int b) { return plan->bufs[a].first < plan->bufs[b].first; });
@@ -588,23 +612,27 @@ static int build_detector(ysp_handle* h, Plan* plan, int B, int H, int W) {
   // Detect (nc=1): raw maps NHWC fp32 [.., 65] (row stride 68)
   TRef feats[3] = {t14, t17, t20};
   TRef raws[3];
+  g.fork();                                   // 3 levels x (box branch, class branch) = 6 independent chains
   for (int i = 0; i < 3; ++i) {
     TRef f = feats[i];
     std::string s = std::to_string(i);
     TRef raw = g.alloc(B, f.H, f.W, 65, DT_F32, 68);
     raws[i] = raw;
     TRef a = g.alloc(B, f.H, f.W, 64), b = g.alloc(B, f.H, f.W, 64);
+    g.lane(2 * i);
     g.conv("model.21.cv2." + s + ".0", f, a, 3, 1, ACT_SILU);
     g.conv("model.21.cv2." + s + ".1", a, b, 3, 1, ACT_SILU);
     g.conv("model.21.cv2." + s + ".2", b, Builder::slice(raw, 0, 64), 1, 1, ACT_NONE);
     TRef d1 = g.alloc(B, f.H, f.W, f.C), p1 = g.alloc(B, f.H, f.W, 64), d2 = g.alloc(B, f.H, f.W, 64),
          p2 = g.alloc(B, f.H, f.W, 64);
+    g.lane(2 * i + 1);
     g.dw("model.21.cv3." + s + ".0.0", f, d1, 3, ACT_SILU);
     g.conv("model.21.cv3." + s + ".0.1", d1, p1, 1, 1, ACT_SILU);
     g.dw("model.21.cv3." + s + ".1.0", p1, d2, 3, ACT_SILU);
     g.conv("model.21.cv3." + s + ".1.1", d2, p2, 1, 1, ACT_SILU);
     g.conv("model.21.cv3." + s + ".2", p2, Builder::slice(raw, 64, 1), 1, 1, ACT_NONE);
   }
+  g.join();
   if (g.rc) return g.rc;
   DecodeP dp = {};
   dp.B = B; dp.nc = 1; dp.cs = 68;
@@ -638,8 +666,10 @@ static int build_seg(ysp_handle* h, Plan* plan, int B, int H, int W) {
   TRef e3 = g.alloc(B, h8, w8, 64);  g.conv("encoder.3", skipA, e3, 3, 2, ACT_SILU);        g.name("encoder.3", e3);
   const int c0 = 129, c0s = g.dt == DT_F32 ? 132 : 144;
   TRef cat0 = g.alloc(B, h8, w8, c0, -1, c0s);  // dec0 input: [skipB 128 | logits 1 | zero pad]
+  cat0.zpad = g.dt == DT_BF16;
   TRef skipB = Builder::slice(cat0, 0, 128);    g.c3k2("encoder.4", e3, skipB, false, 0.25, true);   g.name("encoder.4", skipB);
   g.bn_eps = 1e-5;
+  plan->split = (int)plan->steps.size();       // everything above is independent of the detector
   {
     TRef lg = Builder::slice(cat0, 128, 1);
     Plan* pl = plan; int dt = g.dt; int zp = c0s - 129;
@@ -694,26 +724,73 @@ static void prof_add(ysp_handle* h, const StepInfo& in, float ms) {
   a.kind = in.kind; a.ms += ms; a.bytes += in.bytes; a.flops += in.flops; a.calls += 1; a.launches += in.launches;
 }
 
-static int run_plan(ysp_handle* h, Plan* p, RunCtx& c) {
+static cudaEvent_t sync_event(ysp_handle* h, size_t i) {
+  while (h->sync_events.size() <= i) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); h->sync_events.push_back(e); }
+  return h->sync_events[i];
+}
+static cudaStream_t lane_stream(ysp_handle* h, int lane, cudaStream_t main) {
+  if (lane == 0) return main;
+  while ((int)h->lanes.size() < lane) { cudaStream_t s; cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); h->lanes.push_back(s); }
+  return h->lanes[lane - 1];
+}
+
+// Run steps [lo, hi) of a plan on c.s.  Fork-join regions spread their lanes over extra streams (event fork/join);
+// while profiling everything runs serially on c.s with an event pair around each step.
+static int run_plan(ysp_handle* h, Plan* p, RunCtx& c, int lo = 0, int hi = -1, size_t ev_base = 0) {
+  if (hi < 0) hi = (int)p->steps.size();
+  static const bool no_lanes = getenv("YSP_NO_LANES") != nullptr;
   if (h->profiling) {
     size_t need = 2 * p->steps.size();
     while (h->prof_events.size() < need) { cudaEvent_t e; cudaEventCreate(&e); h->prof_events.push_back(e); }
-    for (size_t i = 0; i < p->steps.size(); ++i) {
+    for (int i = lo; i < hi; ++i) {
       cudaEventRecord(h->prof_events[2 * i], c.s);
       p->steps[i](c);
       cudaEventRecord(h->prof_events[2 * i + 1], c.s);
     }
     cudaStreamSynchronize(c.s);
-    for (size_t i = 0; i < p->steps.size(); ++i) {
+    for (int i = lo; i < hi; ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]);
       prof_add(h, p->infos[i], ms);
     }
+  } else if (no_lanes) {
+    for (int i = lo; i < hi; ++i) p->steps[i](c);
   } else {
-    for (auto& f : p->steps) f(c);
+    const cudaStream_t main = c.s;
+    size_t ev = ev_base;
+    int cur = 0;
+    unsigned used = 0;                                     // lanes (bit k) used in the current region
+    auto join = [&]() {
+      for (int k = 1; k < 32; ++k)
+        if (used & (1u << k)) {
+          cudaEvent_t e = sync_event(h, ev++);
+          cudaEventRecord(e, lane_stream(h, k, main));
+          cudaStreamWaitEvent(main, e, 0);
+        }
+      used = 0;
+    };
+    for (int i = lo; i < hi; ++i) {
+      const int r = p->region[i];
+      if (r != cur) {
+        if (cur) join();
+        if (r) {
+          cudaEvent_t e = sync_event(h, ev++);
+          cudaEventRecord(e, main);
+          for (int j = p->region_span[r].first; j <= p->region_span[r].second; ++j) {
+            int k = p->lane[j];
+            if (k && !(used & (1u << k))) { cudaStreamWaitEvent(lane_stream(h, k, main), e, 0); used |= 1u << k; }
+          }
+        }
+        cur = r;
+      }
+      RunCtx cc = c;
+      cc.s = lane_stream(h, r ? p->lane[i] : 0, main);
+      p->steps[i](cc);
+    }
+    if (cur) join();
   }
   h->last_plan = p;
-  h->last_launches += p->launches;
+  for (int i = lo; i < hi; ++i) h->last_launches += p->infos[i].launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(YSP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
   return 0;
@@ -757,6 +834,10 @@ void ysp_destroy(ysp_handle* h) {
   h->plans.clear();
   for (auto& kv : h->convs) { cudaFree(kv.second.w); cudaFree(kv.second.bias); if (kv.second.w_tc) cudaFree(kv.second.w_tc); }
   for (auto& kv : h->vecs) cudaFree(kv.second);
+  for (auto st : h->lanes) cudaStreamDestroy(st);
+  if (h->aux) cudaStreamDestroy(h->aux);
+  for (auto e : h->sync_events) cudaEventDestroy(e);
+  for (auto e : h->prof_events) cudaEventDestroy(e);
   delete h;
 }
 
@@ -919,10 +1000,10 @@ int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, 
   const int SH = (H + 31) / 32 * 32, SW = (W + 31) / 32 * 32;
   const int A = (SH / 8) * (SW / 8) + (SH / 16) * (SW / 16) + (SH / 32) * (SW / 32);
   const int max_det = io->max_det > 0 ? io->max_det : 300;
-  // workspace carve-up: [det | seg] share one region? No: the seg head starts while nothing of det is live, but the
-  // y / bottleneck tensors cross the two plans, so they get their own slots after the larger of the two arenas.
-  size_t arena = std::max(align_up(pd->ws_bytes, 256), align_up(ps->ws_bytes, 256));
-  size_t off_y = arena;
+  // workspace carve-up: [det arena | seg arena | y | bottleneck | nms].  The two arenas are disjoint because the seg
+  // encoder (which does not depend on the detector) runs concurrently with the detector on an auxiliary stream.
+  const size_t det_b = align_up(pd->ws_bytes, 256), seg_b = align_up(ps->ws_bytes, 256);
+  size_t off_y = det_b + seg_b;
   size_t off_b = off_y + align_up((size_t)B * 5 * A * 4, 256);
   size_t off_n = off_b + align_up((size_t)B * (H / 8) * (W / 8) * 4, 256);
   size_t need = off_n + nms_workspace_bytes(B, 5, A, max_det);
@@ -932,25 +1013,44 @@ int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, 
   float* bott = io->d_bottleneck ? io->d_bottleneck : (float*)(ws + off_b);
   cudaStream_t s = (cudaStream_t)stream;
   h->last_launches = 0;
+  static const bool no_overlap = getenv("YSP_NO_OVERLAP") != nullptr;
+  const bool overlap = !h->profiling && !no_overlap && ps->split > 0;
+  if (overlap && !h->aux) CUDA_OK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+  cudaStream_t s2 = overlap ? h->aux : s;
+  enum { EV_FORK = 48, EV_ENC, EV_DET, EV_NMS };          // sync-event slots above those used inside the plans
   RunCtx c = {};
   c.ws = ws; c.s = s;
   c.ext[X_IMG] = (void*)io->d_img; c.ext[X_IMG_U8] = (void*)io->d_img_u8; c.ext[X_Y] = y; c.ext[X_BOTT] = bott;
+  RunCtx c2 = {};
+  c2.ws = ws + det_b; c2.s = s2;
+  c2.ext[X_IMG] = (void*)io->d_img; c2.ext[X_IMG_U8] = (void*)io->d_img_u8; c2.ext[X_LOGITS] = bott;
+  c2.ext[X_OUT] = io->d_mask_logits;
+  if (overlap) {
+    cudaEventRecord(sync_event(h, EV_FORK), s);
+    cudaStreamWaitEvent(s2, sync_event(h, EV_FORK), 0);
+    if ((rc = run_plan(h, ps, c2, 0, ps->split, 24))) return rc;                         // seg encoder on the aux stream
+    cudaEventRecord(sync_event(h, EV_ENC), s2);
+  }
   if ((rc = run_plan(h, pd, c))) return rc;                                             // evaluate_model.py:141-144
   cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
   if (h->profiling) { for (auto& e : pe) cudaEventCreate(&e); cudaEventRecord(pe[0], s); }
+  if (overlap) {                                                                         // NMS on aux, concurrent with the decoder
+    cudaEventRecord(sync_event(h, EV_DET), s);
+    cudaStreamWaitEvent(s2, sync_event(h, EV_DET), 0);
+  }
   if (launch_nms(y, B, 5, A, 1, io->conf_thres, io->iou_thres, max_det, 30000, 7680.f, 0, nullptr, 0, io->d_det_boxes,
-                 io->d_det_idx, io->d_det_count, ws + off_n, ws_bytes - off_n, s))       // :147
+                 io->d_det_idx, io->d_det_count, ws + off_n, ws_bytes - off_n, s2))      // :147
     return fail(YSP_ESTATE, "nms workspace");
+  if (overlap) cudaEventRecord(sync_event(h, EV_NMS), s2);
   if (h->profiling) cudaEventRecord(pe[1], s);
   h->last_launches += 2;
-  RunCtx c2 = {};
-  c2.ws = ws; c2.s = s;
-  c2.ext[X_IMG] = (void*)io->d_img; c2.ext[X_IMG_U8] = (void*)io->d_img_u8; c2.ext[X_LOGITS] = bott;
-  c2.ext[X_OUT] = io->d_mask_logits;
-  if ((rc = run_plan(h, ps, c2))) return rc;                                            // :156
+  c2.s = s;
+  if (overlap) cudaStreamWaitEvent(s, sync_event(h, EV_ENC), 0);
+  if ((rc = run_plan(h, ps, c2, overlap ? ps->split : 0, -1, 24))) return rc;           // :156
   if (h->profiling) cudaEventRecord(pe[2], s);
   launch_mask_dice(io->d_mask_logits, io->d_target, B, H * W, io->d_counts, io->d_mask, s);   // :157-174
   h->last_launches += 1;
+  if (overlap) cudaStreamWaitEvent(s, sync_event(h, EV_NMS), 0);
   if (h->profiling) {
     cudaEventRecord(pe[3], s);
     cudaStreamSynchronize(s);

@@ -96,7 +96,10 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_dense_kernel(ConvP
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int co = n0 + tx * TN + j;
-      if (co >= p.Cout) continue;
+      if (co >= p.Cout) {
+        if (co < p.cout_store) out[(size_t)m * p.out_cs + co] = from_f<TO>(0.f);   // zero channel padding
+        continue;
+      }
       float v = acc[i][j] + (p.bias ? p.bias[co] : 0.f);
       v = apply_act(v, p.act);
       if (res) v += to_f<TI>(res[(size_t)m * p.res_cs + co]);
@@ -107,14 +110,15 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_dense_kernel(ConvP
 
 template <typename TI, typename TO>
 static void conv_dense_dispatch(const ConvP& p, cudaStream_t s) {
-  if (p.Cout <= 16) {
-    dim3 g(cdiv(p.M, 128), cdiv(p.Cout, 16));
+  const int cs_ = p.cout_store > p.Cout ? p.cout_store : p.Cout;
+  if (cs_ <= 16) {
+    dim3 g(cdiv(p.M, 128), cdiv(cs_, 16));
     conv_dense_kernel<TI, TO, 128, 16, 4, 2><<<g, 256, 0, s>>>(p);
-  } else if (p.Cout <= 32) {
-    dim3 g(cdiv(p.M, 128), cdiv(p.Cout, 32));
+  } else if (cs_ <= 32) {
+    dim3 g(cdiv(p.M, 128), cdiv(cs_, 32));
     conv_dense_kernel<TI, TO, 128, 32, 4, 4><<<g, 256, 0, s>>>(p);
   } else {
-    dim3 g(cdiv(p.M, 64), cdiv(p.Cout, 64));
+    dim3 g(cdiv(p.M, 64), cdiv(cs_, 64));
     conv_dense_kernel<TI, TO, 64, 64, 4, 4><<<g, 256, 0, s>>>(p);
   }
 }
