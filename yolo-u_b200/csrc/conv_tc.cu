@@ -25,6 +25,7 @@ namespace ysp {
 struct TcParams {
   int kw, ntaps, stride, pad, kchunks, Kc, cin_pad;
   int TW, TH, TN, tiles_w, tiles_h, tiles_n, n_tiles_m, n_tiles_n, N_tile, flat;
+  int tw_shift, th_shift; unsigned magic_w, magic_h;   // row decode shifts; ceil(2^32 / tiles_{w,h}) for exact small divisions
   int OH, OW, NB, Cout, Cout_st;
   long long M;
   const float* bias; const bf16* res; void* out;
@@ -97,6 +98,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo, uint32_t layout_type) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)layout_type << 61);
+}
+
+// SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2: one MUFU (tanh.approx, rel. error ~2^-11, below bf16 resolution)
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
 }
 
 constexpr int kMaxStages = 8;
@@ -190,17 +199,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    // tile-invariant part of the row -> pixel map (TW, TH are powers of two)
+    const int tw = row & (p.TW - 1), r2 = row >> p.tw_shift;
+    const int th = r2 & (p.TH - 1), tn = r2 >> p.th_shift;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int tn_i = tile % p.n_tiles_n, tm = tile / p.n_tiles_n;
+      int tn_i = 0, tm = tile;
+      if (p.n_tiles_n > 1) { tn_i = tile % p.n_tiles_n; tm = tile / p.n_tiles_n; }
       long long pix; bool valid;
       if (p.flat) { pix = (long long)tm * 128 + row; valid = pix < p.M; }
       else {
-        int ti = tm % p.tiles_w, r = tm / p.tiles_w;
-        int tj = r % p.tiles_h, tk = r / p.tiles_h;
-        int tw = row % p.TW, r2 = row / p.TW;
-        int th = r2 % p.TH, tn = r2 / p.TH;
-        int ox = ti * p.TW + tw, oy = tj * p.TH + th, n = tk * p.TN + tn;
+        const int r = p.magic_w ? (int)__umulhi((unsigned)tm, p.magic_w) : tm;     // tm / tiles_w
+        const int ti = tm - r * p.tiles_w;
+        const int tk = p.magic_h ? (int)__umulhi((unsigned)r, p.magic_h) : r;       // r / tiles_h
+        const int tj = r - tk * p.tiles_h;
+        const int ox = ti * p.TW + tw, oy = tj * p.TH + th, n = tk * p.TN + tn;
         valid = ox < p.OW && oy < p.OH && n < p.NB;
         pix = ((long long)n * p.OH + oy) * p.OW + ox;
       }
@@ -219,7 +232,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float x = __uint_as_float(v[j]) + s_bias[cg + j];
-            f[j] = p.act == ACT_SILU ? __fdividef(x, 1.0f + __expf(-x)) : x;
+            f[j] = p.act == ACT_SILU ? silu_tanh(x) : x;
           }
           if (p.res) {
             const bf16* rp = p.res + (size_t)pix * p.res_cs + cg;
@@ -367,6 +380,10 @@ TcConvPlan* tc_conv_plan_create(const ConvP& c, const void* w_bf16, int out_dt) 
     p.tiles_w = (c.OW + bw - 1) / bw; p.tiles_h = (c.OH + bh - 1) / bh; p.tiles_n = (c.N + bn - 1) / bn;
     p.n_tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   }
+  p.tw_shift = 0; while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
+  p.th_shift = 0; while ((1 << p.th_shift) < p.TH) ++p.th_shift;
+  p.magic_w = p.tiles_w > 1 ? (unsigned)((0x100000000ull + p.tiles_w - 1) / p.tiles_w) : 0u;
+  p.magic_h = p.tiles_h > 1 ? (unsigned)((0x100000000ull + p.tiles_h - 1) / p.tiles_h) : 0u;
   pl->swizzle = p.Kc * 2;
   p.sbo = 8u * pl->swizzle;
   p.layout_type = pl->swizzle == 128 ? 2u : (pl->swizzle == 64 ? 4u : 6u);
