@@ -32,6 +32,7 @@ struct TcParams {
   int res_cs, out_cs, out_f32, act;
   uint32_t idesc, sbo, layout_type, a_bytes, b_bytes, stage_bytes;
   int stages, tmem_cols;
+  int w_resident; uint32_t w_bytes;          // weights kept in smem for the whole kernel (loaded once per CTA)
 };
 
 struct TcConvPlan {
@@ -115,7 +116,7 @@ constexpr int kTcThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue
 __global__ void __launch_bounds__(kTcThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2], wfull_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_bias[528];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -126,6 +127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    mbar_init(&wfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -139,10 +141,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = tmem_base_s;
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
   const int kiters = p.ntaps * p.kchunks;
+  uint8_t* const wsm = smem;                          // resident weights: [n_tiles_n][tap][kchunk] tiles of b_bytes
+  uint8_t* const ring = smem + p.w_bytes;             // A (+B when streaming) stage ring
 
   if (warp == 0) {
     // ===== TMA producer (one lane) =====
     if (lane == 0) {
+      if (p.w_resident) {
+        // every CTA used to re-fetch the same few-KB weight tile from the same L2 lines on every k-iteration (an L2
+        // hot spot that cost up to half the kernel); now the whole packed weight matrix is loaded once per CTA.
+        mbar_expect_tx(&wfull_bar, (uint32_t)(p.n_tiles_n * kiters) * (uint32_t)p.N_tile * p.Kc * 2u);
+        for (int t = 0; t < p.n_tiles_n; ++t)
+          for (int it = 0; it < kiters; ++it)
+            tma_load_2d(wsm + (size_t)(t * kiters + it) * p.b_bytes, &tmB, &wfull_bar, (it / p.kchunks) * p.cin_pad + (it % p.kchunks) * p.Kc,
+                        t * p.N_tile);
+      }
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int tn_i = tile % p.n_tiles_n, tm = tile / p.n_tiles_n;
@@ -157,11 +170,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int tr = tap / p.kw, ts = tap - tr * p.kw;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-            uint8_t* sb = sa + p.a_bytes;
-            mbar_expect_tx(&full_bar[stage], 128u * p.Kc * 2u + (uint32_t)p.N_tile * p.Kc * 2u);
-            tma_load_4d(sa, &tmA, &full_bar[stage], kc * p.Kc, cw + ts, ch + tr, cn);
-            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.cin_pad + kc * p.Kc, tn_i * p.N_tile);
+            uint8_t* sa = ring + (size_t)stage * p.stage_bytes;
+            if (p.w_resident) {
+              mbar_expect_tx(&full_bar[stage], 128u * p.Kc * 2u);
+              tma_load_4d(sa, &tmA, &full_bar[stage], kc * p.Kc, cw + ts, ch + tr, cn);
+            } else {
+              mbar_expect_tx(&full_bar[stage], 128u * p.Kc * 2u + (uint32_t)p.N_tile * p.Kc * 2u);
+              tma_load_4d(sa, &tmA, &full_bar[stage], kc * p.Kc, cw + ts, ch + tr, cn);
+              tma_load_2d(sa + p.a_bytes, &tmB, &full_bar[stage], tap * p.cin_pad + kc * p.Kc, tn_i * p.N_tile);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -171,15 +188,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== MMA issuer (one lane) =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      if (p.w_resident) mbar_wait(&wfull_bar, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tn_i = tile % p.n_tiles_n;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.N_tile);
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sb = sa + p.a_bytes;
+          const uint32_t sa = smem_u32(ring + (size_t)stage * p.stage_bytes);
+          const uint32_t sb = p.w_resident ? smem_u32(wsm + (size_t)(tn_i * kiters + it) * p.b_bytes) : sa + p.a_bytes;
           const int nk = p.Kc >> 4;
           for (int k = 0; k < nk; ++k) {
             uint64_t ad = make_desc(sa + k * 32, p.sbo, p.layout_type);
@@ -389,18 +408,24 @@ TcConvPlan* tc_conv_plan_create(const ConvP& c, const void* w_bf16, int out_dt) 
   p.layout_type = pl->swizzle == 128 ? 2u : (pl->swizzle == 64 ? 4u : 6u);
   p.a_bytes = (128u * p.Kc * 2u + 1023u) & ~1023u;
   p.b_bytes = ((uint32_t)p.N_tile * p.Kc * 2u + 1023u) & ~1023u;
-  p.stage_bytes = p.a_bytes + p.b_bytes;
   int cols = 32;
   while (cols < 2 * p.N_tile) cols <<= 1;
   p.tmem_cols = cols;
-  // two CTAs share an SM (TMEM <= 256 columns and <= ~105 KB smem each) unless the tile needs all 512 TMEM columns
-  int st = (int)(((cols <= 256 ? 104u : 200u) * 1024u) / p.stage_bytes);
+  // weights stay resident in smem when the whole packed matrix is small (true for all but the widest 3x3 layers)
+  const uint32_t w_all = (uint32_t)(p.n_tiles_n * p.ntaps * p.kchunks) * p.b_bytes;
+  p.w_resident = w_all <= 80u * 1024u ? 1 : 0;
+  p.w_bytes = p.w_resident ? w_all : 0u;
+  p.stage_bytes = p.w_resident ? p.a_bytes : p.a_bytes + p.b_bytes;
+  // two CTAs share an SM (TMEM <= 256 columns and <= ~105 KB smem each) when at least 3 stages fit next to the weights
+  uint32_t budget = 104u * 1024u;
+  if (cols > 256 || p.w_bytes + 3u * p.stage_bytes > budget) budget = 200u * 1024u;
+  int st = (int)((budget - p.w_bytes) / p.stage_bytes);
   p.stages = st > kMaxStages ? kMaxStages : (st < 2 ? 2 : st);
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=BF16, K-major both, N>>3 @17, M>>4 @24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.bias = c.bias; p.res_cs = c.res_cs; p.out_cs = c.out_cs; p.out_f32 = out_dt == DT_F32; p.act = c.act;
   pl->in_cs = c.in_cs; pl->H = c.H; pl->W = c.W; pl->NB = c.N;
-  pl->smem = (size_t)p.stages * p.stage_bytes + 1024;
+  pl->smem = (size_t)p.w_bytes + (size_t)p.stages * p.stage_bytes + 1024;
   const int total = p.n_tiles_m * p.n_tiles_n;
   const int ctas_per_sm = (p.tmem_cols <= 256 && pl->smem <= 110 * 1024) ? 2 : 1;
   pl->grid = total < ctas_per_sm * num_sms() ? total : ctas_per_sm * num_sms();
