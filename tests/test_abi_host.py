@@ -97,3 +97,18 @@ def test_dice_and_metrics_match_oracle():
     assert (r["TP"], r["FP"], r["FN"]) == (tp, fp, fn)
     assert r["dice"] == pytest.approx(float(odice(counts).double().mean()), abs=1e-7)
     assert r["slices"] == 16
+
+
+def test_synthetic_checkpoint_matches_reference_layout(models):
+    """yolo_u_b200.synth (product-side random checkpoints for the bench) has exactly the reference's parameter names /
+    shapes, so the same dict loads into the oracle (strict) and into libysp."""
+    from yolo_u_b200.synth import detector_spec, seg_spec, synth_state_dicts
+    pred, seg = models
+    det_ref, seg_ref = pred.model.model.state_dict(), seg.state_dict()
+    assert [k for k, _, _ in detector_spec()] == list(det_ref.keys())
+    assert {k: tuple(s) for k, s, _ in detector_spec()} == {k: tuple(v.shape) for k, v in det_ref.items()}
+    assert {k: tuple(s) for k, s, _ in seg_spec()} == {k: tuple(v.shape) for k, v in seg_ref.items()}
+    d, s = synth_state_dicts(3)
+    assert s["encoder.0.conv.weight"] is d["model.0.conv.weight"]          # shared encoder, like YOLOSegPlusPlus.py:150
+    from oracle.model import DetectionModel
+    DetectionModel().fuse().load_state_dict(d)                             # strict

@@ -1,0 +1,105 @@
+"""GPU: evaluation-loop level behaviour -- sharded volumes (BASELINE cfg 3 in miniature), the double-buffered host
+pipeline, odd batch sizes, reference-native 160x160 resolution, error behaviour."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ysp():
+    import yolo_u_b200
+    assert torch.cuda.is_available()
+    return yolo_u_b200
+
+
+@pytest.fixture(scope="module")
+def predictor(ysp, models):
+    pred, seg = models
+    return ysp.Predictor.from_modules(pred, seg, mode="fp32")
+
+
+def _oracle_counts(models, x, tg):
+    from oracle.model import pipeline, mask_counts
+    from oracle import nms as onms
+    pred, seg = models
+    with torch.no_grad():
+        out, dets, keep, y, bott = pipeline(pred, seg, x, onms.non_max_suppression)
+    return out, mask_counts(out, tg)
+
+
+def test_sharded_volumes_match_single_pass(ysp, models, predictor):
+    """2 'volumes' x 5 slices, sharded over 2 ranks and batched by 3 (ragged last batch): the merged counters equal the
+    oracle's over all 10 slices (Dice <= 1e-4, counters equal up to the fp32 1e-3 logit tolerance => exact here)."""
+    from oracle.model import dice_from_counts
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(10, 4, 240, 240, generator=g)
+    tg = (torch.rand(10, 1, 240, 240, generator=g) > 0.5).float()
+    _, want = _oracle_counts(models, x, tg)
+    merged = ysp.SegMetrics()
+    per_slice = []
+    for rank in range(2):
+        lo, hi = ysp.shard_slices(2, 5, 2, rank)
+        m = ysp.SegMetrics()
+        for a, b in ysp.batches(lo, hi, 3):
+            c = predictor.predict_raw(x[a:b].cuda(), tg[a:b].cuda())["counts"].cpu()
+            per_slice.append(c)
+            m.update(c)
+        merged.state += m.state
+    got = torch.cat(per_slice)
+    d_got, d_want = ysp.dice_from_counts(got), dice_from_counts(want)
+    assert (d_got - d_want).abs().max().item() <= 1e-4
+    assert (got.long() - want).abs().max().item() <= 2            # a logit within 1e-5 of 0 may flip a pixel
+    assert merged.compute()["slices"] == 10
+
+
+def test_host_pipeline_matches_direct_call(ysp, predictor):
+    g = torch.Generator().manual_seed(5)
+    B = 6
+    u8 = [torch.randint(0, 256, (B, 240, 240, 4), dtype=torch.uint8, generator=g).pin_memory() for _ in range(3)]
+    tg = (torch.rand(B, 1, 240, 240, generator=g) > 0.5).float().pin_memory()
+    hp = ysp.HostPipeline(predictor, B, 240, 240)
+    got = []
+    for i in range(3):
+        slot = hp.submit(u8[i], tg)
+        got.append({k: v.clone() for k, v in hp.results(slot).items()})
+    hp.synchronize()
+    for i in range(3):
+        o = predictor.predict_raw(u8[i].cuda(), tg.cuda())
+        torch.cuda.synchronize()
+        for k in ("counts", "det_count", "det_idx", "det_boxes"):
+            n = o["det_count"].cpu()
+            if k in ("det_idx", "det_boxes"):
+                for b in range(B):
+                    assert torch.equal(got[i][k][b, : n[b]], o[k].cpu()[b, : n[b]]), (i, k, b)
+            else:
+                assert torch.equal(got[i][k], o[k].cpu()), (i, k)
+    assert hp.h2d_bytes == B * 240 * 240 * 4 + B * 240 * 240 * 4 and hp.d2h_bytes > 0
+
+
+@pytest.mark.parametrize("B,size", [(1, 240), (3, 160), (5, 96)])
+def test_odd_batches_and_sizes(ysp, models, predictor, B, size):
+    g = torch.Generator().manual_seed(B * 1000 + size)
+    x = torch.rand(B, 4, size, size, generator=g)
+    tg = (torch.rand(B, 1, size, size, generator=g) > 0.5).float()
+    want_logits, want = _oracle_counts(models, x, tg)
+    ml, dets, keep, counts = predictor.predict(x.cuda(), tg.cuda())
+    assert (ml.cpu() - want_logits).abs().max().item() <= 1e-3
+    assert (counts.cpu().long() - want).abs().max().item() <= 2
+    assert len(dets) == B and all(d.shape[1] == 6 for d in dets)
+
+
+def test_error_behaviour(ysp, models, predictor):
+    pred, seg = models
+    with pytest.raises(ysp.YspError):
+        predictor.predict(torch.rand(1, 4, 240, 240))                       # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        predictor.predict(torch.rand(1, 3, 240, 240).cuda())                # 3 channels
+    with pytest.raises(ValueError):
+        predictor.predict(torch.rand(1, 4, 100, 100).cuda())                # H, W not multiples of 8
+    eng = ysp.Engine("cuda:0", "fp32")
+    sd = dict(seg.state_dict())
+    sd.pop("decoder.3.1.conv.1.conv1.conv.weight")
+    eng.load_state_dict("seg", sd)
+    with pytest.raises(KeyError, match="decoder.3.1.conv.1.conv1"):
+        eng.finalize(det=False, seg=True)
