@@ -133,7 +133,7 @@ void launch_conv_dense(const ConvP& p, int in_dt, int out_dt, cudaStream_t s) {
 // Depthwise k x k, stride 1, 'same' padding (ultralytics DWConv / LightConv.conv2 / GhostConv.cv2 / AAttn.pe).
 // One thread = one pixel x 4 channels; weights [k*k][C] fp32.  HBM-bound: the k*k re-reads hit L1/L2.
 // =====================================================================================================================
-template <typename T>
+template <typename T, int K>   // K = 0: runtime kernel size
 __global__ void __launch_bounds__(256) conv_dw_kernel(DwP p, long long total) {
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
@@ -147,16 +147,42 @@ __global__ void __launch_bounds__(256) conv_dw_kernel(DwP p, long long total) {
   const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
   const int cin = (c / p.grp) * p.grp_stride + (c % p.grp);
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int r = 0; r < p.k; ++r) {
-    int iy = y + r - p.pad;
-    if (iy < 0 || iy >= p.H) continue;
-    for (int s = 0; s < p.k; ++s) {
-      int ix = x + s - p.pad;
-      if (ix < 0 || ix >= p.W) continue;
-      F4 v = load4<T>(in + ((size_t)(n * p.H + iy) * p.W + ix) * p.in_cs + cin);
-      float4 wv = *reinterpret_cast<const float4*>(p.w + (size_t)(r * p.k + s) * p.C + c);
-      a0 = fmaf(v.v[0], wv.x, a0); a1 = fmaf(v.v[1], wv.y, a1);
-      a2 = fmaf(v.v[2], wv.z, a2); a3 = fmaf(v.v[3], wv.w, a3);
+  if (K > 0) {
+    // compile-time kernel size: fully unrolled, all K*K loads independent and in flight together (the runtime-k loop
+    // serialised one L1 round trip per tap)
+    constexpr int KK = K > 0 ? K : 1;
+    const T* base = in + ((size_t)(n * p.H + y) * p.W + x) * p.in_cs + cin;
+    const float* wb = p.w + c;
+#pragma unroll
+    for (int r = 0; r < KK; ++r) {
+      const int iy = y + r - KK / 2;
+      const bool oky = iy >= 0 && iy < p.H;
+      F4 v[KK];
+#pragma unroll
+      for (int s = 0; s < KK; ++s) {                 // issue the whole row of loads before any use
+        const int ix = x + s - KK / 2;
+        if (oky && ix >= 0 && ix < p.W) v[s] = load4<T>(base + ((long long)(r - KK / 2) * p.W + (s - KK / 2)) * p.in_cs);
+        else v[s].v[0] = v[s].v[1] = v[s].v[2] = v[s].v[3] = 0.f;
+      }
+#pragma unroll
+      for (int s = 0; s < KK; ++s) {
+        float4 wv = *reinterpret_cast<const float4*>(wb + (size_t)(r * KK + s) * p.C);
+        a0 = fmaf(v[s].v[0], wv.x, a0); a1 = fmaf(v[s].v[1], wv.y, a1);
+        a2 = fmaf(v[s].v[2], wv.z, a2); a3 = fmaf(v[s].v[3], wv.w, a3);
+      }
+    }
+  } else {
+    for (int r = 0; r < p.k; ++r) {
+      int iy = y + r - p.pad;
+      if (iy < 0 || iy >= p.H) continue;
+      for (int s = 0; s < p.k; ++s) {
+        int ix = x + s - p.pad;
+        if (ix < 0 || ix >= p.W) continue;
+        F4 v = load4<T>(in + ((size_t)(n * p.H + iy) * p.W + ix) * p.in_cs + cin);
+        float4 wv = *reinterpret_cast<const float4*>(p.w + (size_t)(r * p.k + s) * p.C + c);
+        a0 = fmaf(v.v[0], wv.x, a0); a1 = fmaf(v.v[1], wv.y, a1);
+        a2 = fmaf(v.v[2], wv.z, a2); a3 = fmaf(v.v[3], wv.w, a3);
+      }
     }
   }
   float4 b = *reinterpret_cast<const float4*>(p.bias + c);
@@ -171,11 +197,107 @@ __global__ void __launch_bounds__(256) conv_dw_kernel(DwP p, long long total) {
   store4<T>(reinterpret_cast<T*>(p.out) + (size_t)pix * p.out_cs + c, o);
 }
 
+// Tiled variant for the larger kernels (5x5 GhostConv, 7x7 AAttn.pe) and big maps: a TY x TX output tile of 16 channels
+// per CTA, input tile + halo staged once in shared memory (fp32, pixel pitch 20 floats: conflict-free float4 reads),
+// every thread slides a K-wide window over 4 consecutive output pixels so each staged value is reused from registers.
+template <typename T, int K, int TY, int TX>
+__global__ void __launch_bounds__(TY * TX) conv_dw_tiled_kernel(DwP p) {
+  constexpr int NT = TY * TX;                        // (TX/4) x TY x 4 channel quads
+  constexpr int IH = TY + K - 1, IW = TX + K - 1, PS = 20;
+  extern __shared__ __align__(16) float dsm[];
+  float* sIn = dsm;                                  // [IH][IW][PS]
+  float* sW = sIn + IH * IW * PS;                    // [K*K][16]
+  const int tid = threadIdx.x;
+  const int tiles_x = (p.W + TX - 1) / TX, tiles_y = (p.H + TY - 1) / TY;
+  int t = blockIdx.x;
+  const int tx0 = (t % tiles_x) * TX; t /= tiles_x;
+  const int ty0 = (t % tiles_y) * TY; t /= tiles_y;
+  const int cg = (t % (p.C >> 4)) << 4;              // 16-channel group
+  const int n = t / (p.C >> 4);
+  const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
+  const int cin = (cg / p.grp) * p.grp_stride + (cg % p.grp);
+  for (int i = tid; i < K * K * 4; i += NT)
+    *reinterpret_cast<float4*>(sW + (i >> 2) * 16 + (i & 3) * 4) = *reinterpret_cast<const float4*>(p.w + (size_t)(i >> 2) * p.C + cg + (i & 3) * 4);
+  for (int i = tid; i < IH * IW * 4; i += NT) {
+    const int q = i & 3, pp = i >> 2;
+    const int iy = ty0 + pp / IW - K / 2, ix = tx0 + pp % IW - K / 2;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+      F4 f = load4<T>(in + ((size_t)(n * p.H + iy) * p.W + ix) * p.in_cs + cin + q * 4);
+      v = make_float4(f.v[0], f.v[1], f.v[2], f.v[3]);
+    }
+    *reinterpret_cast<float4*>(sIn + pp * PS + q * 4) = v;
+  }
+  __syncthreads();
+  const int q = tid & 3, txi = (tid >> 2) % (TX / 4), ty = tid / TX;
+  float4 acc[4];
+  const float4 bias = *reinterpret_cast<const float4*>(p.bias + cg + q * 4);
+#pragma unroll
+  for (int o = 0; o < 4; ++o) acc[o] = bias;
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    const float* rp = sIn + ((ty + r) * IW + txi * 4) * PS + q * 4;
+    float4 v[K + 3], w[K];
+#pragma unroll
+    for (int j = 0; j < K + 3; ++j) v[j] = *reinterpret_cast<const float4*>(rp + j * PS);
+#pragma unroll
+    for (int s2 = 0; s2 < K; ++s2) w[s2] = *reinterpret_cast<const float4*>(sW + (r * K + s2) * 16 + q * 4);
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int s2 = 0; s2 < K; ++s2) {
+        acc[o].x = fmaf(v[o + s2].x, w[s2].x, acc[o].x); acc[o].y = fmaf(v[o + s2].y, w[s2].y, acc[o].y);
+        acc[o].z = fmaf(v[o + s2].z, w[s2].z, acc[o].z); acc[o].w = fmaf(v[o + s2].w, w[s2].w, acc[o].w);
+      }
+  }
+  const int y = ty0 + ty;
+  if (y >= p.H) return;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int x = tx0 + txi * 4 + o;
+    if (x >= p.W) break;
+    const size_t pix = (size_t)(n * p.H + y) * p.W + x;
+    F4 ov;
+    ov.v[0] = apply_act(acc[o].x, p.act); ov.v[1] = apply_act(acc[o].y, p.act);
+    ov.v[2] = apply_act(acc[o].z, p.act); ov.v[3] = apply_act(acc[o].w, p.act);
+    if (p.res) {
+      F4 rv = load4<T>(reinterpret_cast<const T*>(p.res) + pix * p.res_cs + cg + q * 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ov.v[i] += rv.v[i];
+    }
+    store4<T>(reinterpret_cast<T*>(p.out) + pix * p.out_cs + cg + q * 4, ov);
+  }
+}
+
+template <typename T, int K, int TY, int TX>
+static void conv_dw_tiled_launch(const DwP& p, cudaStream_t s) {
+  constexpr size_t smem = sizeof(float) * ((TY + K - 1) * (TX + K - 1) * 20 + K * K * 16);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(conv_dw_tiled_kernel<T, K, TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  const int tiles = ((p.W + TX - 1) / TX) * ((p.H + TY - 1) / TY) * (p.C >> 4) * p.N;
+  conv_dw_tiled_kernel<T, K, TY, TX><<<tiles, TY * TX, smem, s>>>(p);
+}
+
+template <typename T>
+static void conv_dw_dispatch(const DwP& p, long long total, int g, cudaStream_t s) {
+  const bool tileable = (p.C % 16 == 0) && (p.grp % 16 == 0);
+  if (tileable && (p.k == 5 || p.k == 7)) {
+    const bool small = p.H <= 8 && p.W <= 8;
+    if (p.k == 7) { if (small) conv_dw_tiled_launch<T, 7, 8, 8>(p, s); else conv_dw_tiled_launch<T, 7, 16, 16>(p, s); }
+    else          { if (small) conv_dw_tiled_launch<T, 5, 8, 8>(p, s); else conv_dw_tiled_launch<T, 5, 16, 16>(p, s); }
+    return;
+  }
+  if (p.k == 3) conv_dw_kernel<T, 3><<<g, 256, 0, s>>>(p, total);
+  else if (p.k == 5) conv_dw_kernel<T, 5><<<g, 256, 0, s>>>(p, total);
+  else if (p.k == 7) conv_dw_kernel<T, 7><<<g, 256, 0, s>>>(p, total);
+  else conv_dw_kernel<T, 0><<<g, 256, 0, s>>>(p, total);
+}
+
 void launch_conv_dw(const DwP& p, int dt, cudaStream_t s) {
   long long total = (long long)p.N * p.H * p.W * (p.C >> 2);
   int g = cdiv(total, 256);
-  if (dt == DT_F32) conv_dw_kernel<float><<<g, 256, 0, s>>>(p, total);
-  else conv_dw_kernel<bf16><<<g, 256, 0, s>>>(p, total);
+  if (dt == DT_F32) conv_dw_dispatch<float>(p, total, g, s);
+  else conv_dw_dispatch<bf16>(p, total, g, s);
 }
 
 // =====================================================================================================================
