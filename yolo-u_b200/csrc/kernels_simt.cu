@@ -212,17 +212,20 @@ __global__ void __launch_bounds__(TY * TX) conv_dw_tiled_kernel(DwP p) {
   int t = blockIdx.x;
   const int tx0 = (t % tiles_x) * TX; t /= tiles_x;
   const int ty0 = (t % tiles_y) * TY; t /= tiles_y;
-  const int cg = (t % (p.C >> 4)) << 4;              // 16-channel group
-  const int n = t / (p.C >> 4);
+  const int ngrp = (p.C + 15) >> 4;
+  const int cg = (t % ngrp) << 4;                    // 16-channel group (the last one may be partial: C % 4 == 0)
+  const int n = t / ngrp;
+  const int nq = min(4, (p.C - cg) >> 2);            // valid channel quads in this group
   const T* __restrict__ in = reinterpret_cast<const T*>(p.in);
   const int cin = (cg / p.grp) * p.grp_stride + (cg % p.grp);
   for (int i = tid; i < K * K * 4; i += NT)
-    *reinterpret_cast<float4*>(sW + (i >> 2) * 16 + (i & 3) * 4) = *reinterpret_cast<const float4*>(p.w + (size_t)(i >> 2) * p.C + cg + (i & 3) * 4);
+    *reinterpret_cast<float4*>(sW + (i >> 2) * 16 + (i & 3) * 4) =
+        (i & 3) < nq ? *reinterpret_cast<const float4*>(p.w + (size_t)(i >> 2) * p.C + cg + (i & 3) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = tid; i < IH * IW * 4; i += NT) {
     const int q = i & 3, pp = i >> 2;
     const int iy = ty0 + pp / IW - K / 2, ix = tx0 + pp % IW - K / 2;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+    if (q < nq && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
       F4 f = load4<T>(in + ((size_t)(n * p.H + iy) * p.W + ix) * p.in_cs + cin + q * 4);
       v = make_float4(f.v[0], f.v[1], f.v[2], f.v[3]);
     }
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(TY * TX) conv_dw_tiled_kernel(DwP p) {
   __syncthreads();
   const int q = tid & 3, txi = (tid >> 2) % (TX / 4), ty = tid / TX;
   float4 acc[4];
-  const float4 bias = *reinterpret_cast<const float4*>(p.bias + cg + q * 4);
+  const float4 bias = q < nq ? *reinterpret_cast<const float4*>(p.bias + cg + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int o = 0; o < 4; ++o) acc[o] = bias;
 #pragma unroll
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(TY * TX) conv_dw_tiled_kernel(DwP p) {
       }
   }
   const int y = ty0 + ty;
-  if (y >= p.H) return;
+  if (y >= p.H || q >= nq) return;
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
     const int x = tx0 + txi * 4 + o;
@@ -274,17 +277,18 @@ static void conv_dw_tiled_launch(const DwP& p, cudaStream_t s) {
   constexpr size_t smem = sizeof(float) * ((TY + K - 1) * (TX + K - 1) * 20 + K * K * 16);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(conv_dw_tiled_kernel<T, K, TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  const int tiles = ((p.W + TX - 1) / TX) * ((p.H + TY - 1) / TY) * (p.C >> 4) * p.N;
+  const int tiles = ((p.W + TX - 1) / TX) * ((p.H + TY - 1) / TY) * ((p.C + 15) >> 4) * p.N;
   conv_dw_tiled_kernel<T, K, TY, TX><<<tiles, TY * TX, smem, s>>>(p);
 }
 
 template <typename T>
 static void conv_dw_dispatch(const DwP& p, long long total, int g, cudaStream_t s) {
-  const bool tileable = (p.C % 16 == 0) && (p.grp % 16 == 0);
-  if (tileable && (p.k == 5 || p.k == 7)) {
+  const bool tileable = (p.C % 4 == 0) && (p.grp % 16 == 0 || p.grp == p.C);
+  if (tileable && (p.k == 3 || p.k == 5 || p.k == 7)) {
     const bool small = p.H <= 8 && p.W <= 8;
-    if (p.k == 7) { if (small) conv_dw_tiled_launch<T, 7, 8, 8>(p, s); else conv_dw_tiled_launch<T, 7, 16, 16>(p, s); }
-    else          { if (small) conv_dw_tiled_launch<T, 5, 8, 8>(p, s); else conv_dw_tiled_launch<T, 5, 16, 16>(p, s); }
+    if (p.k == 7)      { if (small) conv_dw_tiled_launch<T, 7, 8, 8>(p, s); else conv_dw_tiled_launch<T, 7, 16, 16>(p, s); }
+    else if (p.k == 5) { if (small) conv_dw_tiled_launch<T, 5, 8, 8>(p, s); else conv_dw_tiled_launch<T, 5, 16, 16>(p, s); }
+    else               { if (small) conv_dw_tiled_launch<T, 3, 8, 8>(p, s); else conv_dw_tiled_launch<T, 3, 16, 16>(p, s); }
     return;
   }
   if (p.k == 3) conv_dw_kernel<T, 3><<<g, 256, 0, s>>>(p, total);
