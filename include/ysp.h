@@ -100,6 +100,15 @@ int ysp_xywh2xyxy_inplace(float* d_pred, int B, int C, int A, void* stream);
 int ysp_mask_dice(const float* d_logits, const float* d_target, int B, int HW, int32_t* d_counts, uint8_t* d_mask,
                   void* stream);
 
+/* -- SURVEY 8(f) "next" rows ------------------------------------------------------------------------------------ */
+/* dataset.py:86-97: per-map  sigmoid((x - mean) / std)  (torch.std, unbiased; std == 0 -> x - mean) on B maps of n
+ * elements each (the raw P3 class-logit maps written by generate_objectmaps.py:91-106). */
+int ysp_objectmap_transform(const float* d_maps, float* d_out, int B, int n, void* stream);
+/* ultralytics ops.scale_boxes (custom_detseg_predictor.py:177): in place on n rows of `row` floats (xyxy first):
+ * (b - pad) / gain, clipped to [0,w0] x [0,h0]. */
+int ysp_scale_boxes(float* d_boxes, long long n, int row, float gain, float pad_x, float pad_y, float w0, float h0,
+                    void* stream);
+
 /* -- fused pipeline (evaluate_model.py:134-174 with decision D1) -------------------------------------------------- */
 typedef struct ysp_pipeline_io {
   const float* d_img;        /* fp32 NCHW [B,4,H,W]   (or NULL if d_img_u8 given) */

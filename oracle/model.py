@@ -344,3 +344,33 @@ def dice_loss(pred_logits: torch.Tensor, target: torch.Tensor, smooth: float = 1
     sp, st = p.sum(), target.sum()
     tp = (sp + st - (p - target).abs().sum()) / 2
     return 1 - (2 * tp + smooth) / (sp + st + smooth)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# SURVEY 8(f) "next" rows: objectmap consumer transform (dataset.py:86-97) and upstream ops.scale_boxes
+# ----------------------------------------------------------------------------------------------------------
+
+
+def objectmap_transform(objectmap: torch.Tensor) -> torch.Tensor:
+    """dataset.py:86-97 for ONE map tensor: z-score with torch.std (unbiased), guarded for std == 0, then sigmoid."""
+    mean, std = objectmap.mean(), objectmap.std()
+    objectmap = (objectmap - mean) / std if std > 0 else objectmap - mean
+    return torch.sigmoid(objectmap)
+
+
+def scale_boxes(img1_shape, boxes, img0_shape, padding=True):
+    """Upstream ultralytics.utils.ops.scale_boxes (xyxy, ratio_pad=None), as called at custom_detseg_predictor.py:177."""
+    gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+    pad = (round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1), round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1))
+    boxes = boxes.clone()
+    if padding:
+        boxes[..., 0] -= pad[0]
+        boxes[..., 1] -= pad[1]
+        boxes[..., 2] -= pad[0]
+        boxes[..., 3] -= pad[1]
+    boxes[..., :4] /= gain
+    boxes[..., 0].clamp_(0, img0_shape[1])
+    boxes[..., 1].clamp_(0, img0_shape[0])
+    boxes[..., 2].clamp_(0, img0_shape[1])
+    boxes[..., 3].clamp_(0, img0_shape[0])
+    return boxes

@@ -103,3 +103,35 @@ def test_error_behaviour(ysp, models, predictor):
     eng.load_state_dict("seg", sd)
     with pytest.raises(KeyError, match="decoder.3.1.conv.1.conv1"):
         eng.finalize(det=False, seg=True)
+
+
+def test_objectmap_formats(ysp, models, tmp_path):
+    """producer (generate_objectmaps.py:91-106) and consumer (dataset.py:86-97) of the bottleneck map."""
+    from oracle.model import objectmap_transform as oref
+    pred, _ = models
+    det = ysp.B200Detector.from_predictor(pred, mode="fp32")
+    x = torch.rand(3, 4, 160, 160, generator=torch.Generator().manual_seed(2))
+    paths = ysp.save_objectmaps(det, x.cuda(), ["a", "b", "c"], str(tmp_path))
+    with torch.no_grad():
+        _, raws = pred.model(x)
+    maps = []
+    for i, p in enumerate(paths):
+        m = torch.load(p)
+        assert m.shape == (1, 1, 20, 20) and p.endswith("_20.pt")
+        assert (m - raws[0][i:i + 1, -1:]).abs().max().item() <= 1e-3
+        maps.append(m)
+    maps = torch.cat(maps + [torch.full((1, 1, 20, 20), 0.75)])         # last map: std == 0 branch (exactly representable)
+    got = ysp.objectmap_transform(maps.cuda()).cpu()
+    want = torch.stack([oref(m) for m in maps])
+    assert (got - want).abs().max().item() <= 1e-6
+
+
+def test_scale_boxes(ysp):
+    from oracle.model import scale_boxes as sref
+    g = torch.Generator().manual_seed(4)
+    b = torch.rand(37, 6, generator=g) * 300 - 20
+    for img1, img0, padding in (((256, 256), (240, 240, 4), False), ((640, 640), (240, 320, 3), True), ((160, 160), (240, 240), True)):
+        want = sref(img1, b[:, :4], img0, padding=padding)
+        d = b.clone().cuda()
+        out = ysp.scale_boxes(img1, d[:, :4], img0, padding=padding)
+        assert torch.allclose(out.cpu(), want, atol=1e-5) and torch.equal(d[:, 4:].cpu(), b[:, 4:])

@@ -39,6 +39,8 @@ PROTOTYPES = {
     "ysp_nms_core": (i32, [vp, vp, i32, f32, vp, vp, vp, sz, vp]),
     "ysp_xywh2xyxy_inplace": (i32, [vp, i32, i32, i32, vp]),
     "ysp_mask_dice": (i32, [vp, vp, i32, i32, vp, vp, vp]),
+    "ysp_objectmap_transform": (i32, [vp, vp, i32, i32, vp]),
+    "ysp_scale_boxes": (i32, [vp, C.c_longlong, i32, f32, f32, f32, f32, f32, vp]),
     "ysp_pipeline": (i32, [vp, C.POINTER(PipelineIO), i32, i32, i32, vp, sz, vp]),
     "ysp_last_launch_count": (i32, [vp]),
     "ysp_set_keep_intermediates": (i32, [vp, i32]),

@@ -1066,6 +1066,20 @@ int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, 
   return 0;
 }
 
+int ysp_objectmap_transform(const float* d_maps, float* d_out, int B, int n, void* stream) {
+  if (!d_maps || !d_out || B < 0 || n <= 0) return fail(YSP_EINVAL, "ysp_objectmap_transform: bad arguments");
+  launch_objectmap_transform(d_maps, d_out, B, n, (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int ysp_scale_boxes(float* d_boxes, long long n, int row, float gain, float pad_x, float pad_y, float w0, float h0, void* stream) {
+  if (!d_boxes || n < 0 || row < 4 || !(gain > 0.f)) return fail(YSP_EINVAL, "ysp_scale_boxes: bad arguments");
+  launch_scale_boxes(d_boxes, n, row, gain, pad_x, pad_y, w0, h0, (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int ysp_last_launch_count(ysp_handle* h) { return h ? h->last_launches : 0; }
 
 int ysp_profile(ysp_handle* h, int enable) {

@@ -34,6 +34,9 @@ void launch_mask_dice(const float* logits, const float* target, int B, int HW, i
                       cudaStream_t s);
 void launch_nhwc_to_nchw_f32(const void* in, float* out, int N, int H, int W, int C, int in_cs, int dt, cudaStream_t s);
 
+void launch_objectmap_transform(const float* in, float* out, int B, int n, cudaStream_t s);
+void launch_scale_boxes(float* boxes, long long n, int row, float gain, float pad_x, float pad_y, float w0, float h0, cudaStream_t s);
+
 // kernels_stem_attn.cu
 void launch_stem_conv(const void* in, int in_u8, void* out, const float* w, const float* bias, int N, int H, int W, int OH,
                       int OW, int out_cs, int wld, int dt, cudaStream_t s);

@@ -666,4 +666,56 @@ void launch_mask_dice(const float* logits, const float* target, int B, int HW, i
   mask_dice_kernel<<<g, 256, 0, s>>>(logits, target, HW, counts, mask);
 }
 
+
+// =====================================================================================================================
+// bottleneck producer/consumer format.  generate_objectmaps.py:91-106 stores the raw P3 class-logit map
+// per image; dataset.py:86-97 turns it into the training-time bottleneck  sigmoid((x - mean) / std)  per map (torch.std:
+// unbiased; std == 0 -> x - mean).  One CTA per map, two-pass mean / variance in fp32 with fp64 block totals.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) objectmap_transform_kernel(const float* __restrict__ in, float* __restrict__ out, int n) {
+  __shared__ double red[8];
+  __shared__ float s_mean, s_inv;
+  const float* x = in + (size_t)blockIdx.x * n;
+  float* y = out + (size_t)blockIdx.x * n;
+  auto block_sum = [&](double v) -> double {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    return t;
+  };
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += x[i];
+  const double mean = block_sum(s) / n;
+  double q = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) { double d = (double)x[i] - mean; q += d * d; }
+  const double var = n > 1 ? block_sum(q) / (n - 1) : 0.0;
+  if (threadIdx.x == 0) { s_mean = (float)mean; float sd = (float)sqrt(var); s_inv = sd > 0.f ? 1.f / sd : 1.f; }
+  __syncthreads();
+  const float m = s_mean, inv = s_inv;
+  for (int i = threadIdx.x; i < n; i += 256) y[i] = sigmoid_f((x[i] - m) * inv);
+}
+void launch_objectmap_transform(const float* in, float* out, int B, int n, cudaStream_t s) {
+  if (B > 0) objectmap_transform_kernel<<<B, 256, 0, s>>>(in, out, n);
+}
+
+// ultralytics ops.scale_boxes as used by custom_detseg_predictor.py:177 -- xyxy boxes from the network
+// canvas back to the original image: subtract the letterbox pad, divide by the gain, clip.  In place on [n, row] rows.
+__global__ void __launch_bounds__(256) scale_boxes_kernel(float* boxes, long long n, int row, float gain, float pad_x,
+                                                          float pad_y, float w0, float h0) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float* b = boxes + e * row;
+  float x1 = (b[0] - pad_x) / gain, y1 = (b[1] - pad_y) / gain, x2 = (b[2] - pad_x) / gain, y2 = (b[3] - pad_y) / gain;
+  b[0] = fminf(fmaxf(x1, 0.f), w0); b[1] = fminf(fmaxf(y1, 0.f), h0);
+  b[2] = fminf(fmaxf(x2, 0.f), w0); b[3] = fminf(fmaxf(y2, 0.f), h0);
+}
+void launch_scale_boxes(float* boxes, long long n, int row, float gain, float pad_x, float pad_y, float w0, float h0, cudaStream_t s) {
+  if (n > 0) scale_boxes_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(boxes, n, row, gain, pad_x, pad_y, w0, h0);
+}
+
 }  // namespace ysp
