@@ -135,6 +135,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 528; i += kTcThreads) s_bias[i] = i < p.Cout ? p.bias[i] : 0.f;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, bias staging --
+  // constants only) may overlap the tail of the previous kernel in the stream; activations are touched only below.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -455,7 +459,14 @@ void launch_conv_tc(const TcConvPlan* pl, const ConvP& c, cudaStream_t s) {
   if (pl->last_in != c.in && !encode_A(pl, c.in)) return;
   TcParams p = pl->p;
   p.res = reinterpret_cast<const bf16*>(c.res); p.out = c.out;
-  conv_tc_kernel<<<pl->grid, kTcThreads, pl->smem, s>>>(pl->tmA, pl->tmB, p);
+  static const bool no_pdl = getenv("YSP_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl->grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = pl->smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaLaunchKernelEx(&cfg, conv_tc_kernel, pl->tmA, pl->tmB, p);
 }
 
 }  // namespace ysp
