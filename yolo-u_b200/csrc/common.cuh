@@ -70,4 +70,24 @@ struct EwP {                // generic elementwise / resampling ops over NHWC vi
   int OH, OW;
 };
 
+// ---- programmatic dependent launch --------------------------------------------------------------------------------------
+// Every kernel of the layer chain is launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts with
+// pdl_sync(): it lets ITS successor begin launching right away and then waits until its predecessor has completed and
+// flushed.  Launch latency and CTA ramp-up of kernel N+1 overlap the tail of kernel N; ordering is unchanged.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace ysp

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
   constexpr int CS = C + 4;                            // fp32 b: padded pixel stride (conflict-free float4 per-pixel reads)
   constexpr int CSH = C + 8;                           // bf16 b: padded pixel stride (conflict-free mma A-fragment loads)
   static_assert(BH % S2 == 0 && TH % S4 == 0, "strip heights");
+  pdl_sync();
   extern __shared__ __align__(16) float sm[];
   float* sP = sm;                                      // [PH*PW][2C]
   float* sA = sP + PH * PW * 2 * C;                    // [AH*AW][C]      (re-used for c: [BH*BW][C])
@@ -306,7 +307,7 @@ static void dlc_launch(const DlcP& p, cudaStream_t s) {
   if (!attr) { cudaFuncSetAttribute(dlc_fused_kernel<T, C, TH, TW, S2, S4, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
   const int H = 2 * p.h, W = 2 * p.w;
   const int tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH) * p.N;
-  dlc_fused_kernel<T, C, TH, TW, S2, S4, FAST><<<tiles, 256, smem, s>>>(p);
+  launch_pdl(dlc_fused_kernel<T, C, TH, TW, S2, S4, FAST>, dim3(tiles), dim3(256), smem, s, p);
 }
 
 void launch_dlc_fused(const DlcP& p, int dt, cudaStream_t s) {

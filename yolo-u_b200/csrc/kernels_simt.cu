@@ -135,6 +135,7 @@ void launch_conv_dense(const ConvP& p, int in_dt, int out_dt, cudaStream_t s) {
 // =====================================================================================================================
 template <typename T, int K>   // K = 0: runtime kernel size
 __global__ void __launch_bounds__(256) conv_dw_kernel(DwP p, long long total) {
+  pdl_sync();
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int C4 = p.C >> 2;
@@ -204,6 +205,7 @@ template <typename T, int K, int TY, int TX>
 __global__ void __launch_bounds__(TY * TX) conv_dw_tiled_kernel(DwP p) {
   constexpr int NT = TY * TX;                        // (TX/4) x TY x 4 channel quads
   constexpr int IH = TY + K - 1, IW = TX + K - 1, PS = 20;
+  pdl_sync();
   extern __shared__ __align__(16) float dsm[];
   float* sIn = dsm;                                  // [IH][IW][PS]
   float* sW = sIn + IH * IW * PS;                    // [K*K][16]
@@ -278,7 +280,7 @@ static void conv_dw_tiled_launch(const DwP& p, cudaStream_t s) {
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(conv_dw_tiled_kernel<T, K, TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
   const int tiles = ((p.W + TX - 1) / TX) * ((p.H + TY - 1) / TY) * ((p.C + 15) >> 4) * p.N;
-  conv_dw_tiled_kernel<T, K, TY, TX><<<tiles, TY * TX, smem, s>>>(p);
+  launch_pdl(conv_dw_tiled_kernel<T, K, TY, TX>, dim3(tiles), dim3(TY * TX), smem, s, p);
 }
 
 template <typename T>
@@ -291,10 +293,10 @@ static void conv_dw_dispatch(const DwP& p, long long total, int g, cudaStream_t 
     else               { if (small) conv_dw_tiled_launch<T, 3, 8, 8>(p, s); else conv_dw_tiled_launch<T, 3, 16, 16>(p, s); }
     return;
   }
-  if (p.k == 3) conv_dw_kernel<T, 3><<<g, 256, 0, s>>>(p, total);
-  else if (p.k == 5) conv_dw_kernel<T, 5><<<g, 256, 0, s>>>(p, total);
-  else if (p.k == 7) conv_dw_kernel<T, 7><<<g, 256, 0, s>>>(p, total);
-  else conv_dw_kernel<T, 0><<<g, 256, 0, s>>>(p, total);
+  if (p.k == 3) launch_pdl(conv_dw_kernel<T, 3>, dim3(g), dim3(256), 0, s, p, total);
+  else if (p.k == 5) launch_pdl(conv_dw_kernel<T, 5>, dim3(g), dim3(256), 0, s, p, total);
+  else if (p.k == 7) launch_pdl(conv_dw_kernel<T, 7>, dim3(g), dim3(256), 0, s, p, total);
+  else launch_pdl(conv_dw_kernel<T, 0>, dim3(g), dim3(256), 0, s, p, total);
 }
 
 void launch_conv_dw(const DwP& p, int dt, cudaStream_t s) {
@@ -309,6 +311,7 @@ void launch_conv_dw(const DwP& p, int dt, cudaStream_t s) {
 // =====================================================================================================================
 template <typename T, int MODE>  // 0 add, 1 nearest x2, 2 bilinear x2
 __global__ void __launch_bounds__(256) ew_kernel(EwP p, long long total) {
+  pdl_sync();
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int C4 = p.C >> 2;
@@ -349,8 +352,8 @@ template <int MODE>
 static void ew_launch(const EwP& p, int dt, cudaStream_t s) {
   long long total = (long long)p.N * p.OH * p.OW * (p.C >> 2);
   int g = cdiv(total, 256);
-  if (dt == DT_F32) ew_kernel<float, MODE><<<g, 256, 0, s>>>(p, total);
-  else ew_kernel<bf16, MODE><<<g, 256, 0, s>>>(p, total);
+  if (dt == DT_F32) launch_pdl(ew_kernel<float, MODE>, dim3(g), dim3(256), 0, s, p, total);
+  else launch_pdl(ew_kernel<bf16, MODE>, dim3(g), dim3(256), 0, s, p, total);
 }
 void launch_add(const EwP& p, int dt, cudaStream_t s) { ew_launch<0>(p, dt, s); }
 void launch_up_nearest2(const EwP& p, int dt, cudaStream_t s) { ew_launch<1>(p, dt, s); }
@@ -362,6 +365,7 @@ void launch_up_bilinear2(const EwP& p, int dt, cudaStream_t s) { ew_launch<2>(p,
 // =====================================================================================================================
 template <typename T>
 __global__ void __launch_bounds__(256) eca_mean_kernel(const T* __restrict__ x, int HW, int C, int cs, float* mean) {
+  pdl_sync();
   __shared__ float red[8][33];
   int n = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
   float s = 0.f;
@@ -379,6 +383,7 @@ __global__ void __launch_bounds__(256) eca_mean_kernel(const T* __restrict__ x, 
 template <typename T>
 __global__ void __launch_bounds__(256) eca_scale_kernel(T* x, int HW, int C, int cs, const float* __restrict__ mean,
                                                         const float* __restrict__ w3, long long total) {
+  pdl_sync();
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int C4 = C >> 2;
@@ -401,11 +406,11 @@ void launch_eca(void* x, int N, int HW, int C, int cs, const float* w3, float* m
   dim3 g(N, cdiv(C, 32));
   long long total = (long long)N * HW * (C >> 2);
   if (dt == DT_F32) {
-    eca_mean_kernel<float><<<g, 256, 0, s>>>((const float*)x, HW, C, cs, mean_ws);
-    eca_scale_kernel<float><<<cdiv(total, 256), 256, 0, s>>>((float*)x, HW, C, cs, mean_ws, w3, total);
+    launch_pdl(eca_mean_kernel<float>, g, dim3(256), 0, s, (const float*)x, HW, C, cs, mean_ws);
+    launch_pdl(eca_scale_kernel<float>, dim3(cdiv(total, 256)), dim3(256), 0, s, (float*)x, HW, C, cs, (const float*)mean_ws, w3, total);
   } else {
-    eca_mean_kernel<bf16><<<g, 256, 0, s>>>((const bf16*)x, HW, C, cs, mean_ws);
-    eca_scale_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>((bf16*)x, HW, C, cs, mean_ws, w3, total);
+    launch_pdl(eca_mean_kernel<bf16>, g, dim3(256), 0, s, (const bf16*)x, HW, C, cs, mean_ws);
+    launch_pdl(eca_scale_kernel<bf16>, dim3(cdiv(total, 256)), dim3(256), 0, s, (bf16*)x, HW, C, cs, (const float*)mean_ws, w3, total);
   }
 }
 

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const void* __restrict__
                                                         int N, int H, int W, int OH, int OW, int out_cs, int wld) {
   __shared__ __align__(16) float sw[36 * 16];
   __shared__ float sb[16];
+  pdl_sync();
   for (int i = threadIdx.x; i < 36 * 16; i += 128) sw[i] = w[(i >> 4) * wld + (i & 15)];
   if (threadIdx.x < 16) sb[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
@@ -90,11 +91,11 @@ void launch_stem_conv(const void* in, int in_u8, void* out, const float* w, cons
   long long total = (long long)N * OH * ((OW + 1) / 2);
   int g = cdiv2(total, 128);
   if (dt == DT_F32) {
-    if (in_u8) stem_conv_kernel<float, true><<<g, 128, 0, s>>>(in, (float*)out, w, bias, N, H, W, OH, OW, out_cs, wld);
-    else stem_conv_kernel<float, false><<<g, 128, 0, s>>>(in, (float*)out, w, bias, N, H, W, OH, OW, out_cs, wld);
+    if (in_u8) launch_pdl(stem_conv_kernel<float, true>, dim3(g), dim3(128), 0, s, in, (float*)out, w, bias, N, H, W, OH, OW, out_cs, wld);
+    else launch_pdl(stem_conv_kernel<float, false>, dim3(g), dim3(128), 0, s, in, (float*)out, w, bias, N, H, W, OH, OW, out_cs, wld);
   } else {
-    if (in_u8) stem_conv_kernel<bf16, true><<<g, 128, 0, s>>>(in, (bf16*)out, w, bias, N, H, W, OH, OW, out_cs, wld);
-    else stem_conv_kernel<bf16, false><<<g, 128, 0, s>>>(in, (bf16*)out, w, bias, N, H, W, OH, OW, out_cs, wld);
+    if (in_u8) launch_pdl(stem_conv_kernel<bf16, true>, dim3(g), dim3(128), 0, s, in, (bf16*)out, w, bias, N, H, W, OH, OW, out_cs, wld);
+    else launch_pdl(stem_conv_kernel<bf16, false>, dim3(g), dim3(128), 0, s, in, (bf16*)out, w, bias, N, H, W, OH, OW, out_cs, wld);
   }
 }
 
@@ -118,6 +119,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __global__ void __launch_bounds__(128) attention64_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int Ntok,
                                                           int area, int qkv_cs, int out_cs) {
   constexpr int NT = 64, HD = 32, KS = HD + 8, VS = NT + 8;
+  pdl_sync();
   __shared__ __align__(16) bf16 sK[NT * KS];
   __shared__ __align__(16) bf16 sV[HD * VS];
   const int b = blockIdx.x / area, ar = blockIdx.x % area, h = blockIdx.y;
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(128) attention64_kernel(const bf16* __restrict
 void launch_attention64_bf16(const void* qkv, void* out, int B, int Ntok, int heads, int area, int qkv_cs, int out_cs,
                              cudaStream_t s) {
   dim3 g(B * area, heads);
-  attention64_kernel<<<g, 128, 0, s>>>((const bf16*)qkv, (bf16*)out, Ntok, area, qkv_cs, out_cs);
+  launch_pdl(attention64_kernel, g, dim3(128), 0, s, (const bf16*)qkv, (bf16*)out, Ntok, area, qkv_cs, out_cs);
 }
 
 }  // namespace ysp
