@@ -418,13 +418,14 @@ struct Builder {
   }
   void c3k(const std::string& p, TRef x, TRef out, int n, bool shortcut) {
     int c_ = (int)(out.C * 0.5);
-    TRef cat = alloc(x.N, x.H, x.W, 2 * c_);
-    TRef a = alloc(x.N, x.H, x.W, c_);
-    conv(p + ".cv1", x, a, 1, 1, ACT_SILU);
-    conv(p + ".cv2", x, slice(cat, c_, c_), 1, 1, ACT_SILU);
+    // buffer [m(cv1(x)) | cv2(x) | cv1(x)]: cv1 and cv2 read the same input, so they run as ONE GEMM (N = 2c_) writing
+    // channels [c_, 3c_); cv3 reads the first 2c_ channels (the concat of the reference)
+    TRef buf = alloc(x.N, x.H, x.W, 3 * c_);
+    TRef cat = slice(buf, 0, 2 * c_), a = slice(buf, 2 * c_, c_);
+    conv(p + ".cv2+" + p + ".cv1", x, slice(buf, c_, 2 * c_), 1, 1, ACT_SILU);
     TRef cur = a;
     for (int i = 0; i < n; ++i) {
-      TRef dst = (i == n - 1) ? slice(cat, 0, c_) : alloc(x.N, x.H, x.W, c_);
+      TRef dst = (i == n - 1) ? slice(buf, 0, c_) : alloc(x.N, x.H, x.W, c_);
       bottleneck(p + ".m." + std::to_string(i), cur, dst, shortcut, 3, 3, 1.0);
       cur = dst;
     }
@@ -485,14 +486,14 @@ struct Builder {
   }
   void c3ghost(const std::string& p, TRef x, TRef out) {
     int c_ = (int)(out.C * 0.5);
-    TRef cat = alloc(x.N, x.H, x.W, 2 * c_);
-    TRef a = alloc(x.N, x.H, x.W, c_);
-    conv(p + ".cv1", x, a, 1, 1, ACT_SILU);
-    conv(p + ".cv2", x, slice(cat, c_, c_), 1, 1, ACT_SILU);
+    // [m(cv1(x)) | cv2(x) | cv1(x)] with cv1/cv2 as one GEMM, like c3k()
+    TRef buf = alloc(x.N, x.H, x.W, 3 * c_);
+    TRef cat = slice(buf, 0, 2 * c_), a = slice(buf, 2 * c_, c_);
+    conv(p + ".cv2+" + p + ".cv1", x, slice(buf, c_, 2 * c_), 1, 1, ACT_SILU);
     // GhostBottleneck(c_, c_), stride 1: GhostConv(c_, c_/2) -> Identity -> GhostConv(c_/2, c_, act=False); + x
     TRef g1 = alloc(x.N, x.H, x.W, c_ / 2);
     ghostconv(p + ".m.0.conv.0", a, g1, ACT_SILU, nullptr);
-    TRef dst = slice(cat, 0, c_);
+    TRef dst = slice(buf, 0, c_);
     ghostconv(p + ".m.0.conv.2", g1, dst, ACT_NONE, &a);
     conv(p + ".cv3", cat, out, 1, 1, ACT_SILU);
   }
