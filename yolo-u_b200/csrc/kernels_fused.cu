@@ -67,10 +67,11 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
   constexpr int NB = BH * BW;
   constexpr int CS = C + 4;                            // fp32 b: padded pixel stride (conflict-free float4 per-pixel reads)
   constexpr int CSH = C + 8;                           // bf16 b: padded pixel stride (conflict-free mma A-fragment loads)
-  static_assert(BH % S2 == 0 && TH % S4 == 0, "strip heights");
+  static_assert(BH % S2 == 0 && TH % S4 == 0 && S4 % 2 == 0, "strip heights");
   pdl_sync();
   extern __shared__ __align__(16) float sm[];
-  float* sP = sm;                                      // [PH*PW][2C]
+  float* sP = sm;                                      // [2][PH*PW][C]: plane 0 = conv1 half, plane 1 = residual half
+                                                       // (two planes: consecutive pixels are contiguous -> no bank conflicts)
   float* sA = sP + PH * PW * 2 * C;                    // [AH*AW][C]      (re-used for c: [BH*BW][C])
   float* sB = sA + AH * AW * C;                        // fp32 [NB][CS]  or  bf16 [NB16][CSH]
   constexpr int NB16 = (NB + 15) / 16 * 16;
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
     int c4 = i % (2 * C4), pp = i / (2 * C4);
     int gx = min(max(px0 + pp % PW, 0), p.w - 1), gy = min(max(py0 + pp / PW, 0), p.h - 1);
     F4 v = load4<T>(P + ((size_t)(n * p.h + gy) * p.w + gx) * p.p_cs + c4 * 4);
-    *reinterpret_cast<float4*>(sP + pp * 2 * C + c4 * 4) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    *reinterpret_cast<float4*>(sP + (c4 / C4) * (PH * PW * C) + pp * C + (c4 % C4) * 4) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
   }
   __syncthreads();
 
@@ -110,8 +111,8 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
     const int gi = py0 + li, gj = px0 + lj;
     float4 o00, o01, o10, o11;
     if (gi >= 0 && gi < p.h && gj >= 0 && gj < p.w) {
-      const float* c = sP + (li * PW + lj) * 2 * C + c4 * 4;
-      constexpr int RS = PW * 2 * C, PS = 2 * C;
+      const float* c = sP + (li * PW + lj) * C + c4 * 4;
+      constexpr int RS = PW * C, PS = C;
       float4 m0 = *reinterpret_cast<const float4*>(c - RS - PS), m1 = *reinterpret_cast<const float4*>(c - RS), m2 = *reinterpret_cast<const float4*>(c - RS + PS);
       float4 z0 = *reinterpret_cast<const float4*>(c - PS), z1 = *reinterpret_cast<const float4*>(c), z2 = *reinterpret_cast<const float4*>(c + PS);
       float4 q0 = *reinterpret_cast<const float4*>(c + RS - PS), q1 = *reinterpret_cast<const float4*>(c + RS), q2 = *reinterpret_cast<const float4*>(c + RS + PS);
@@ -264,22 +265,22 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
       float4 acc[S4];
       dw_strip<S4>(sA + (oy0 * BW + ox) * C + c4 * 4, BW, C, wk, bias, acc);
       const int X = X0 + ox;
-      // residual: bilinear x2 of P[:, C:] -- column pair weights fixed by the parity of X, rows walk down the strip
+      // residual: bilinear x2 of P[:, C:].  Column pair + weights are fixed by the parity of X; the strip starts on an
+      // even row, so its S4 rows need S4/2 + 2 low-res rows: lerp each once horizontally, then blend vertically.
       const int lj = (X >> 1) - px0;                   // low-res column of X in the P tile
       const int ja = (X & 1) ? lj : lj - 1, jb = (X & 1) ? lj + 1 : lj;
       const float wa = (X & 1) ? 0.75f : 0.25f, wb = 1.f - wa;
+      const int li0 = ((Y0 + oy0) >> 1) - py0;         // low-res row of the strip's first output
+      const float* rp0 = sP + PH * PW * C + ((li0 - 1) * PW) * C + c4 * 4;
+      float4 hrow[S4 / 2 + 2];
+#pragma unroll
+      for (int k = 0; k < S4 / 2 + 2; ++k)
+        hrow[k] = lerp4(*reinterpret_cast<const float4*>(rp0 + (k * PW + ja) * C), wa, *reinterpret_cast<const float4*>(rp0 + (k * PW + jb) * C), wb);
 #pragma unroll
       for (int o = 0; o < S4; ++o) {
         const int Y = Y0 + oy0 + o;
         const bool inside = Y < H && X < W;
-        const int li = (Y >> 1) - py0;
-        const int ia = (Y & 1) ? li : li - 1, ib = (Y & 1) ? li + 1 : li;
-        const float va = (Y & 1) ? 0.75f : 0.25f, vb = 1.f - va;
-        const float* ra = sP + (ia * PW) * 2 * C + C + c4 * 4;
-        const float* rb = sP + (ib * PW) * 2 * C + C + c4 * 4;
-        float4 ta = lerp4(*reinterpret_cast<const float4*>(ra + ja * 2 * C), wa, *reinterpret_cast<const float4*>(ra + jb * 2 * C), wb);
-        float4 tb = lerp4(*reinterpret_cast<const float4*>(rb + ja * 2 * C), wa, *reinterpret_cast<const float4*>(rb + jb * 2 * C), wb);
-        float4 rs = lerp4(ta, va, tb, vb);
+        const float4 rs = (o & 1) ? lerp4(hrow[o / 2 + 1], 0.75f, hrow[o / 2 + 2], 0.25f) : lerp4(hrow[o / 2], 0.25f, hrow[o / 2 + 1], 0.75f);
         F4 ov;
         ov.v[0] = silu_t<FAST>(acc[o].x) + rs.x; ov.v[1] = silu_t<FAST>(acc[o].y) + rs.y;
         ov.v[2] = silu_t<FAST>(acc[o].z) + rs.z; ov.v[3] = silu_t<FAST>(acc[o].w) + rs.w;
