@@ -135,10 +135,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 528; i += kTcThreads) s_bias[i] = i < p.Cout ? p.bias[i] : 0.f;
-  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, bias staging --
-  // constants only) may overlap the tail of the previous kernel in the stream; activations are touched only below.
+  // Programmatic dependent launch: everything up to griddepcontrol.wait touches constants only (barrier init, TMEM
+  // allocation, descriptor prefetch, bias staging, and the resident-weight TMA loads) and overlaps the tail of the
+  // previous kernel in the stream; activations (A tiles, residuals) are read only after the wait.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -147,19 +147,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kiters = p.ntaps * p.kchunks;
   uint8_t* const wsm = smem;                          // resident weights: [n_tiles_n][tap][kchunk] tiles of b_bytes
   uint8_t* const ring = smem + p.w_bytes;             // A (+B when streaming) stage ring
+  if (warp == 0 && lane == 0 && p.w_resident) {
+    // every CTA used to re-fetch the same few-KB weight tile from the same L2 lines on every k-iteration (an L2
+    // hot spot that cost up to half the kernel); now the whole packed weight matrix is loaded once per CTA, and
+    // (weights being constants) before the dependency wait.
+    mbar_expect_tx(&wfull_bar, (uint32_t)(p.n_tiles_n * kiters) * (uint32_t)p.N_tile * p.Kc * 2u);
+    for (int t = 0; t < p.n_tiles_n; ++t)
+      for (int it = 0; it < kiters; ++it)
+        tma_load_2d(wsm + (size_t)(t * kiters + it) * p.b_bytes, &tmB, &wfull_bar, (it / p.kchunks) * p.cin_pad + (it % p.kchunks) * p.Kc,
+                    t * p.N_tile);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===== TMA producer (one lane) =====
     if (lane == 0) {
-      if (p.w_resident) {
-        // every CTA used to re-fetch the same few-KB weight tile from the same L2 lines on every k-iteration (an L2
-        // hot spot that cost up to half the kernel); now the whole packed weight matrix is loaded once per CTA.
-        mbar_expect_tx(&wfull_bar, (uint32_t)(p.n_tiles_n * kiters) * (uint32_t)p.N_tile * p.Kc * 2u);
-        for (int t = 0; t < p.n_tiles_n; ++t)
-          for (int it = 0; it < kiters; ++it)
-            tma_load_2d(wsm + (size_t)(t * kiters + it) * p.b_bytes, &tmB, &wfull_bar, (it / p.kchunks) * p.cin_pad + (it % p.kchunks) * p.Kc,
-                        t * p.N_tile);
-      }
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int tn_i = tile % p.n_tiles_n, tm = tile / p.n_tiles_n;
