@@ -55,6 +55,7 @@ struct ConvP {
   int M, K, wld;            // M = N*OH*OW, K = kh*kw*Cin, weights [K][wld] fp32
   int cout_store;           // >= Cout: channels [Cout, cout_store) are written as act(0) = 0 (zero channel padding)
   int in_zpad;              // input view has zero-filled channels up to a multiple of 16 (tensor-core K padding)
+  int in_pw, in_ph;         // memory pitch of the input view in pixels (0 = dense H x W); tensor-core path only
 };
 
 struct DwP {

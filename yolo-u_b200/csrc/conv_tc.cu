@@ -40,7 +40,7 @@ struct TcConvPlan {
   CUtensorMap tmB;
   mutable CUtensorMap tmA;
   mutable const void* last_in = nullptr;
-  int in_cs, H, W, NB, swizzle;
+  int in_cs, H, W, NB, swizzle, pw, ph;
   size_t smem;
   int grid;
 };
@@ -359,7 +359,7 @@ static bool encode_A(const TcConvPlan* pl, const void* in) {
     es[0] = es[1] = es[2] = es[3] = 1;
   } else {
     dims[0] = p.cin_pad; dims[1] = pl->W; dims[2] = pl->H; dims[3] = pl->NB;
-    strides[0] = px; strides[1] = px * pl->W; strides[2] = px * pl->W * pl->H;
+    strides[0] = px; strides[1] = px * pl->pw; strides[2] = px * pl->pw * pl->ph;
     box[0] = p.Kc; box[1] = p.TW * p.stride; box[2] = p.TH * p.stride; box[3] = p.TN;
     es[0] = 1; es[1] = p.stride; es[2] = p.stride; es[3] = 1;
   }
@@ -383,7 +383,8 @@ TcConvPlan* tc_conv_plan_create(const ConvP& c, const void* w_bf16, int out_dt) 
   p.OH = c.OH; p.OW = c.OW; p.NB = c.N; p.Cout = c.Cout; p.Cout_st = c.cout_store > c.Cout ? c.cout_store : c.Cout; p.M = c.M;
   p.n_tiles_n = (cout_pad + 255) / 256;
   p.N_tile = ((cout_pad + p.n_tiles_n - 1) / p.n_tiles_n + 15) / 16 * 16;
-  p.flat = (c.kh == 1 && c.stride == 1 && c.OH == c.H && c.OW == c.W) ? 1 : 0;
+  const bool pitched = (c.in_pw && c.in_pw != c.W) || (c.in_ph && c.in_ph != c.H);
+  p.flat = (c.kh == 1 && c.stride == 1 && c.OH == c.H && c.OW == c.W && !pitched) ? 1 : 0;
   if (p.flat) {
     p.TW = 128; p.TH = 1; p.TN = 1; p.tiles_w = p.tiles_h = p.tiles_n = 1;
     p.n_tiles_m = (int)((c.M + 127) / 128);
@@ -431,6 +432,7 @@ TcConvPlan* tc_conv_plan_create(const ConvP& c, const void* w_bf16, int out_dt) 
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.bias = c.bias; p.res_cs = c.res_cs; p.out_cs = c.out_cs; p.out_f32 = out_dt == DT_F32; p.act = c.act;
   pl->in_cs = c.in_cs; pl->H = c.H; pl->W = c.W; pl->NB = c.N;
+  pl->pw = c.in_pw ? c.in_pw : c.W; pl->ph = c.in_ph ? c.in_ph : c.H;
   pl->smem = (size_t)p.w_bytes + (size_t)p.stages * p.stage_bytes + 1024;
   const int total = p.n_tiles_m * p.n_tiles_n;
   const int ctas_per_sm = (p.tmem_cols <= 256 && pl->smem <= 110 * 1024) ? 2 : 1;

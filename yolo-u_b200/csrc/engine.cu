@@ -43,7 +43,7 @@ struct DevConv {           // packed weights of one conv (BN folded)
   bool dw = false;
 };
 
-struct TRef { int buf = -1; int N = 0, H = 0, W = 0, C = 0, cs = 0, co = 0, dt = 0; bool zpad = false; };
+struct TRef { int buf = -1; int N = 0, H = 0, W = 0, C = 0, cs = 0, co = 0, dt = 0; bool zpad = false; int pw = 0, ph = 0; };
 struct BufInfo { size_t bytes = 0, off = 0; int first = 1 << 30, last = -1; std::vector<int> regions; };
 struct RunCtx { char* ws; void* ext[16]; cudaStream_t s; };
 
@@ -59,6 +59,8 @@ struct Plan {
   std::vector<int> lane, region;             // per step: stream lane (0 = caller's stream) and fork-join region (0 = none)
   std::vector<std::pair<int, int>> region_span = {{0, 0}};   // [first step, last step] per region id
   int split = -1;                            // seg plan: first step that needs the detector's bottleneck
+  int share_step = -1, share_buf = -1;       // det plan: steps [0, share_step) produce layer 1 (buffer share_buf), kept alive
+  bool shared_stem = false;                  // seg plan: encoder.0/1 skipped, encoder.2 reads the detector's layer 1 (X_E1)
   std::vector<BufInfo> bufs;
   std::map<std::string, TRef> named;
   std::vector<TcConvPlan*> tc_plans;
@@ -80,6 +82,7 @@ struct ysp_handle {
   std::map<std::string, float*> vecs;        // small raw fp32 vectors (ECA conv1d weights)
   bool det_ready = false, seg_ready = false;
   bool keep_all = false;                     // disable buffer reuse so ysp_debug_tensor sees every intermediate
+  bool no_share = false;                     // YSP_NO_SHARE at ysp_create: seg head recomputes encoder layers 0-1 (A/B testing)
   std::map<std::string, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   int last_launches = 0;
@@ -223,7 +226,7 @@ static int pack_vec(ysp_handle* h, const std::string& key, float** out) {
 // graph builder
 // ---------------------------------------------------------------------------------------------------------------------
 // ext slots
-enum { X_IMG = 0, X_Y = 1, X_P3 = 2, X_P4 = 3, X_P5 = 4, X_LOGITS = 5, X_OUT = 6, X_BOTT = 7, X_IMG_U8 = 8 };
+enum { X_IMG = 0, X_Y = 1, X_P3 = 2, X_P4 = 3, X_P5 = 4, X_LOGITS = 5, X_OUT = 6, X_BOTT = 7, X_IMG_U8 = 8, X_E1 = 9 };
 
 struct Builder {
   ysp_handle* h; Plan* plan; int dt; std::string ns; double bn_eps; int rc = 0;
@@ -311,6 +314,7 @@ struct Builder {
     p.M = out.N * out.H * out.W; p.K = dc->K; p.wld = dc->wld;
     p.cout_store = out.zpad ? std::min((out.C + 15) / 16 * 16, out.cs) : out.C;
     p.in_zpad = in.zpad ? 1 : 0;
+    p.in_pw = in.pw; p.in_ph = in.ph;
     (void)padH; (void)padW;
     Plan* pl = plan;
     TRef rres = res ? *res : TRef();
@@ -325,6 +329,7 @@ struct Builder {
         if (tcp) pl->tc_plans.push_back(tcp);
       }
     }
+    if ((in.pw || in.ph) && !tcp) { rc = fail(YSP_EINVAL, "conv %s: pitched input needs the tensor-core path", prefix.c_str()); return; }
     emit([=](RunCtx& c) {
       ConvP q = p;
       q.in = pl->ptr(c, in); q.out = pl->ptr(c, out); q.res = has_res ? pl->ptr(c, rres) : nullptr;
@@ -590,6 +595,8 @@ static int build_detector(ysp_handle* h, Plan* plan, int B, int H, int W) {
   // backbone
   TRef t0 = g.alloc(B, h2, w2, 16);  g.stem("model.0", t0, B, H, W);                        g.name("model.0", t0);
   TRef t1 = g.alloc(B, h4, w4, 32);  g.conv("model.1", t0, t1, 3, 2, ACT_SILU);             g.name("model.1", t1);
+  plan->share_step = (int)plan->steps.size(); plan->share_buf = t1.buf;
+  plan->bufs[t1.buf].last = 1 << 29;          // kept for the whole plan: the seg head may read it (shared stem, see build_seg)
   TRef t2 = g.alloc(B, h4, w4, 64);  g.c3k2("model.2", t1, t2, false, 0.25, true);          g.name("model.2", t2);
   TRef t3 = g.alloc(B, h8, w8, 64);  g.conv("model.3", t2, t3, 3, 2, ACT_SILU);             g.name("model.3", t3);
   TRef cat13 = g.alloc(B, h8, w8, 256);        // [up(L11) 128 | L4 128]
@@ -655,13 +662,26 @@ static int build_detector(ysp_handle* h, Plan* plan, int B, int H, int W) {
 }
 
 // YOLO-Seg++ head (YOLOSegPlusPlus.py:150-178, :242-272)
-static int build_seg(ysp_handle* h, Plan* plan, int B, int H, int W) {
+// `shared_stem` (pipeline, bf16 mode): encoder layers 0 and 1 are NOT recomputed.  They are stride-2 3x3 convs whose
+// outputs inside the H/4 x W/4 window depend only on input pixels inside the H x W image, and the detector computes the
+// very same layers (shared weights, YOLOSegPlusPlus.py:150) on the image zero-padded to %32 -- so the detector's layer-1
+// output, read through a pitched H/4 x W/4 view, IS encoder.1's output, exactly.  (From layer 2 on the 3x3 stride-1
+// convs see real values instead of zero padding at the window border, so sharing stops there: decision D1.)
+static int build_seg(ysp_handle* h, Plan* plan, int B, int H, int W, bool shared_stem = false) {
   Builder g(h, plan, "seg", 1e-5);
   const int h2 = (H + 1) / 2, w2 = (W + 1) / 2, h4 = (h2 + 1) / 2, w4 = (w2 + 1) / 2, h8 = (h4 + 1) / 2, w8 = (w4 + 1) / 2;
   // encoder = detector layers 0..4 (frozen, BN already folded; falls back to eps 1e-3 when it arrives unfused)
   g.bn_eps = 1e-3;
-  TRef e0 = g.alloc(B, h2, w2, 16);  g.stem("encoder.0", e0, B, H, W);                      g.name("encoder.0", e0);
-  TRef e1 = g.alloc(B, h4, w4, 32);  g.conv("encoder.1", e0, e1, 3, 2, ACT_SILU);           g.name("encoder.1", e1);
+  TRef e1;
+  if (shared_stem) {
+    const int SH = (H + 31) / 32 * 32, SW = (W + 31) / 32 * 32;
+    e1 = Builder::ext(X_E1, B, h4, w4, 32, 32, g.dt);
+    e1.pw = SW / 4; e1.ph = SH / 4;
+    plan->shared_stem = true;
+  } else {
+    TRef e0 = g.alloc(B, h2, w2, 16);  g.stem("encoder.0", e0, B, H, W);                    g.name("encoder.0", e0);
+    e1 = g.alloc(B, h4, w4, 32);       g.conv("encoder.1", e0, e1, 3, 2, ACT_SILU);         g.name("encoder.1", e1);
+  }
   TRef cat2 = g.alloc(B, h4, w4, 128);          // dec2 input: [dec1 out 64 | skipA 64]
   TRef skipA = Builder::slice(cat2, 64, 64);    g.c3k2("encoder.2", e1, skipA, false, 0.25, true);   g.name("encoder.2", skipA);
   TRef e3 = g.alloc(B, h8, w8, 64);  g.conv("encoder.3", skipA, e3, 3, 2, ACT_SILU);        g.name("encoder.3", e3);
@@ -713,7 +733,7 @@ static int get_plan(ysp_handle* h, const char* kind, int B, int H, int W, Plan**
   auto it = h->plans.find(key);
   if (it != h->plans.end()) { *out = it->second.get(); return 0; }
   std::unique_ptr<Plan> p(new Plan());
-  int rc = (kind[0] == 'd') ? build_detector(h, p.get(), B, H, W) : build_seg(h, p.get(), B, H, W);
+  int rc = (kind[0] == 'd') ? build_detector(h, p.get(), B, H, W) : build_seg(h, p.get(), B, H, W, strcmp(kind, "segs") == 0);
   if (rc) return rc;
   *out = p.get();
   h->plans[key] = std::move(p);
@@ -825,6 +845,7 @@ int ysp_create(ysp_handle** out, int device, int mode) {
   ysp_handle* h = new ysp_handle();
   h->device = device; h->mode = mode;
   h->keep_all = getenv("YSP_KEEP_INTERMEDIATES") != nullptr;
+  h->no_share = getenv("YSP_NO_SHARE") != nullptr;
   *out = h;
   return 0;
 }
@@ -997,7 +1018,8 @@ int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, 
     return fail(YSP_EINVAL, "invalid thresholds");
   Plan *pd = nullptr, *ps = nullptr;
   if ((rc = get_plan(h, "det", B, H, W, &pd))) return rc;
-  if ((rc = get_plan(h, "seg", B, H, W, &ps))) return rc;
+  const bool share = h->mode == YSP_MODE_BF16 && !h->no_share && (long long)B * (H / 4) * (W / 4) >= 128;
+  if ((rc = get_plan(h, share ? "segs" : "seg", B, H, W, &ps))) return rc;
   const int SH = (H + 31) / 32 * 32, SW = (W + 31) / 32 * 32;
   const int A = (SH / 8) * (SW / 8) + (SH / 16) * (SW / 16) + (SH / 32) * (SW / 32);
   const int max_det = io->max_det > 0 ? io->max_det : 300;
@@ -1018,7 +1040,7 @@ int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, 
   const bool overlap = !h->profiling && !no_overlap && ps->split > 0;
   if (overlap && !h->aux) CUDA_OK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
   cudaStream_t s2 = overlap ? h->aux : s;
-  enum { EV_FORK = 48, EV_ENC, EV_DET, EV_NMS };          // sync-event slots above those used inside the plans
+  enum { EV_FORK = 48, EV_ENC, EV_DET, EV_NMS, EV_E1 };          // sync-event slots above those used inside the plans
   RunCtx c = {};
   c.ws = ws; c.s = s;
   c.ext[X_IMG] = (void*)io->d_img; c.ext[X_IMG_U8] = (void*)io->d_img_u8; c.ext[X_Y] = y; c.ext[X_BOTT] = bott;
@@ -1026,13 +1048,21 @@ int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, 
   c2.ws = ws + det_b; c2.s = s2;
   c2.ext[X_IMG] = (void*)io->d_img; c2.ext[X_IMG_U8] = (void*)io->d_img_u8; c2.ext[X_LOGITS] = bott;
   c2.ext[X_OUT] = io->d_mask_logits;
+  c2.ext[X_E1] = ws + pd->bufs[pd->share_buf].off;                                       // detector layer-1 output (shared stem)
+  int det_lo = 0;
   if (overlap) {
     cudaEventRecord(sync_event(h, EV_FORK), s);
     cudaStreamWaitEvent(s2, sync_event(h, EV_FORK), 0);
+    if (ps->shared_stem) {                       // the seg encoder starts once the detector's layers 0-1 are done
+      if ((rc = run_plan(h, pd, c, 0, pd->share_step))) return rc;
+      det_lo = pd->share_step;
+      cudaEventRecord(sync_event(h, EV_E1), s);
+      cudaStreamWaitEvent(s2, sync_event(h, EV_E1), 0);
+    }
     if ((rc = run_plan(h, ps, c2, 0, ps->split, 24))) return rc;                         // seg encoder on the aux stream
     cudaEventRecord(sync_event(h, EV_ENC), s2);
   }
-  if ((rc = run_plan(h, pd, c))) return rc;                                             // evaluate_model.py:141-144
+  if ((rc = run_plan(h, pd, c, det_lo))) return rc;                                     // evaluate_model.py:141-144
   cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
   if (h->profiling) { for (auto& e : pe) cudaEventCreate(&e); cudaEventRecord(pe[0], s); }
   if (overlap) {                                                                         // NMS on aux, concurrent with the decoder
