@@ -534,6 +534,54 @@ struct Builder {
     StepInfo{p + ".fused", "dlc_fused", tbytes(P) + (hd ? hi * 4 : tbytes(out)), 2.0 * hi * C * (9 + C + 9 + (hd ? 1 : 0)) + 16.0 * hi * C, 1});
   }
 
+  // bf16 mode, (Cin, C) in {(32,16)+head, (64,32)}: the whole stage on tcgen05 (kernels_dlc_tc.cu); no low-res GEMM needed.
+  bool doublelight_tc(const std::string& p, TRef xlow, TRef out, const std::string& head_prefix) {
+    if (rc) return true;
+    const bool head = !head_prefix.empty();
+    const int C = head ? 16 : out.C, Cin = xlow.C;
+    if (dt != DT_BF16 || !dlc_tc_supported(Cin, C, head) || getenv("YSP_NO_DLC_TC") != nullptr) return false;
+    DevConv *c1 = nullptr, *d1 = nullptr, *c2 = nullptr, *d2 = nullptr, *rr = nullptr, *hd = nullptr;
+    if ((rc = pack_conv(h, ns + "." + p + ".conv.0.conv1", bn_eps, &c1))) return true;
+    if ((rc = pack_conv(h, ns + "." + p + ".conv.0.conv2", bn_eps, &d1))) return true;
+    if ((rc = pack_conv(h, ns + "." + p + ".conv.1.conv1", bn_eps, &c2))) return true;
+    if ((rc = pack_conv(h, ns + "." + p + ".conv.1.conv2", bn_eps, &d2))) return true;
+    if ((rc = pack_conv(h, ns + "." + p + ".residual_conv", bn_eps, &rr))) return true;
+    if (head && (rc = pack_conv(h, ns + "." + head_prefix, bn_eps, &hd))) return true;
+    if (c1->Cin != Cin || c1->Cout != C || !d1->dw || d1->Cout != C || c2->Cin != C || c2->Cout != C || !d2->dw || d2->Cout != C ||
+        rr->Cin != Cin || rr->Cout != C || (hd && (hd->Cin != C || hd->Cout != 1)) || (xlow.cs & 7)) {
+      rc = fail(YSP_EINVAL, "doublelight_tc %s: unexpected weight shapes", p.c_str());
+      return true;
+    }
+    const std::string key = ns + "." + p + ".tcpack";
+    auto it = h->vecs.find(key);
+    if (it == h->vecs.end()) {
+      float* buf = nullptr;
+      if (cudaMalloc(&buf, dlc_tc_pack_bytes(Cin, C)) != cudaSuccess) { rc = fail(YSP_ECUDA, "cudaMalloc(tcpack)"); return true; }
+      DlcTcPrep q = {};
+      q.w1 = c1->w; q.c1 = c1->bias; q.w1ld = c1->wld; q.dw1 = d1->w; q.b1 = d1->bias;
+      q.w2 = c2->w; q.c2 = c2->bias; q.w2ld = c2->wld; q.dw2 = d2->w; q.b3 = d2->bias;
+      q.wr = rr->w; q.cr = rr->bias; q.wrld = rr->wld; q.wo = hd ? hd->w : nullptr; q.wold = hd ? hd->wld : 0;
+      q.Cin = Cin; q.C = C;
+      launch_dlc_tc_prepare(q, buf, nullptr);
+      if (cudaDeviceSynchronize() != cudaSuccess) { rc = fail(YSP_ECUDA, "dlc_tc_prepare"); return true; }
+      it = h->vecs.emplace(key, buf).first;
+    }
+    DlcTcP q = {};
+    q.wpack = reinterpret_cast<const uint8_t*>(it->second);
+    q.bo = hd ? hd->bias : nullptr;
+    q.N = xlow.N; q.h = xlow.H; q.w = xlow.W; q.Cin = Cin; q.C = C; q.x_cs = xlow.cs; q.out_cs = out.cs;
+    Plan* pl = plan;
+    const double hi = (double)xlow.N * xlow.H * xlow.W * 4;
+    emit([=](RunCtx& c) {
+      DlcTcP r = q;
+      r.x = pl->ptr(c, xlow); r.out = pl->ptr(c, out);
+      launch_dlc_tc(r, c.s);
+    }, {&xlow, &out}, 1,
+    StepInfo{p + ".tc", "dlc_tc", tbytes(xlow) + (head ? hi * 4 : tbytes(out)),
+             2.0 * hi * (9.0 * Cin * C + 9.0 * C * C + (double)Cin * C + (head ? C : 0)), 1});
+    return true;
+  }
+
   // DoubleLightConv (YOLOSegPlusPlus.py:33-58) on an already-upsampled input
   void doublelight(const std::string& p, TRef x, TRef out) {
     TRef r = alloc(x.N, x.H, x.W, out.C);
@@ -713,8 +761,9 @@ static int build_seg(ysp_handle* h, Plan* plan, int B, int H, int W, bool shared
   TRef d3 = g.alloc(B, h2, w2, 32);
   TRef out = Builder::ext(X_OUT, B, H, W, 1, 1, DT_F32);
   if (fuse) {
-    g.doublelight_fused("decoder.3.1", d2, d3, "");                                           g.name("decoder.3", d3);
-    g.doublelight_fused("decoder.4.1", d3, out, "output");
+    if (!g.doublelight_tc("decoder.3.1", d2, d3, "")) g.doublelight_fused("decoder.3.1", d2, d3, "");
+    g.name("decoder.3", d3);
+    if (!g.doublelight_tc("decoder.4.1", d3, out, "output")) g.doublelight_fused("decoder.4.1", d3, out, "output");
   } else {
     TRef u3 = g.alloc(B, h2, w2, 64);   g.ew(2, d2, nullptr, u3);
     g.doublelight("decoder.3.1", u3, d3);                                                     g.name("decoder.3", d3);

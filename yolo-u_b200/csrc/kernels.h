@@ -74,3 +74,22 @@ struct DlcP {
 };
 void launch_dlc_fused(const DlcP& p, int dt, cudaStream_t s);
 }  // namespace ysp
+
+namespace ysp {
+// kernels_dlc_tc.cu -- decoder stage on tcgen05 (bf16 mode): see the file header
+struct DlcTcP {
+  const void* x;            // low-res NHWC bf16 [N, h, w, Cin] (pixel stride x_cs)
+  void* out;                // HEAD: fp32 [N, 2h, 2w]; else NHWC bf16 [N, 2h, 2w, C] (pixel stride out_cs)
+  const uint8_t* wpack;     // dlc_tc_prepare_kernel output
+  const float* bo;          // head bias (device) or NULL
+  int N, h, w, Cin, C, x_cs, out_cs;
+};
+struct DlcTcPrep {          // fp32 folded weights in the engine's layouts ([K][ld] dense, [9][C] depthwise)
+  const float *w1, *c1, *dw1, *b1, *w2, *c2, *dw2, *b3, *wr, *cr, *wo;
+  int w1ld, w2ld, wrld, wold, Cin, C;
+};
+size_t dlc_tc_pack_bytes(int Cin, int C);
+void launch_dlc_tc_prepare(const DlcTcPrep& q, void* out, cudaStream_t s);
+bool dlc_tc_supported(int Cin, int C, bool head);
+void launch_dlc_tc(const DlcTcP& p, cudaStream_t s);
+}  // namespace ysp
