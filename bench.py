@@ -289,6 +289,8 @@ def main_ours(args):
             ach = flops_per_launch / per_launch_ms / 1e9
             roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": traffic}
         roof.update({"kernel": dom["name"], "kind": dom["kind"], "us_per_launch": per_launch_ms * 1e3,
+                     "algorithmic_intensity_flop_per_byte": intensity,
+                     "note": "bytes/flops are the reference algorithm's (SURVEY 8d), not what the kernel executes; the fused decoder kernels are bound by shared-memory operand traffic and CUDA-core issue, not by HBM or the tensor pipe",
                      "share_of_step": dom["ms"] / tot, "peak_source": peaks["src"],
                      "pipeline_tensor_frac": value / world * GFLOP_PER_SLICE * 1e9 / (peaks["bf16_tflops_sustained"] * 1e12),
                      "pipeline_hbm_frac_compulsory": value / world * IO_BYTES_PER_SLICE["fp32_in"] / (peaks["hbm_gbs"] * 1e9)})

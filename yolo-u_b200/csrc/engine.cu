@@ -577,8 +577,10 @@ struct Builder {
       r.x = pl->ptr(c, xlow); r.out = pl->ptr(c, out);
       launch_dlc_tc(r, c.s);
     }, {&xlow, &out}, 1,
+    // ALGORITHMIC flops of the reference stage (two hi-res 1x1 convs on up(x), two depthwise 3x3, one 1x1, head), not the
+    // 9x larger dense-equivalent count the composite tensor-core convs execute
     StepInfo{p + ".tc", "dlc_tc", tbytes(xlow) + (head ? hi * 4 : tbytes(out)),
-             2.0 * hi * (9.0 * Cin * C + 9.0 * C * C + (double)Cin * C + (head ? C : 0)), 1});
+             2.0 * hi * (2.0 * Cin * C + 18.0 * C + (double)C * C + (head ? C : 0)), 1});
     return true;
   }
 
