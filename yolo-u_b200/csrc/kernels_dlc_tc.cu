@@ -81,8 +81,10 @@ __device__ __forceinline__ uint4 lerp8(const uint4& a, __nv_bfloat162 wa, const 
 
 }  // namespace
 
+constexpr int kDlcThreads = 320;            // warps 0-7: CUDA-core phases + epilogues; warps 8-9: MMA issue
+
 template <int CIN, int C, bool HEAD>
-__global__ void __launch_bounds__(256, C <= 16 ? 2 : 1) dlc_tc_kernel(DlcTcP p) {
+__global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(DlcTcP p) {
   constexpr int KP1 = CIN / 8, KP2 = C / 8;          // 8-channel planes of u and of b
   constexpr int W1B = 9 * KP1 * C * 16, W2B = 9 * KP2 * C * 16, WRB = KP1 * C * 16;
   extern __shared__ __align__(128) uint8_t dsm[];
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(256, C <= 16 ? 2 : 1) dlc_tc_kernel(DlcTcP p) 
   float* sBe2 = sBe1 + 9 * C;                        // [9][C]
   float* sCr = sBe2 + 9 * C;                         // [C] residual bias
   float* sWo = sCr + C;                              // [C] head weights
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar1[4], bar2[4];   // per column block: conv1(+residual) done / conv2 done
   __shared__ uint32_t tmem_s;
   // TMEM columns: D1[h][r] (h = column block, r = tap row: three independent accumulation chains, summed in the epilogue --
   // a chain of tiny dependent MMAs costs ~190 cycles per link) at (3h + r) * C, re-used for D2[h][r]; Dr[h] at (12 + h) * C
@@ -108,7 +110,10 @@ __global__ void __launch_bounds__(256, C <= 16 ? 2 : 1) dlc_tc_kernel(DlcTcP p) 
 
   // ---- prologue: constants only (overlaps the previous kernel under PDL) ----
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(s32(&bar)));   // 4 MMA-issuing threads commit per phase
+    for (int i = 0; i < 4; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar1[i])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar2[i])));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -119,9 +124,9 @@ __global__ void __launch_bounds__(256, C <= 16 ? 2 : 1) dlc_tc_kernel(DlcTcP p) 
   {
     const uint4* g1 = reinterpret_cast<const uint4*>(p.wpack);
     uint4* d1 = reinterpret_cast<uint4*>(sW1);
-    for (int i = tid; i < (W1B + W2B + WRB) / 16; i += 256) d1[i] = g1[i];
+    for (int i = tid; i < (W1B + W2B + WRB) / 16; i += kDlcThreads) d1[i] = g1[i];
     const float* gb = reinterpret_cast<const float*>(p.wpack + W1B + W2B + WRB);
-    for (int i = tid; i < 18 * C + 2 * C; i += 256) sBe1[i] = gb[i];
+    for (int i = tid; i < 18 * C + 2 * C; i += kDlcThreads) sBe1[i] = gb[i];
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(256, C <= 16 ? 2 : 1) dlc_tc_kernel(DlcTcP p) 
     const int n = t / tiles_y;
     const int px0 = tx * TW / 2 - 2, py0 = ty * TH / 2 - 2;
     const bf16* xg = reinterpret_cast<const bf16*>(p.x);
-    for (int i = tid; i < XR * XC * KP1; i += 256) {
+    for (int i = tid; i < XR * XC * KP1; i += kDlcThreads) {
       const int kc = i % KP1, pp = i / KP1;
       const int gx = min(max(px0 + pp % XC, 0), p.w - 1), gy = min(max(py0 + pp / XC, 0), p.h - 1);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s32(sX + (pp * CIN + kc * 8) * 2)),
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(256, C <= 16 ? 2 : 1) dlc_tc_kernel(DlcTcP p) 
   };
   prefetch_x(blockIdx.x);
   // persistent CTA: weights, TMEM and the barrier are set up once; tiles are strided over the grid
+  uint32_t tpar = 0;                                                   // mbarrier phase parity: every barrier completes once per tile
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
   int t = tile;
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(256, C <= 16 ? 2 : 1) dlc_tc_kernel(DlcTcP p) 
   // ---- phase 1: u = up2(x) on the 18 x 34 tile, one thread per (2x2 hi-res block, 8 channels); zero outside the image ----
   {
     const __nv_bfloat162 q25 = __floats2bfloat162_rn(0.25f, 0.25f), q75 = __floats2bfloat162_rn(0.75f, 0.75f);
-    for (int i = tid; i < (AR / 2) * (AP / 2) * KP1; i += 256) {
+    for (int i = tid; i < (AR / 2) * (AP / 2) * KP1; i += kDlcThreads) {
       const int kc = i % KP1, bb = i / KP1;
       const int bi = bb / (AP / 2), bj = bb % (AP / 2);
       const int li = bi + 1, lj = bj + 1;
@@ -193,35 +199,39 @@ __global__ void __launch_bounds__(256, C <= 16 ? 2 : 1) dlc_tc_kernel(DlcTcP p) 
   __syncthreads();
   prefetch_x(tile + gridDim.x);                                      // sX is free until the next tile's phase 1
 
-  // ---- phase 2: conv1 (D1[h], h = 8-pixel column block of the 16 x 32 b region) and the residual 1x1 (Dr[h]).
-  //      One issuing thread per column block (lane 0 of warps 0..3); all descriptors are base + compile-time offset. ----
-  if (lane == 0 && warp < 4) {
-    const int h = warp;
-    const uint32_t a_lo = ((s32(sU) & 0x3FFFF) >> 4) + (uint32_t)(8 * h) + (((uint32_t)PLANE >> 4) << 16);
-    const uint32_t w_lo = ((s32(sW1) & 0x3FFFF) >> 4) + (((uint32_t)(C * 16) >> 4) << 16);
-    const uint32_t r_lo = ((s32(sWr) & 0x3FFFF) >> 4) + (((uint32_t)(C * 16) >> 4) << 16);
+  // ---- phase 2: conv1 (D1[h][r], h = 8-pixel column block of the 16 x 32 b region) and the residual 1x1 (Dr[h]),
+  //      issued block by block by warp 8 with one commit per block, so the epilogue of block h (warps 0-7 below)
+  //      overlaps the MMAs of blocks h+1..  All descriptors are base + compile-time offset. ----
+  constexpr int ISSUERS = C <= 16 ? 1 : 2;            // wide layers need two issuing threads to keep the tensor pipe fed
+  if (warp >= 8 && warp < 8 + ISSUERS && lane == 0) {
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
+    for (int h = warp - 8; h < 4; h += ISSUERS) {
+      const uint32_t a_lo = ((s32(sU) & 0x3FFFF) >> 4) + (uint32_t)(8 * h) + (((uint32_t)PLANE >> 4) << 16);
+      const uint32_t w_lo = ((s32(sW1) & 0x3FFFF) >> 4) + (((uint32_t)(C * 16) >> 4) << 16);
+      const uint32_t r_lo = ((s32(sWr) & 0x3FFFF) >> 4) + (((uint32_t)(C * 16) >> 4) << 16);
 #pragma unroll
-      for (int ks = 0; ks < CIN / 16; ++ks)
-        umma2(tmem + (3 * h + tap / 3) * C, a_lo + (((2 * ks) * PLANE) >> 4) + (tap / 3) * AP + (tap % 3), a_hi,
-              w_lo + (((tap * KP1 + 2 * ks) * C * 16) >> 4), b_hi, idesc, ((tap % 3) | ks) != 0);
+      for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+        for (int ks = 0; ks < CIN / 16; ++ks)
+          umma2(tmem + (3 * h + tap / 3) * C, a_lo + (((2 * ks) * PLANE) >> 4) + (tap / 3) * AP + (tap % 3), a_hi,
+                w_lo + (((tap * KP1 + 2 * ks) * C * 16) >> 4), b_hi, idesc, ((tap % 3) | ks) != 0);
+      }
+#pragma unroll
+      for (int ks = 0; ks < CIN / 16; ++ks)            // residual: output pixel (oy, ox) <-> u(oy + 2, ox + 2)
+        umma2(tmem + (12 + h) * C, a_lo + (((2 * ks) * PLANE) >> 4) + 2 * AP + 2, a_hi, r_lo + (((2 * ks) * C * 16) >> 4), b_hi, idesc, ks != 0);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar1[h])) : "memory");
     }
-#pragma unroll
-    for (int ks = 0; ks < CIN / 16; ++ks)            // residual: output pixel (oy, ox) <-> u(oy + 2, ox + 2)
-      umma2(tmem + (12 + h) * C, a_lo + (((2 * ks) * PLANE) >> 4) + 2 * AP + 2, a_hi, r_lo + (((2 * ks) * C * 16) >> 4), b_hi, idesc, ks != 0);
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar)) : "memory");
   }
-  mbar_wait_parity(&bar, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---- phase 3: epilogue 1: b = SiLU(D1 + bias_eff1), zero outside the image, bf16 into the b tile ----
   const int q = warp & 3;                             // TMEM lane quarter this warp may read
   const int row = q * 32 + lane;                      // M row: (by = row / 8, bxl = row % 8)
   const int by = row >> 3, bxl = row & 7;
 #pragma unroll 1
-  for (int hh = 0; hh < 2; ++hh) {
-    const int h = (warp >> 2) * 2 + hh;
+  for (int hh = 0; hh < 2 && warp < 8; ++hh) {
+    const int h = (warp >> 2) + 2 * hh;               // blocks complete in order 0,1,2,3: warps 0-3 take 0 and 2, warps 4-7 take 1 and 3
+    mbar_wait_parity(&bar1[h], tpar);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int bx = 8 * h + bxl;
     const int Y = Y0 - 1 + by, X = X0 - 1 + bx;
     const bool inside = Y >= 0 && Y < H && X >= 0 && X < W;
@@ -253,29 +263,31 @@ __global__ void __launch_bounds__(256, C <= 16 ? 2 : 1) dlc_tc_kernel(DlcTcP p) 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
 
-  // ---- phase 4: conv2 on the b tile: D2[h], output pixel (oy, 8h + oxl) <-> b(oy + r, 8h + oxl + s) ----
-  if (lane == 0 && warp < 4) {
+  // ---- phase 4: conv2 on the b tile: D2[h][r], output pixel (oy, 8h + oxl) <-> b(oy + r, 8h + oxl + s) ----
+  if (warp >= 8 && warp < 8 + ISSUERS && lane == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int h = warp;
-    const uint32_t a_lo = ((s32(sB) & 0x3FFFF) >> 4) + (uint32_t)(8 * h) + (((uint32_t)PLANE >> 4) << 16);
-    const uint32_t w_lo = ((s32(sW2) & 0x3FFFF) >> 4) + (((uint32_t)(C * 16) >> 4) << 16);
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
+    for (int h = warp - 8; h < 4; h += ISSUERS) {
+      const uint32_t a_lo = ((s32(sB) & 0x3FFFF) >> 4) + (uint32_t)(8 * h) + (((uint32_t)PLANE >> 4) << 16);
+      const uint32_t w_lo = ((s32(sW2) & 0x3FFFF) >> 4) + (((uint32_t)(C * 16) >> 4) << 16);
 #pragma unroll
-      for (int ks = 0; ks < C / 16; ++ks)
-        umma2(tmem + (3 * h + tap / 3) * C, a_lo + (((2 * ks) * PLANE) >> 4) + (tap / 3) * AP + (tap % 3), a_hi,
-              w_lo + (((tap * KP2 + 2 * ks) * C * 16) >> 4), b_hi, idesc, ((tap % 3) | ks) != 0);
+      for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+        for (int ks = 0; ks < C / 16; ++ks)
+          umma2(tmem + (3 * h + tap / 3) * C, a_lo + (((2 * ks) * PLANE) >> 4) + (tap / 3) * AP + (tap % 3), a_hi,
+                w_lo + (((tap * KP2 + 2 * ks) * C * 16) >> 4), b_hi, idesc, ((tap % 3) | ks) != 0);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar2[h])) : "memory");
     }
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar)) : "memory");
   }
-  mbar_wait_parity(&bar, 1);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---- phase 5: epilogue 2: out = SiLU(D2 + bias_eff2) + Dr + cr;  head: logit = wo . out + bo ----
   const int oy = by, oxl = bxl;
 #pragma unroll 1
-  for (int hh = 0; hh < 2; ++hh) {
-    const int h = (warp >> 2) * 2 + hh;
+  for (int hh = 0; hh < 2 && warp < 8; ++hh) {
+    const int h = (warp >> 2) + 2 * hh;
+    mbar_wait_parity(&bar2[h], tpar);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int ox = 8 * h + oxl;
     const int Y = Y0 + oy, X = X0 + ox;
     const bool valid = oy < TH && ox < TW && Y < H && X < W;
@@ -315,6 +327,7 @@ __global__ void __launch_bounds__(256, C <= 16 ? 2 : 1) dlc_tc_kernel(DlcTcP p) 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  tpar ^= 1;
   }  // tile loop
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -387,7 +400,7 @@ static void dlc_tc_launch(const DlcTcP& p, cudaStream_t s) {
   static int sms = 0;
   if (!sms) { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d); if (sms <= 0) sms = 148; }
   const int ctas = (C <= 16 ? 2 : 1) * sms;
-  launch_pdl(dlc_tc_kernel<CIN, C, HEAD>, dim3(tiles < ctas ? tiles : ctas), dim3(256), smem, s, p);
+  launch_pdl(dlc_tc_kernel<CIN, C, HEAD>, dim3(tiles < ctas ? tiles : ctas), dim3(kDlcThreads), smem, s, p);
 }
 
 void launch_dlc_tc(const DlcTcP& p, cudaStream_t s) {
