@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
   // ---- phase 1: u = up2(x) on the 18 x 34 tile, one thread per (2x2 hi-res block, 8 channels); zero outside the image ----
   {
     const __nv_bfloat162 q25 = __floats2bfloat162_rn(0.25f, 0.25f), q75 = __floats2bfloat162_rn(0.75f, 0.75f);
+#pragma unroll 2
     for (int i = tid; i < (AR / 2) * (AP / 2) * KP1; i += kDlcThreads) {
       const int kc = i % KP1, bb = i / KP1;
       const int bi = bb / (AP / 2), bj = bb % (AP / 2);
