@@ -128,6 +128,42 @@ typedef struct ysp_pipeline_io {
 int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, void* d_ws, size_t ws_bytes,
                  void* stream);
 
+/* -- seg-head training step (reference train.py:241-360, non-AMP branch) -------------------------
+ * Trainable = everything of YOLOSegPlusPlus outside `encoder.*` and the unused `param` scalar (train.py:256-267).
+ * The trainer owns no tensors: the caller (yolo_u_b200/trainer.py) allocates flat fp32 DEVICE buffers
+ *   params / grads / adam_m / adam_v  [ysp_train_param_count]   and   stats (BN running mean/var) [ysp_train_stat_count]
+ * whose sub-tensors are named by the reference's state_dict keys in PyTorch's own layouts (ysp_train_tensor_info), so
+ * a `best.pth` (train.py:428) round-trips by plain slicing, and `grads` can be all-reduced with ONE collective. */
+typedef struct ysp_trainer ysp_trainer;
+int ysp_train_create(ysp_trainer** out, int device, int B, int H, int W);
+void ysp_train_destroy(ysp_trainer* t);
+int ysp_train_num_tensors(const ysp_trainer* t);
+/* kind 0 = parameter (offset into params/grads/adam buffers), 1 = BN running statistic (offset into stats) */
+int ysp_train_tensor_info(const ysp_trainer* t, int i, char* name, int name_cap, int* kind, int64_t* offset,
+                          int64_t* numel);
+int64_t ysp_train_param_count(const ysp_trainer* t);
+int64_t ysp_train_stat_count(const ysp_trainer* t);
+size_t ysp_train_workspace_bytes(const ysp_trainer* t);
+int ysp_train_last_launch_count(const ysp_trainer* t);
+/* frozen encoder (YOLOSegPlusPlus.py:255-259) through the inference engine: x [B,4,H,W] fp32 ->
+ * skipA [B,H/4,W/4,64], skipB [B,H/8,W/8,128] dense NHWC fp32.  Workspace: ysp_workspace_bytes. */
+int ysp_encoder_forward(ysp_handle* h, const float* d_x, float* d_skipA, float* d_skipB, int B, int H, int W, void* d_ws,
+                        size_t ws_bytes, void* stream);
+/* optimizer.zero_grad(); pred = decoder(skips, logits) in train() mode (BN batch statistics; running statistics in
+ * `d_stats` updated with `momentum` unless d_stats is NULL); loss = monai DiceLoss(sigmoid, soft_label, batch=True)
+ * (loss_kind 0, train.py:98-104) or Dice + mean BCE-with-logits (loss_kind 1); loss.backward() -> d_grads, every
+ * gradient multiplied by grad_scale (AMP loss scale / 1 / 1/world_size).  d_loss3 = {total, dice, bce}.
+ * d_mask_logits (optional) receives pred [B,1,H,W].  d_logits [B,1,H/8,W/8], d_target [B,1,H,W]. */
+int ysp_train_step(ysp_trainer* t, const float* d_skipA, const float* d_skipB, const float* d_logits,
+                   const float* d_target, const float* d_params, float* d_grads, float* d_stats, float momentum,
+                   int loss_kind, float grad_scale, float* d_loss3, float* d_mask_logits, void* d_ws, size_t ws_bytes,
+                   void* stream);
+/* torch.optim.AdamW step over a flat buffer (train.py:262, :325): grads are multiplied by grad_scale first; max_norm > 0
+ * applies clip_grad_norm_ semantics (train.py:324 -- a no-op in the reference, its parameter generator is already
+ * exhausted; so callers pass 0).  d_ws8 = 8 bytes of device scratch (only read when clipping). */
+int ysp_adamw(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n, float lr, float beta1, float beta2,
+              float eps, float weight_decay, int step, float grad_scale, float max_norm, void* d_ws8, void* stream);
+
 /* -- introspection (tests / profiling) ---------------------------------------------------------------------------- */
 /* keep every intermediate alive (no workspace reuse) so ysp_debug_tensor can read them; affects plans built later */
 int ysp_set_keep_intermediates(ysp_handle* h, int on);

@@ -42,6 +42,17 @@ PROTOTYPES = {
     "ysp_objectmap_transform": (i32, [vp, vp, i32, i32, vp]),
     "ysp_scale_boxes": (i32, [vp, C.c_longlong, i32, f32, f32, f32, f32, f32, vp]),
     "ysp_pipeline": (i32, [vp, C.POINTER(PipelineIO), i32, i32, i32, vp, sz, vp]),
+    "ysp_train_create": (i32, [C.POINTER(vp), i32, i32, i32, i32]),
+    "ysp_train_destroy": (None, [vp]),
+    "ysp_train_num_tensors": (i32, [vp]),
+    "ysp_train_tensor_info": (i32, [vp, i32, C.c_char_p, i32, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]),
+    "ysp_train_param_count": (i64, [vp]),
+    "ysp_train_stat_count": (i64, [vp]),
+    "ysp_train_workspace_bytes": (sz, [vp]),
+    "ysp_train_last_launch_count": (i32, [vp]),
+    "ysp_encoder_forward": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]),
+    "ysp_train_step": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, f32, vp, vp, vp, sz, vp]),
+    "ysp_adamw": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, f32, vp, vp]),
     "ysp_last_launch_count": (i32, [vp]),
     "ysp_set_keep_intermediates": (i32, [vp, i32]),
     "ysp_profile": (i32, [vp, i32]),

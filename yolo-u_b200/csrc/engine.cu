@@ -21,6 +21,7 @@
 
 #include "../../include/ysp.h"
 #include "kernels.h"
+#include "kernels_train.h"
 
 using namespace ysp;
 
@@ -29,6 +30,7 @@ static int fail(int code, const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
   return code;
 }
+namespace ysp { void set_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); } }   // train.cu
 #define CUDA_OK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(YSP_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
 
 namespace {
@@ -1010,6 +1012,33 @@ int ysp_segpp_forward(ysp_handle* h, const float* d_x, const float* d_logits, fl
   c.ext[X_IMG] = (void*)d_x; c.ext[X_LOGITS] = (void*)d_logits; c.ext[X_OUT] = d_out;
   h->last_launches = 0;
   return run_plan(h, p, c);
+}
+
+// Frozen encoder only (YOLOSegPlusPlus.py:255-259): runs the seg plan up to the first decoder step and hands the two
+// skips to the caller as dense NHWC fp32 -- the input of the training step (train.cu).
+int ysp_encoder_forward(ysp_handle* h, const float* d_x, float* d_skipA, float* d_skipB, int B, int H, int W, void* d_ws,
+                        size_t ws_bytes, void* stream) {
+  int rc = check_device(h);
+  if (rc) return rc;
+  if (!h->seg_ready) return fail(YSP_ESTATE, "seg head weights not finalized");
+  if (!d_x || !d_skipA || !d_skipB || B <= 0) return fail(YSP_EINVAL, "ysp_encoder_forward: bad arguments");
+  if (H % 8 || W % 8 || H <= 0 || W <= 0) return fail(YSP_EINVAL, "H and W must be positive multiples of 8 (got %dx%d)", H, W);
+  Plan* p = nullptr;
+  if ((rc = get_plan(h, "seg", B, H, W, &p))) return rc;
+  if (ws_bytes < p->ws_bytes || !d_ws) return fail(YSP_ESTATE, "workspace too small: need %zu bytes, got %zu", p->ws_bytes, ws_bytes);
+  RunCtx c = {};
+  c.ws = (char*)d_ws; c.s = (cudaStream_t)stream;
+  c.ext[X_IMG] = (void*)d_x;
+  h->last_launches = 0;
+  if ((rc = run_plan(h, p, c, 0, p->split, 0))) return rc;
+  auto a = p->named.find("seg:encoder.2"), b = p->named.find("seg:encoder.4");
+  if (a == p->named.end() || b == p->named.end()) return fail(YSP_ESTATE, "ysp_encoder_forward: skips not found in the plan");
+  const TRef &ta = a->second, &tb = b->second;
+  launch_export_view(p->ptr(c, ta), ta.cs, ta.dt, d_skipA, ta.C, (long long)ta.N * ta.H * ta.W, c.s);
+  launch_export_view(p->ptr(c, tb), tb.cs, tb.dt, d_skipB, tb.C, (long long)tb.N * tb.H * tb.W, c.s);
+  h->last_launches += 2;
+  CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 size_t ysp_nms_workspace_bytes(int B, int C, int A, int max_det) { return nms_workspace_bytes(B, C, A, max_det); }

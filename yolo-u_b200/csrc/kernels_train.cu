@@ -1,0 +1,743 @@
+// kernels_train.cu -- fp32 CUDA-core kernels of the seg-head TRAINING step (BASELINE cfg 4).
+//
+// The trainable part of YOLO-Seg++ is the 63.8 K-parameter decoder (reference train.py:256-267 excludes `encoder.*`),
+// run in train() mode: every ultralytics Conv is conv(no bias) -> BatchNorm2d with BATCH statistics -> SiLU/identity.
+// The work is HBM-bound (full-resolution activations, channel counts 8..129), so these are coalesced NHWC kernels:
+//   pw_gemm / pw_wgrad          1x1 convs: forward, input-gradient (same kernel, transposed weight view), weight-gradient
+//   dw_conv / dw_wgrad          depthwise k x k: forward, input-gradient (flipped taps), weight-gradient
+//   col_reduce<MODE>            per-channel double-precision reductions: BN statistics, BN backward sums, bias
+//                               gradients, ECA pooling and its backward
+//   bn_finalize / bn_apply / bn_bwd_apply, up2 / up2_bwd (bilinear, align_corners=False), ECA gate fwd/bwd,
+//   Dice(+BCE) loss fwd/bwd (monai DiceLoss(sigmoid, soft_label, batch=True), train.py:98-104), AdamW.
+// Weights stay in PyTorch's own layouts ([Cout][Cin] and [C][k*k]) so the flat parameter buffer IS the state_dict.
+#include <algorithm>
+#include <cmath>
+
+#include "kernels.h"
+#include "kernels_train.h"
+
+namespace ysp {
+
+static inline int cdivl(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// =====================================================================================================================
+// C[m][j] = beta*C[m][j] + bias[j] + sum_i A[m][i] * Wop(i,j)      Wop(i,j) = trans ? W[i*ldw + j] : W[j*ldw + i]
+//   forward 1x1 conv:   i = ci, j = co, trans = 0 (W = [Cout][Cin]);   input gradient: i = co, j = ci, trans = 1.
+// Thread micro-tile 4x4; BN in {16,32,64} columns per CTA and 4*(256/(BN/4)) rows, so narrow outputs waste nothing.
+// =====================================================================================================================
+template <int BN>
+__global__ void __launch_bounds__(256) pw_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
+                                                      int ldw, int trans, const float* __restrict__ bias, float* C,
+                                                      int ldc, long long M, int I, int J, int beta) {
+  constexpr int BK = 16, TX = BN / 4, TY = 256 / TX, BM = TY * 4;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int j0 = blockIdx.y * BN;
+  float acc[4][4] = {};
+  for (int i0 = 0; i0 < I; i0 += BK) {
+    for (int e = tid; e < BM * BK; e += 256) {
+      int r = e / BK, i = e % BK;
+      long long m = m0 + r;
+      As[i][r] = (m < M && i0 + i < I) ? A[m * lda + i0 + i] : 0.f;
+    }
+    for (int e = tid; e < BK * BN; e += 256) {
+      int i = e / BN, j = e % BN;
+      int ig = i0 + i, jg = j0 + j;
+      Bs[i][j] = (ig < I && jg < J) ? (trans ? W[(size_t)ig * ldw + jg] : W[(size_t)jg * ldw + ig]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    long long m = m0 + ty * 4 + r;
+    if (m >= M) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int j = j0 + tx * 4 + c;
+      if (j >= J) continue;
+      float v = acc[r][c] + (bias ? bias[j] : 0.f);
+      float* o = C + m * ldc + j;
+      *o = beta ? *o + v : v;
+    }
+  }
+}
+
+void launch_pw_gemm(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc,
+                    long long M, int I, int J, int beta, cudaStream_t s) {
+  if (J <= 16) {
+    pw_gemm_kernel<16><<<dim3(cdivl(M, 256), cdivl(J, 16)), 256, 0, s>>>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta);
+  } else if (J <= 32) {
+    pw_gemm_kernel<32><<<dim3(cdivl(M, 128), cdivl(J, 32)), 256, 0, s>>>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta);
+  } else {
+    pw_gemm_kernel<64><<<dim3(cdivl(M, 64), cdivl(J, 64)), 256, 0, s>>>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta);
+  }
+}
+
+// =====================================================================================================================
+// dW[j][i] += sum_m D[m][j] * X[m][i]   (weight gradient of a 1x1 conv; dW in PyTorch layout, ld = I)
+// CTA = one (TJ x TI) tile of dW and one chunk of rows; the 256 threads form G = 256/((TJ/4)(TI/4)) row groups, each
+// with a 4x4 micro-tile; groups combine through shared-memory atomics, CTAs through global atomics (dW pre-zeroed).
+// =====================================================================================================================
+template <int TJ, int TI>
+__global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__ D, int ldd, const float* __restrict__ X,
+                                                       int ldx, float* dW, int ldw, long long M, int I, int J,
+                                                       int rows_per_cta) {
+  constexpr int TPG = (TJ / 4) * (TI / 4), G = 256 / TPG, RS = 32;     // RS rows staged per pass
+  __shared__ __align__(16) float sD[RS][TJ + 4];
+  __shared__ __align__(16) float sX[RS][TI + 4];
+  __shared__ float sAcc[TJ * TI];
+  const int tid = threadIdx.x, g = tid / TPG, t = tid % TPG;
+  const int tj = t / (TI / 4), ti = t % (TI / 4);
+  const int j0 = blockIdx.y * TJ, i0 = blockIdx.z * TI;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = (r0 + rows_per_cta < M) ? r0 + rows_per_cta : M;
+  for (int e = tid; e < TJ * TI; e += 256) sAcc[e] = 0.f;
+  __syncthreads();
+  float acc[4][4] = {};
+  for (long long rb = r0; rb < r1; rb += RS) {
+    __syncthreads();
+    for (int e = tid; e < RS * TJ; e += 256) {
+      int r = e / TJ, j = e % TJ;
+      sD[r][j] = (rb + r < r1 && j0 + j < J) ? D[(rb + r) * ldd + j0 + j] : 0.f;
+    }
+    for (int e = tid; e < RS * TI; e += 256) {
+      int r = e / TI, i = e % TI;
+      sX[r][i] = (rb + r < r1 && i0 + i < I) ? X[(rb + r) * ldx + i0 + i] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = g; r < RS; r += G) {
+      float4 d = *reinterpret_cast<const float4*>(&sD[r][tj * 4]);
+      float4 x = *reinterpret_cast<const float4*>(&sX[r][ti * 4]);
+      const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) atomicAdd(&sAcc[(tj * 4 + a) * TI + ti * 4 + b], acc[a][b]);
+  __syncthreads();
+  for (int e = tid; e < TJ * TI; e += 256) {
+    int j = j0 + e / TI, i = i0 + e % TI;
+    if (j < J && i < I) atomicAdd(&dW[(size_t)j * ldw + i], sAcc[e]);
+  }
+}
+
+template <int TJ, int TI>
+static void pw_wgrad_launch(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I,
+                            int J, cudaStream_t s) {
+  int tiles = cdivl(J, TJ) * cdivl(I, TI);
+  long long want = (148 * 4 + tiles - 1) / tiles;                       // ~4 CTAs per SM in total
+  long long rows = (M + want - 1) / want;
+  rows = ((rows + 31) / 32) * 32;
+  if (rows < 256) rows = 256;
+  pw_wgrad_kernel<TJ, TI><<<dim3(cdivl(M, rows), cdivl(J, TJ), cdivl(I, TI)), 256, 0, s>>>(D, ldd, X, ldx, dW, ldw, M, I,
+                                                                                          J, (int)rows);
+}
+
+void launch_pw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I, int J,
+                     cudaStream_t s) {
+  const int cj = J <= 16 ? 16 : J <= 32 ? 32 : 64, ci = I <= 16 ? 16 : I <= 32 ? 32 : 64;
+#define YSP_WG(a, b) if (cj == a && ci == b) return pw_wgrad_launch<a, b>(D, ldd, X, ldx, dW, ldw, M, I, J, s)
+  YSP_WG(16, 16); YSP_WG(16, 32); YSP_WG(16, 64); YSP_WG(32, 16); YSP_WG(32, 32); YSP_WG(32, 64);
+  YSP_WG(64, 16); YSP_WG(64, 32); YSP_WG(64, 64);
+#undef YSP_WG
+}
+
+// =====================================================================================================================
+// Depthwise k x k, stride 1, "same" padding, weights [C][k*k] (PyTorch [C,1,k,k]).  flip = 1 gives the input gradient.
+// One thread = one pixel x 4 channels (float4); taps staged transposed in shared memory.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) dw_conv_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
+                                                      float* Y, int ldy, int N, int H, int Wd, int C, int k, int flip,
+                                                      int beta) {
+  extern __shared__ float sW[];   // [k*k][C]
+  const int kk = k * k;
+  for (int e = threadIdx.x; e < kk * C; e += 256) {
+    int c = e / kk, tp = e % kk;
+    sW[(flip ? kk - 1 - tp : tp) * C + c] = W[e];
+  }
+  __syncthreads();
+  const int Q = C >> 2, pad = k >> 1;
+  const long long total = (long long)N * H * Wd * Q;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    int q = (int)(e % Q);
+    long long pix = e / Q;
+    int x = (int)(pix % Wd);
+    long long t = pix / Wd;
+    int y = (int)(t % H);
+    long long n = t / H;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < k; ++r) {
+      int iy = y + r - pad;
+      if (iy < 0 || iy >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        int ix = x + s - pad;
+        if (ix < 0 || ix >= Wd) continue;
+        float4 v = *reinterpret_cast<const float4*>(X + ((n * H + iy) * Wd + ix) * ldx + q * 4);
+        float4 w = *reinterpret_cast<const float4*>(sW + (r * k + s) * C + q * 4);
+        acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y);
+        acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w);
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(Y + pix * ldy + q * 4);
+    if (beta) { float4 p = *o; acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w; }
+    *o = acc;
+  }
+}
+
+void launch_dw_conv(const float* X, int ldx, const float* W, float* Y, int ldy, int N, int H, int Wd, int C, int k,
+                    int flip, int beta, cudaStream_t s) {
+  long long total = (long long)N * H * Wd * (C / 4);
+  int grid = (int)std::min<long long>(cdivl(total, 256), 148 * 16);
+  dw_conv_kernel<<<grid, 256, (size_t)k * k * C * 4, s>>>(X, ldx, W, Y, ldy, N, H, Wd, C, k, flip, beta);
+}
+
+// dW[c][tap] += sum_{n,y,x} D[n,y,x,c] * X[n, y+r-pad, x+s-pad, c]
+template <int K>
+__global__ void __launch_bounds__(256) dw_wgrad_kernel(const float* __restrict__ D, int ldd, const float* __restrict__ X,
+                                                       int ldx, float* dW, int N, int H, int Wd, int C,
+                                                       long long pix_per_cta) {
+  constexpr int KK = K * K, PAD = K / 2;
+  extern __shared__ float sAcc[];   // [C][KK]
+  for (int e = threadIdx.x; e < C * KK; e += 256) sAcc[e] = 0.f;
+  __syncthreads();
+  const int Q = C >> 2, lanes = 256 / Q;
+  const int q = threadIdx.x % Q, lane = threadIdx.x / Q;
+  const long long total = (long long)N * H * Wd;
+  const long long p0 = (long long)blockIdx.x * pix_per_cta;
+  const long long p1 = (p0 + pix_per_cta < total) ? p0 + pix_per_cta : total;
+  float acc[KK][4];
+#pragma unroll
+  for (int tp = 0; tp < KK; ++tp) acc[tp][0] = acc[tp][1] = acc[tp][2] = acc[tp][3] = 0.f;
+  if (lane < lanes) {
+    for (long long pix = p0 + lane; pix < p1; pix += lanes) {
+      int x = (int)(pix % Wd);
+      long long t = pix / Wd;
+      int y = (int)(t % H);
+      long long n = t / H;
+      float4 d = *reinterpret_cast<const float4*>(D + pix * ldd + q * 4);
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        int iy = y + r - PAD;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+          int ix = x + s - PAD;
+          if (ix < 0 || ix >= Wd) continue;
+          float4 v = *reinterpret_cast<const float4*>(X + ((n * H + iy) * Wd + ix) * ldx + q * 4);
+          acc[r * K + s][0] = fmaf(d.x, v.x, acc[r * K + s][0]);
+          acc[r * K + s][1] = fmaf(d.y, v.y, acc[r * K + s][1]);
+          acc[r * K + s][2] = fmaf(d.z, v.z, acc[r * K + s][2]);
+          acc[r * K + s][3] = fmaf(d.w, v.w, acc[r * K + s][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int tp = 0; tp < KK; ++tp)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&sAcc[(q * 4 + j) * KK + tp], acc[tp][j]);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < C * KK; e += 256) atomicAdd(&dW[e], sAcc[e]);
+}
+
+void launch_dw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int N, int H, int Wd, int C, int k,
+                     cudaStream_t s) {
+  long long total = (long long)N * H * Wd;
+  long long per = std::max<long long>(cdivl(total, 148 * 4), 256);
+  int grid = cdivl(total, per);
+  size_t sm = (size_t)C * k * k * 4;
+  if (k == 3) dw_wgrad_kernel<3><<<grid, 256, sm, s>>>(D, ldd, X, ldx, dW, N, H, Wd, C, per);
+  else dw_wgrad_kernel<5><<<grid, 256, sm, s>>>(D, ldd, X, ldx, dW, N, H, Wd, C, per);
+}
+
+// =====================================================================================================================
+// Per-channel reductions in double precision.  sums layout: [segment][2][C]; segment = image (SEG=1) or whole batch.
+//   MODE 0  BN statistics:    v1 = z            v2 = z*z
+//   MODE 1  BN backward:      v1 = dt           v2 = dt*zhat     dt = dy * act'(gamma*zhat+beta)
+//   MODE 2  column sums:      v1 = a                              (bias gradients, ECA average pool)
+//   MODE 3  products:         v1 = a*b                            (ECA backward: d gate)
+// =====================================================================================================================
+__device__ __forceinline__ float silu_grad(float t) {
+  float sg = 1.f / (1.f + expf(-t));
+  return sg * (1.f + t * (1.f - sg));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bv,
+                                                         int ldb, BnRef bn, int act, double* sums, int C,
+                                                         long long rows_per_seg, long long rows_per_cta) {
+  extern __shared__ double sred[];   // [2][C]
+  for (int e = threadIdx.x; e < 2 * C; e += 256) sred[e] = 0.0;
+  __syncthreads();
+  const int Q = C >> 2, lanes = 256 / Q;
+  const int q = threadIdx.x % Q, lane = threadIdx.x / Q;
+  const long long seg = blockIdx.y;
+  const long long r0 = seg * rows_per_seg + (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > (seg + 1) * rows_per_seg) r1 = (seg + 1) * rows_per_seg;
+  if (lane < lanes) {
+    float mu[4], is[4], ga[4], be[4];
+    if (MODE == 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int c = q * 4 + j;
+        mu[j] = bn.mean[c]; is[j] = bn.invstd[c]; ga[j] = bn.gamma[c]; be[j] = bn.beta[c];
+      }
+    }
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    float f1[4] = {0, 0, 0, 0}, f2[4] = {0, 0, 0, 0};
+    int cnt = 0;
+    for (long long m = r0 + lane; m < r1; m += lanes) {
+      float4 a4 = *reinterpret_cast<const float4*>(A + m * lda + q * 4);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      float b[4] = {0, 0, 0, 0};
+      if (MODE == 1 || MODE == 3) {
+        float4 b4 = *reinterpret_cast<const float4*>(Bv + m * ldb + q * 4);
+        b[0] = b4.x; b[1] = b4.y; b[2] = b4.z; b[3] = b4.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (MODE == 0) { f1[j] += a[j]; f2[j] = fmaf(a[j], a[j], f2[j]); }
+        if (MODE == 1) {   // a = dy, b = z
+          float zh = (b[j] - mu[j]) * is[j];
+          float dt = act ? a[j] * silu_grad(fmaf(ga[j], zh, be[j])) : a[j];
+          f1[j] += dt; f2[j] = fmaf(dt, zh, f2[j]);
+        }
+        if (MODE == 2) f1[j] += a[j];
+        if (MODE == 3) f1[j] = fmaf(a[j], b[j], f1[j]);
+      }
+      if (++cnt == 16) {   // short fp32 runs, long double runs
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s1[j] += f1[j]; s2[j] += f2[j]; f1[j] = f2[j] = 0.f; }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&sred[q * 4 + j], s1[j] + (double)f1[j]);
+      if (MODE <= 1) atomicAdd(&sred[C + q * 4 + j], s2[j] + (double)f2[j]);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < (MODE <= 1 ? 2 : 1) * C; e += 256) atomicAdd(&sums[seg * 2 * C + e], sred[e]);
+}
+
+void launch_col_reduce(int mode, const float* A, int lda, const float* B, int ldb, const BnRef& bn, int act, double* sums,
+                       int C, long long segs, long long rows_per_seg, cudaStream_t s) {
+  long long want = std::max<long long>(1, (148 * 8) / segs);
+  long long per = std::max<long long>(cdivl(rows_per_seg, want), 64);
+  dim3 grid(cdivl(rows_per_seg, per), (unsigned)segs);
+  size_t sm = (size_t)2 * C * sizeof(double);
+  switch (mode) {
+    case 0: col_reduce_kernel<0><<<grid, 256, sm, s>>>(A, lda, B, ldb, bn, act, sums, C, rows_per_seg, per); break;
+    case 1: col_reduce_kernel<1><<<grid, 256, sm, s>>>(A, lda, B, ldb, bn, act, sums, C, rows_per_seg, per); break;
+    case 2: col_reduce_kernel<2><<<grid, 256, sm, s>>>(A, lda, B, ldb, bn, act, sums, C, rows_per_seg, per); break;
+    default: col_reduce_kernel<3><<<grid, 256, sm, s>>>(A, lda, B, ldb, bn, act, sums, C, rows_per_seg, per); break;
+  }
+}
+
+// BN: sums -> (mean, invstd) + running-statistics update (nn.BatchNorm2d train(): biased var normalises, unbiased var
+// goes into running_var).  One thread per channel.
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double M, float eps, float momentum,
+                                   float* mean, float* invstd, float* run_mean, float* run_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mu = sums[c] / M;
+  double var = sums[C + c] / M - mu * mu;
+  if (var < 0) var = 0;
+  mean[c] = (float)mu;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (run_mean) {
+    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)mu;
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(var * (M / (M > 1 ? M - 1 : 1)));
+  }
+}
+
+void launch_bn_finalize(const double* sums, int C, long long M, float eps, float momentum, float* mean, float* invstd,
+                        float* run_mean, float* run_var, cudaStream_t s) {
+  bn_finalize_kernel<<<cdivl(C, 128), 128, 0, s>>>(sums, C, (double)M, eps, momentum, mean, invstd, run_mean, run_var);
+}
+
+// y = act(gamma*(z-mean)*invstd + beta) (+ res)
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ Z, int ldz, BnRef bn, int act,
+                                                       const float* __restrict__ R, int ldr, float* Y, int ldy, int C,
+                                                       long long M) {
+  const int Q = C >> 2;
+  const long long total = M * Q;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    int q = (int)(e % Q);
+    long long m = e / Q;
+    float4 z4 = *reinterpret_cast<const float4*>(Z + m * ldz + q * 4);
+    float z[4] = {z4.x, z4.y, z4.z, z4.w}, r[4] = {0, 0, 0, 0}, o[4];
+    if (R) { float4 r4 = *reinterpret_cast<const float4*>(R + m * ldr + q * 4); r[0] = r4.x; r[1] = r4.y; r[2] = r4.z; r[3] = r4.w; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = q * 4 + j;
+      float t = fmaf(bn.gamma[c], (z[j] - bn.mean[c]) * bn.invstd[c], bn.beta[c]);
+      o[j] = (act ? t / (1.f + expf(-t)) : t) + r[j];
+    }
+    *reinterpret_cast<float4*>(Y + m * ldy + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+void launch_bn_apply(const float* Z, int ldz, const BnRef& bn, int act, const float* R, int ldr, float* Y, int ldy, int C,
+                     long long M, cudaStream_t s) {
+  int grid = (int)std::min<long long>(cdivl(M * (C / 4), 256), 148 * 16);
+  bn_apply_kernel<<<grid, 256, 0, s>>>(Z, ldz, bn, act, R, ldr, Y, ldy, C, M);
+}
+
+// dz = gamma*invstd*(dt - S1/M - zhat*S2/M);  block 0 also accumulates dgamma += S2, dbeta += S1.
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ DY, int ldd, const float* __restrict__ Z,
+                                                           int ldz, BnRef bn, int act, const double* __restrict__ sums,
+                                                           float* DZ, int ldo, float* dgamma, float* dbeta, int C,
+                                                           long long M) {
+  const int Q = C >> 2;
+  const long long total = M * Q;
+  const double invM = 1.0 / (double)M;
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < C; c += 256) { dbeta[c] += (float)sums[c]; dgamma[c] += (float)sums[C + c]; }
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    int q = (int)(e % Q);
+    long long m = e / Q;
+    float4 d4 = *reinterpret_cast<const float4*>(DY + m * ldd + q * 4);
+    float4 z4 = *reinterpret_cast<const float4*>(Z + m * ldz + q * 4);
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w}, z[4] = {z4.x, z4.y, z4.z, z4.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = q * 4 + j;
+      float zh = (z[j] - bn.mean[c]) * bn.invstd[c];
+      float dt = act ? d[j] * silu_grad(fmaf(bn.gamma[c], zh, bn.beta[c])) : d[j];
+      float m1 = (float)(sums[c] * invM), m2 = (float)(sums[C + c] * invM);
+      o[j] = bn.gamma[c] * bn.invstd[c] * (dt - m1 - zh * m2);
+    }
+    *reinterpret_cast<float4*>(DZ + m * ldo + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+void launch_bn_bwd_apply(const float* DY, int ldd, const float* Z, int ldz, const BnRef& bn, int act, const double* sums,
+                         float* DZ, int ldo, float* dgamma, float* dbeta, int C, long long M, cudaStream_t s) {
+  int grid = (int)std::min<long long>(cdivl(M * (C / 4), 256), 148 * 16);
+  bn_bwd_apply_kernel<<<grid, 256, 0, s>>>(DY, ldd, Z, ldz, bn, act, sums, DZ, ldo, dgamma, dbeta, C, M);
+}
+
+// g[j] += (float) sum_{f < fold} sums[j*fold + f]   (bias gradients from MODE-2 reductions; fold > 1 when a 1-channel
+// tensor was reduced as [M/fold][fold])
+__global__ void add_sums_kernel(const double* __restrict__ sums, float* g, int n, int fold) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = 0;
+  for (int f = 0; f < fold; ++f) a += sums[i * fold + f];
+  g[i] += (float)a;
+}
+void launch_add_sums(const double* sums, float* g, int n, int fold, cudaStream_t s) {
+  add_sums_kernel<<<cdivl(n, 128), 128, 0, s>>>(sums, g, n, fold);
+}
+
+// =====================================================================================================================
+// Elementwise helpers over [M][C] views (C % 4 == 0 unless noted)
+// =====================================================================================================================
+// out = a (+ b)   (scalar version: any C)
+__global__ void __launch_bounds__(256) add_copy_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B,
+                                                       int ldb, float* O, int ldo, int C, long long M) {
+  const long long total = M * C;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    int c = (int)(e % C);
+    long long m = e / C;
+    float v = A[m * lda + c];
+    if (B) v += B[m * ldb + c];
+    O[m * ldo + c] = v;
+  }
+}
+void launch_add_copy(const float* A, int lda, const float* B, int ldb, float* O, int ldo, int C, long long M, cudaStream_t s) {
+  int grid = (int)std::min<long long>(cdivl(M * C, 256), 148 * 16);
+  add_copy_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, O, ldo, C, M);
+}
+
+// torch Upsample(scale_factor=2, mode="bilinear", align_corners=False) (YOLOSegPlusPlus.py:155) and its adjoint.
+// 1-D taps: out[2j] = .25 in[j-1] + .75 in[j], out[2j+1] = .75 in[j] + .25 in[j+1], indices clamped at the border;
+// adjoint: din[j] = .25 do[2j-1] + .75 do[2j] + .75 do[2j+1] + .25 do[2j+2] with the OUTPUT indices clamped.
+__global__ void __launch_bounds__(256) up2_kernel(const float* __restrict__ X, int ldx, float* Y, int ldy, int N, int h,
+                                                  int w, int C) {
+  const int Q = C >> 2, H = 2 * h, Wd = 2 * w;
+  const long long total = (long long)N * H * Wd * Q;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    int q = (int)(e % Q);
+    long long pix = e / Q;
+    int ox = (int)(pix % Wd);
+    long long t = pix / Wd;
+    int oy = (int)(t % H);
+    long long n = t / H;
+    int jy = oy >> 1, jx = ox >> 1;
+    int y0 = (oy & 1) ? jy : max(jy - 1, 0), y1 = (oy & 1) ? min(jy + 1, h - 1) : jy;
+    int x0 = (ox & 1) ? jx : max(jx - 1, 0), x1 = (ox & 1) ? min(jx + 1, w - 1) : jx;
+    float wy1 = (oy & 1) ? 0.25f : 0.75f, wx1 = (ox & 1) ? 0.25f : 0.75f;   // weight of the higher index
+    const float* b = X + n * h * w * ldx + q * 4;
+    float4 a00 = *reinterpret_cast<const float4*>(b + ((long long)y0 * w + x0) * ldx);
+    float4 a01 = *reinterpret_cast<const float4*>(b + ((long long)y0 * w + x1) * ldx);
+    float4 a10 = *reinterpret_cast<const float4*>(b + ((long long)y1 * w + x0) * ldx);
+    float4 a11 = *reinterpret_cast<const float4*>(b + ((long long)y1 * w + x1) * ldx);
+    float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
+    float4 o;
+    // same association as ATen's upsample_bilinear2d: w_y0*(w_x0*a00 + w_x1*a01) + w_y1*(w_x0*a10 + w_x1*a11)
+    o.x = wy0 * (wx0 * a00.x + wx1 * a01.x) + wy1 * (wx0 * a10.x + wx1 * a11.x);
+    o.y = wy0 * (wx0 * a00.y + wx1 * a01.y) + wy1 * (wx0 * a10.y + wx1 * a11.y);
+    o.z = wy0 * (wx0 * a00.z + wx1 * a01.z) + wy1 * (wx0 * a10.z + wx1 * a11.z);
+    o.w = wy0 * (wx0 * a00.w + wx1 * a01.w) + wy1 * (wx0 * a10.w + wx1 * a11.w);
+    *reinterpret_cast<float4*>(Y + pix * ldy + q * 4) = o;
+  }
+}
+void launch_up2(const float* X, int ldx, float* Y, int ldy, int N, int h, int w, int C, cudaStream_t s) {
+  int grid = (int)std::min<long long>(cdivl((long long)N * 4 * h * w * (C / 4), 256), 148 * 16);
+  up2_kernel<<<grid, 256, 0, s>>>(X, ldx, Y, ldy, N, h, w, C);
+}
+
+__global__ void __launch_bounds__(256) up2_bwd_kernel(const float* __restrict__ DY, int ldd, float* DX, int ldx, int N,
+                                                      int h, int w, int C) {
+  const int Q = C >> 2, H = 2 * h, Wd = 2 * w;
+  const long long total = (long long)N * h * w * Q;
+  const float wt[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    int q = (int)(e % Q);
+    long long pix = e / Q;
+    int jx = (int)(pix % w);
+    long long t = pix / w;
+    int jy = (int)(t % h);
+    long long n = t / h;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* b = DY + n * H * Wd * ldd + q * 4;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int oy = min(max(2 * jy - 1 + a, 0), H - 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        int ox = min(max(2 * jx - 1 + c, 0), Wd - 1);
+        float4 v = *reinterpret_cast<const float4*>(b + ((long long)oy * Wd + ox) * ldd);
+        float ww = wt[a] * wt[c];
+        acc.x = fmaf(ww, v.x, acc.x); acc.y = fmaf(ww, v.y, acc.y);
+        acc.z = fmaf(ww, v.z, acc.z); acc.w = fmaf(ww, v.w, acc.w);
+      }
+    }
+    *reinterpret_cast<float4*>(DX + pix * ldx + q * 4) = acc;
+  }
+}
+void launch_up2_bwd(const float* DY, int ldd, float* DX, int ldx, int N, int h, int w, int C, cudaStream_t s) {
+  int grid = (int)std::min<long long>(cdivl((long long)N * h * w * (C / 4), 256), 148 * 16);
+  up2_bwd_kernel<<<grid, 256, 0, s>>>(DY, ldd, DX, ldx, N, h, w, C);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ECA (YOLOSegPlusPlus.py:60-88): gate[n][c] = sigmoid(sum_j w3[j] * mean[n][c+j-1]);  y = x * gate.
+// eca_gate: pooled sums (double, [n][2][C], slot 0) -> mean, gate.  eca_gate_bwd: dgate sums (slot 0 of dsum) ->
+// dmean[n][c] (already divided by HW) and dw3 (atomics).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void eca_gate_kernel(const double* __restrict__ pool, const float* __restrict__ w3, float* mean, float* gate,
+                                int N, int C, double HW) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * C) return;
+  int n = e / C, c = e % C;
+  const double* p = pool + (size_t)n * 2 * C;
+  float m0 = c > 0 ? (float)(p[c - 1] / HW) : 0.f, m1 = (float)(p[c] / HW), m2 = c + 1 < C ? (float)(p[c + 1] / HW) : 0.f;
+  float v = w3[0] * m0 + w3[1] * m1 + w3[2] * m2;
+  mean[e] = m1;
+  gate[e] = 1.f / (1.f + expf(-v));
+}
+void launch_eca_gate(const double* pool, const float* w3, float* mean, float* gate, int N, int C, long long HW, cudaStream_t s) {
+  eca_gate_kernel<<<cdivl((long long)N * C, 128), 128, 0, s>>>(pool, w3, mean, gate, N, C, (double)HW);
+}
+
+__global__ void eca_gate_bwd_kernel(const double* __restrict__ dsum, const float* __restrict__ w3,
+                                    const float* __restrict__ mean, const float* __restrict__ gate, float* dmean,
+                                    float* dw3, int N, int C, float invHW) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f;
+  if (e < N * C) {
+    int n = e / C, c = e % C;
+    const double* ds = dsum + (size_t)n * 2 * C;
+    const float* g = gate + (size_t)n * C;
+    const float* mu = mean + (size_t)n * C;
+    // dv[c'] = dgate[c'] * g(1-g);  dmean[c] = sum_j w3[j] * dv[c - j + 1]
+    auto dv = [&](int cc) -> float { return (cc < 0 || cc >= C) ? 0.f : (float)ds[cc] * g[cc] * (1.f - g[cc]); };
+    dmean[e] = (w3[0] * dv(c + 1) + w3[1] * dv(c) + w3[2] * dv(c - 1)) * invHW;
+    float d = dv(c);
+    l0 = c > 0 ? d * mu[c - 1] : 0.f;
+    l1 = d * mu[c];
+    l2 = c + 1 < C ? d * mu[c + 1] : 0.f;
+  }
+  // block reduction of the three weight-gradient terms
+  __shared__ float red[3][128];
+  red[0][threadIdx.x] = l0; red[1][threadIdx.x] = l1; red[2][threadIdx.x] = l2;
+  __syncthreads();
+  for (int st = 64; st > 0; st >>= 1) {
+    if (threadIdx.x < st)
+      for (int j = 0; j < 3; ++j) red[j][threadIdx.x] += red[j][threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) atomicAdd(&dw3[threadIdx.x], red[threadIdx.x][0]);
+}
+void launch_eca_gate_bwd(const double* dsum, const float* w3, const float* mean, const float* gate, float* dmean, float* dw3,
+                         int N, int C, long long HW, cudaStream_t s) {
+  eca_gate_bwd_kernel<<<cdivl((long long)N * C, 128), 128, 0, s>>>(dsum, w3, mean, gate, dmean, dw3, N, C, 1.f / (float)HW);
+}
+
+// out[m][c] = a[m][c] * g[n][c] (+ add[n][c])      n = m / HW       (ECA scale forward; backward dx = dy*gate + dmean)
+__global__ void __launch_bounds__(256) scale_rows_kernel(const float* __restrict__ A, int lda, const float* __restrict__ G,
+                                                         const float* __restrict__ ADD, float* O, int ldo, int C,
+                                                         long long M, long long HW) {
+  const int Q = C >> 2;
+  const long long total = M * Q;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    int q = (int)(e % Q);
+    long long m = e / Q, n = m / HW;
+    float4 a = *reinterpret_cast<const float4*>(A + m * lda + q * 4);
+    float4 g = *reinterpret_cast<const float4*>(G + n * C + q * 4);
+    float4 o = make_float4(a.x * g.x, a.y * g.y, a.z * g.z, a.w * g.w);
+    if (ADD) { float4 d = *reinterpret_cast<const float4*>(ADD + n * C + q * 4); o.x += d.x; o.y += d.y; o.z += d.z; o.w += d.w; }
+    *reinterpret_cast<float4*>(O + m * ldo + q * 4) = o;
+  }
+}
+void launch_scale_rows(const float* A, int lda, const float* G, const float* ADD, float* O, int ldo, int C, long long M,
+                       long long HW, cudaStream_t s) {
+  int grid = (int)std::min<long long>(cdivl(M * (C / 4), 256), 148 * 16);
+  scale_rows_kernel<<<grid, 256, 0, s>>>(A, lda, G, ADD, O, ldo, C, M, HW);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Loss (train.py:98-104): monai DiceLoss(sigmoid=True, soft_label=True, batch=True, smooth 1e-5) over the local batch:
+//   p = sigmoid(x);  P = sum p, T = sum t, A = sum |p - t|;  tp = (P+T-A)/2;  L = 1 - (2tp + eps)/(P + T + eps)
+// kind 1 adds mean BCE-with-logits (BASELINE cfg 4 wording "Dice+BCE"; not in the reference).
+// acc (double[4]) = P, T, A, sum bce.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ X, const float* __restrict__ T,
+                                                          long long n, double* acc) {
+  double s[4] = {0, 0, 0, 0};
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) {
+    float x = X[e], t = T[e];
+    float p = 1.f / (1.f + expf(-x));
+    s[0] += p; s[1] += t; s[2] += fabsf(p - t);
+    s[3] += fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+  }
+  __shared__ double red[4][256];
+  for (int j = 0; j < 4; ++j) red[j][threadIdx.x] = s[j];
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st)
+      for (int j = 0; j < 4; ++j) red[j][threadIdx.x] += red[j][threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) atomicAdd(&acc[threadIdx.x], red[threadIdx.x][0]);
+}
+
+__global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ X, const float* __restrict__ T,
+                                                        long long n, const double* __restrict__ acc, int kind,
+                                                        float grad_scale, float* DX, float* loss_out) {
+  const double P = acc[0], Tt = acc[1], A = acc[2], eps = 1e-5;
+  const double D = P + Tt + eps, num = (P + Tt - A) + eps;   // 2 tp + eps
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    loss_out[0] = (float)(1.0 - num / D + (kind == 1 ? acc[3] / (double)n : 0.0));
+    loss_out[1] = (float)(1.0 - num / D);
+    loss_out[2] = kind == 1 ? (float)(acc[3] / (double)n) : 0.f;
+  }
+  const float c1 = (float)(1.0 / D), c2 = (float)(num / (D * D)), invn = 1.f / (float)n;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) {
+    float x = X[e], t = T[e];
+    float p = 1.f / (1.f + expf(-x));
+    float sg = p > t ? 1.f : (p < t ? -1.f : 0.f);
+    float dLdp = -((1.f - sg) * c1 - c2);
+    float g = dLdp * p * (1.f - p);
+    if (kind == 1) g += (p - t) * invn;
+    DX[e] = g * grad_scale;
+  }
+}
+
+void launch_loss(const float* X, const float* T, long long n, double* acc, int kind, float grad_scale, float* DX,
+                 float* loss_out, cudaStream_t s) {
+  int grid = (int)std::min<long long>(cdivl(n, 256), 148 * 8);
+  loss_reduce_kernel<<<grid, 256, 0, s>>>(X, T, n, acc);
+  loss_grad_kernel<<<grid, 256, 0, s>>>(X, T, n, acc, kind, grad_scale, DX, loss_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Optimiser: torch.optim.AdamW (decoupled weight decay, bias-corrected), optional global-norm clip
+// (clip_grad_norm_ semantics: scale = min(1, max_norm/(norm + 1e-6)); 0 disables -- what the reference effectively
+// runs) and a gradient pre-scale (1/world_size after a SUM all-reduce).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, long long n, double* out) {
+  double s = 0;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) s += (double)g[e] * g[e];
+  __shared__ double red[256];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) { if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st]; __syncthreads(); }
+  if (threadIdx.x == 0) atomicAdd(out, red[0]);
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* p, const float* __restrict__ g, float* m, float* v, long long n,
+                                                    float lr, float b1, float b2, float eps, float wd, float bc1,
+                                                    float bc2_sqrt, float gscale, float max_norm,
+                                                    const double* __restrict__ sqn) {
+  float clip = 1.f;
+  if (max_norm > 0.f) {
+    float nrm = (float)sqrt(*sqn) * gscale;
+    clip = fminf(1.f, max_norm / (nrm + 1e-6f));
+  }
+  const float sc = gscale * clip;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) {
+    float gr = g[e] * sc;
+    float pe = p[e] * (1.f - lr * wd);
+    float me = b1 * m[e] + (1.f - b1) * gr;
+    float ve = b2 * v[e] + (1.f - b2) * gr * gr;
+    m[e] = me; v[e] = ve;
+    float denom = sqrtf(ve) / bc2_sqrt + eps;
+    p[e] = pe - (lr / bc1) * (me / denom);
+  }
+}
+
+void launch_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                  float wd, int step, float gscale, float max_norm, double* sqn_ws, cudaStream_t s) {
+  int grid = (int)std::min<long long>(cdivl(n, 256), 148 * 4);
+  if (max_norm > 0.f) {
+    cudaMemsetAsync(sqn_ws, 0, sizeof(double), s);
+    sqnorm_kernel<<<grid, 256, 0, s>>>(g, n, sqn_ws);
+  }
+  double bc1 = 1.0 - std::pow((double)b1, (double)step), bc2 = 1.0 - std::pow((double)b2, (double)step);
+  adamw_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, wd, (float)bc1, (float)std::sqrt(bc2), gscale, max_norm,
+                                    sqn_ws);
+}
+
+// NHWC activation view (fp32 or bf16) -> dense fp32 [M][C]  (hands the frozen encoder's skips to the trainer)
+template <typename T>
+__global__ void __launch_bounds__(256) export_view_kernel(const T* __restrict__ in, int in_cs, float* out, int C, long long M) {
+  const long long total = M * C;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    int c = (int)(e % C);
+    long long m = e / C;
+    out[e] = to_f<T>(in[m * in_cs + c]);
+  }
+}
+void launch_export_view(const void* in, int in_cs, int dt, float* out, int C, long long M, cudaStream_t s) {
+  int grid = (int)std::min<long long>(cdivl(M * C, 256), 148 * 16);
+  if (dt == DT_F32) export_view_kernel<float><<<grid, 256, 0, s>>>((const float*)in, in_cs, out, C, M);
+  else export_view_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, in_cs, out, C, M);
+}
+
+}  // namespace ysp

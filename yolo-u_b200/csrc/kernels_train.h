@@ -1,0 +1,41 @@
+// kernels_train.h -- launchers of the seg-head training kernels (kernels_train.cu).  fp32, NHWC views (ptr + row stride).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ysp {
+
+struct BnRef { const float *gamma, *beta, *mean, *invstd; };
+
+void launch_pw_gemm(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc,
+                    long long M, int I, int J, int beta, cudaStream_t s);
+void launch_pw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I, int J,
+                     cudaStream_t s);
+void launch_dw_conv(const float* X, int ldx, const float* W, float* Y, int ldy, int N, int H, int Wd, int C, int k,
+                    int flip, int beta, cudaStream_t s);
+void launch_dw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int N, int H, int Wd, int C, int k,
+                     cudaStream_t s);
+void launch_col_reduce(int mode, const float* A, int lda, const float* B, int ldb, const BnRef& bn, int act, double* sums,
+                       int C, long long segs, long long rows_per_seg, cudaStream_t s);
+void launch_bn_finalize(const double* sums, int C, long long M, float eps, float momentum, float* mean, float* invstd,
+                        float* run_mean, float* run_var, cudaStream_t s);
+void launch_bn_apply(const float* Z, int ldz, const BnRef& bn, int act, const float* R, int ldr, float* Y, int ldy, int C,
+                     long long M, cudaStream_t s);
+void launch_bn_bwd_apply(const float* DY, int ldd, const float* Z, int ldz, const BnRef& bn, int act, const double* sums,
+                         float* DZ, int ldo, float* dgamma, float* dbeta, int C, long long M, cudaStream_t s);
+void launch_add_sums(const double* sums, float* g, int n, int fold, cudaStream_t s);
+void launch_add_copy(const float* A, int lda, const float* B, int ldb, float* O, int ldo, int C, long long M, cudaStream_t s);
+void launch_up2(const float* X, int ldx, float* Y, int ldy, int N, int h, int w, int C, cudaStream_t s);
+void launch_up2_bwd(const float* DY, int ldd, float* DX, int ldx, int N, int h, int w, int C, cudaStream_t s);
+void launch_eca_gate(const double* pool, const float* w3, float* mean, float* gate, int N, int C, long long HW, cudaStream_t s);
+void launch_eca_gate_bwd(const double* dsum, const float* w3, const float* mean, const float* gate, float* dmean, float* dw3,
+                         int N, int C, long long HW, cudaStream_t s);
+void launch_scale_rows(const float* A, int lda, const float* G, const float* ADD, float* O, int ldo, int C, long long M,
+                       long long HW, cudaStream_t s);
+void launch_loss(const float* X, const float* T, long long n, double* acc, int kind, float grad_scale, float* DX,
+                 float* loss_out, cudaStream_t s);
+void launch_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                  float wd, int step, float gscale, float max_norm, double* sqn_ws, cudaStream_t s);
+void launch_export_view(const void* in, int in_cs, int dt, float* out, int C, long long M, cudaStream_t s);
+
+}  // namespace ysp
