@@ -323,6 +323,114 @@ def main_ours(args):
     return 0
 
 
+def main_train(args):
+    """BASELINE cfg 4 (not the headline metric): seg-head training step, B=128/GPU, frozen detector encoder, Dice+BCE,
+    data-parallel gradient all-reduce, AdamW.  Same timing rules as the inference arm; prints ONE JSON line."""
+    import torch
+    import torch.distributed as dist
+    from yolo_u_b200.synth import synth_state_dicts
+    from yolo_u_b200.trainer import SegHeadTrainer
+
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, Wm = args.batch, args.steps, args.warmup
+    _, seg_sd = synth_state_dicts(0)
+    tr = SegHeadTrainer(seg_sd, batch_size=B, image_size=H, lr=1e-4, epochs=100, loss=args.loss, device=dev,
+                        encoder_mode=args.mode)
+    g = torch.Generator().manual_seed(77 + rank)
+    nbuf = 3
+    xs = [torch.rand(B, 4, H, W, generator=g).to(dev) for _ in range(nbuf)]
+    lgs = [torch.sigmoid(torch.randn(B, 1, H // 8, W // 8, generator=g)).to(dev) for _ in range(nbuf)]
+    tg = torch.zeros(B, 1, H, W)
+    tg[:, :, 60:180, 80:200] = 1.0
+    tg = tg.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(Wm):
+        tr.step(xs[i % nbuf], tg, lgs[i % nbuf])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        loss, _ = tr.step(xs[i % nbuf], tg, lgs[i % nbuf])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * K / (ms / 1e3)
+    loss_host = [float(v) for v in loss.cpu()]
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        # CPU baseline: the oracle module under torch autograd + torch.optim.AdamW on a bounded sample (B=4)
+        from oracle.model import build_models, dice_loss, synth_inputs
+        import torch.nn.functional as F
+        torch.set_num_threads(os.cpu_count() or 1)
+        _, seg = build_models(0)
+        seg.train()
+        params = [p for k, p in seg.named_parameters() if not k.startswith("encoder.") and k != "param"]
+        for p in params:
+            p.requires_grad_(True)
+        opt = torch.optim.AdamW(params, lr=1e-4)
+        cx, clg, ctg = synth_inputs(4, H, 0)
+
+        def cpu_step():
+            opt.zero_grad()
+            pred = seg(cx, clg)
+            l = dice_loss(pred, ctg)
+            if args.loss != "dice":
+                l = l + F.binary_cross_entropy_with_logits(pred, ctg)
+            l.backward()
+            opt.step()
+
+        cpu_step()
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < args.cpu_seconds or n < 2:
+            cpu_step()
+            n += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": round(4 * n / dt, 2), "unit": "slices/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n} training steps of batch 4 (oracle module under torch autograd + AdamW, fp32, {dt:.1f} s)"}
+    if rank == 0:
+        line = {"metric": "seg-head training slices/sec (frozen encoder + decoder fwd/bwd + loss + AdamW)",
+                "value": round(value, 1), "unit": "slices/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"BASELINE cfg 4: batch {B}/GPU 4x{H}x{W}, loss {args.loss}, frozen encoder ({args.mode} engine), "
+                                       "decoder fp32 train mode (BN batch statistics), flat-buffer gradient all-reduce, AdamW",
+                           "inputs": "3 rotating device-resident batches (each > L2)"},
+                "gpu_launches": int(K * tr.launches_per_step),
+                "loss": loss_host, "clocks": clocks, "cpu_baseline": cpu}
+        peaks = load_peaks()
+        gbs = tr.bytes_per_step / (ms / K / 1e3) / 1e9
+        line["roofline"] = {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": round(gbs / peaks["hbm_gbs"], 4), "traffic": None, "peak_source": peaks["src"],
+                            "note": "whole decoder fwd+bwd step: libysp's per-launch ALGORITHMIC bytes (unfused, fp32) / step time"}
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -333,7 +441,12 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer = the headline metric (default); train = BASELINE cfg 4 (seg-head training step)")
+    ap.add_argument("--loss", default="dice_bce", choices=["dice", "dice_bce"])
     args = ap.parse_args()
+    if args.workload == "train" and args.batch == 256:
+        args.batch = 128
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return main_reference(args)
@@ -344,7 +457,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(random.randint(20000, 40000)), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
-    return main_ours(args)
+    return main_train(args) if args.workload == "train" else main_ours(args)
 
 
 if __name__ == "__main__":

@@ -145,6 +145,8 @@ int64_t ysp_train_param_count(const ysp_trainer* t);
 int64_t ysp_train_stat_count(const ysp_trainer* t);
 size_t ysp_train_workspace_bytes(const ysp_trainer* t);
 int ysp_train_last_launch_count(const ysp_trainer* t);
+/* ALGORITHMIC HBM bytes (compulsory fp32 reads + writes of every kernel, unfused) of the last ysp_train_step */
+double ysp_train_last_step_bytes(const ysp_trainer* t);
 /* frozen encoder (YOLOSegPlusPlus.py:255-259) through the inference engine: x [B,4,H,W] fp32 ->
  * skipA [B,H/4,W/4,64], skipB [B,H/8,W/8,128] dense NHWC fp32.  Workspace: ysp_workspace_bytes. */
 int ysp_encoder_forward(ysp_handle* h, const float* d_x, float* d_skipA, float* d_skipB, int B, int H, int W, void* d_ws,

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "ysp_train_stat_count": (i64, [vp]),
     "ysp_train_workspace_bytes": (sz, [vp]),
     "ysp_train_last_launch_count": (i32, [vp]),
+    "ysp_train_last_step_bytes": (C.c_double, [vp]),
     "ysp_encoder_forward": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]),
     "ysp_train_step": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, f32, vp, vp, vp, sz, vp]),
     "ysp_adamw": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, f32, vp, vp]),

@@ -35,12 +35,24 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(const float* __restrict__ 
   const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
   const long long m0 = (long long)blockIdx.x * BM;
   const int j0 = blockIdx.y * BN;
+  const bool vecA = ((lda | I) & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+  const bool vecC = ((ldc | J) & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
   float acc[4][4] = {};
   for (int i0 = 0; i0 < I; i0 += BK) {
-    for (int e = tid; e < BM * BK; e += 256) {
-      int r = e / BK, i = e % BK;
-      long long m = m0 + r;
-      As[i][r] = (m < M && i0 + i < I) ? A[m * lda + i0 + i] : 0.f;
+    if (vecA) {
+      for (int e = tid; e < BM * (BK / 4); e += 256) {
+        int r = e / (BK / 4), i = (e % (BK / 4)) * 4;
+        long long m = m0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < M && i0 + i < I) v = *reinterpret_cast<const float4*>(A + m * lda + i0 + i);   // I % 4 == 0
+        As[i][r] = v.x; As[i + 1][r] = v.y; As[i + 2][r] = v.z; As[i + 3][r] = v.w;
+      }
+    } else {
+      for (int e = tid; e < BM * BK; e += 256) {
+        int r = e / BK, i = e % BK;
+        long long m = m0 + r;
+        As[i][r] = (m < M && i0 + i < I) ? A[m * lda + i0 + i] : 0.f;
+      }
     }
     for (int e = tid; e < BK * BN; e += 256) {
       int i = e / BN, j = e % BN;
@@ -64,9 +76,19 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(const float* __restrict__ 
   for (int r = 0; r < 4; ++r) {
     long long m = m0 + ty * 4 + r;
     if (m >= M) continue;
+    const int jb = j0 + tx * 4;
+    if (vecC) {
+      if (jb >= J) continue;
+      float4* o = reinterpret_cast<float4*>(C + m * ldc + jb);
+      float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      if (bias) { v.x += bias[jb]; v.y += bias[jb + 1]; v.z += bias[jb + 2]; v.w += bias[jb + 3]; }
+      if (beta) { float4 p = *o; v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+      *o = v;
+      continue;
+    }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      int j = j0 + tx * 4 + c;
+      int j = jb + c;
       if (j >= J) continue;
       float v = acc[r][c] + (bias ? bias[j] : 0.f);
       float* o = C + m * ldc + j;
@@ -95,7 +117,8 @@ template <int TJ, int TI>
 __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__ D, int ldd, const float* __restrict__ X,
                                                        int ldx, float* dW, int ldw, long long M, int I, int J,
                                                        int rows_per_cta) {
-  constexpr int TPG = (TJ / 4) * (TI / 4), G = 256 / TPG, RS = 32;     // RS rows staged per pass
+  constexpr int TPG = (TJ / 4) * (TI / 4), G = 256 / TPG;
+  constexpr int RS = (TJ + TI <= 48) ? 128 : (TJ + TI <= 96 ? 64 : 32);                       // rows staged per pass
   __shared__ __align__(16) float sD[RS][TJ + 4];
   __shared__ __align__(16) float sX[RS][TI + 4];
   __shared__ float sAcc[TJ * TI];
@@ -104,19 +127,34 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
   const int j0 = blockIdx.y * TJ, i0 = blockIdx.z * TI;
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = (r0 + rows_per_cta < M) ? r0 + rows_per_cta : M;
+  const bool vecD = (ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0;
+  const bool vecX = (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
   for (int e = tid; e < TJ * TI; e += 256) sAcc[e] = 0.f;
-  __syncthreads();
   float acc[4][4] = {};
+  // one staged tile: rows [rb, rb+RS) x columns [c0, c0+TC) of a row-major matrix, zero-filled outside
+  auto stage = [&](const float* __restrict__ src, int ld, int c0, int cols, bool vec, float* dst, int dld, int TC,
+                   long long rb) {
+    const int q4 = TC / 4;
+    for (int e = tid; e < RS * q4; e += 256) {
+      int r = e / q4, c = (e % q4) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rb + r < r1) {
+        const float* p = src + (rb + r) * ld + c0 + c;
+        if (vec && c0 + c + 3 < cols) v = *reinterpret_cast<const float4*>(p);
+        else {
+          if (c0 + c < cols) v.x = p[0];
+          if (c0 + c + 1 < cols) v.y = p[1];
+          if (c0 + c + 2 < cols) v.z = p[2];
+          if (c0 + c + 3 < cols) v.w = p[3];
+        }
+      }
+      *reinterpret_cast<float4*>(dst + r * dld + c) = v;
+    }
+  };
   for (long long rb = r0; rb < r1; rb += RS) {
     __syncthreads();
-    for (int e = tid; e < RS * TJ; e += 256) {
-      int r = e / TJ, j = e % TJ;
-      sD[r][j] = (rb + r < r1 && j0 + j < J) ? D[(rb + r) * ldd + j0 + j] : 0.f;
-    }
-    for (int e = tid; e < RS * TI; e += 256) {
-      int r = e / TI, i = e % TI;
-      sX[r][i] = (rb + r < r1 && i0 + i < I) ? X[(rb + r) * ldx + i0 + i] : 0.f;
-    }
+    stage(D, ldd, j0, J, vecD, &sD[0][0], TJ + 4, TJ, rb);
+    stage(X, ldx, i0, I, vecX, &sX[0][0], TI + 4, TI, rb);
     __syncthreads();
 #pragma unroll 4
     for (int r = g; r < RS; r += G) {
@@ -129,6 +167,7 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
         for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
     }
   }
+  __syncthreads();
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -146,7 +185,7 @@ static void pw_wgrad_launch(const float* D, int ldd, const float* X, int ldx, fl
   int tiles = cdivl(J, TJ) * cdivl(I, TI);
   long long want = (148 * 4 + tiles - 1) / tiles;                       // ~4 CTAs per SM in total
   long long rows = (M + want - 1) / want;
-  rows = ((rows + 31) / 32) * 32;
+  rows = ((rows + 127) / 128) * 128;
   if (rows < 256) rows = 256;
   pw_wgrad_kernel<TJ, TI><<<dim3(cdivl(M, rows), cdivl(J, TJ), cdivl(I, TI)), 256, 0, s>>>(D, ldd, X, ldx, dW, ldw, M, I,
                                                                                           J, (int)rows);
@@ -169,21 +208,19 @@ __global__ void __launch_bounds__(256) dw_conv_kernel(const float* __restrict__ 
                                                       float* Y, int ldy, int N, int H, int Wd, int C, int k, int flip,
                                                       int beta) {
   extern __shared__ float sW[];   // [k*k][C]
-  const int kk = k * k;
-  for (int e = threadIdx.x; e < kk * C; e += 256) {
+  const int kk = k * k, nthr = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int e = tid; e < kk * C; e += nthr) {
     int c = e / kk, tp = e % kk;
     sW[(flip ? kk - 1 - tp : tp) * C + c] = W[e];
   }
   __syncthreads();
-  const int Q = C >> 2, pad = k >> 1;
-  const long long total = (long long)N * H * Wd * Q;
-  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-    int q = (int)(e % Q);
-    long long pix = e / Q;
-    int x = (int)(pix % Wd);
-    long long t = pix / Wd;
-    int y = (int)(t % H);
-    long long n = t / H;
+  const int pad = k >> 1, q = threadIdx.x;
+  const unsigned total = (unsigned)N * H * Wd;
+  for (unsigned pix = blockIdx.x * blockDim.y + threadIdx.y; pix < total; pix += gridDim.x * blockDim.y) {
+    const int x = pix % (unsigned)Wd;
+    const unsigned t = pix / (unsigned)Wd;
+    const int y = t % (unsigned)H;
+    const float* xb = X + (size_t)(pix - (unsigned)(y * Wd + x)) * ldx + q * 4;   // image base
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < k; ++r) {
       int iy = y + r - pad;
@@ -191,72 +228,77 @@ __global__ void __launch_bounds__(256) dw_conv_kernel(const float* __restrict__ 
       for (int s = 0; s < k; ++s) {
         int ix = x + s - pad;
         if (ix < 0 || ix >= Wd) continue;
-        float4 v = *reinterpret_cast<const float4*>(X + ((n * H + iy) * Wd + ix) * ldx + q * 4);
+        float4 v = *reinterpret_cast<const float4*>(xb + (size_t)(iy * Wd + ix) * ldx);
         float4 w = *reinterpret_cast<const float4*>(sW + (r * k + s) * C + q * 4);
         acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y);
         acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w);
       }
     }
-    float4* o = reinterpret_cast<float4*>(Y + pix * ldy + q * 4);
+    float4* o = reinterpret_cast<float4*>(Y + (size_t)pix * ldy + q * 4);
     if (beta) { float4 p = *o; acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w; }
     *o = acc;
   }
 }
 
+// block = (C/4 channel quads, 256/(C/4) rows): consecutive threads walk consecutive quads of consecutive rows, so a warp's
+// accesses are contiguous whenever the row stride equals C, and no kernel needs an integer division per element.
+static inline dim3 quad_block(int C) { int Q = C / 4; return dim3(Q, 256 / Q); }
+static inline int quad_grid(long long rows, int C, int per_sm = 16) {
+  int rpb = 256 / (C / 4);
+  return (int)std::min<long long>(cdivl(rows, rpb), 148 * per_sm);
+}
+
 void launch_dw_conv(const float* X, int ldx, const float* W, float* Y, int ldy, int N, int H, int Wd, int C, int k,
                     int flip, int beta, cudaStream_t s) {
-  long long total = (long long)N * H * Wd * (C / 4);
-  int grid = (int)std::min<long long>(cdivl(total, 256), 148 * 16);
-  dw_conv_kernel<<<grid, 256, (size_t)k * k * C * 4, s>>>(X, ldx, W, Y, ldy, N, H, Wd, C, k, flip, beta);
+  long long total = (long long)N * H * Wd;
+  dw_conv_kernel<<<quad_grid(total, C), quad_block(C), (size_t)k * k * C * 4, s>>>(X, ldx, W, Y, ldy, N, H, Wd, C, k, flip, beta);
 }
 
 // dW[c][tap] += sum_{n,y,x} D[n,y,x,c] * X[n, y+r-pad, x+s-pad, c]
 template <int K>
 __global__ void __launch_bounds__(256) dw_wgrad_kernel(const float* __restrict__ D, int ldd, const float* __restrict__ X,
                                                        int ldx, float* dW, int N, int H, int Wd, int C,
-                                                       long long pix_per_cta) {
+                                                       unsigned pix_per_cta) {
   constexpr int KK = K * K, PAD = K / 2;
   extern __shared__ float sAcc[];   // [C][KK]
-  for (int e = threadIdx.x; e < C * KK; e += 256) sAcc[e] = 0.f;
+  const int nthr = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int e = tid; e < C * KK; e += nthr) sAcc[e] = 0.f;
   __syncthreads();
-  const int Q = C >> 2, lanes = 256 / Q;
-  const int q = threadIdx.x % Q, lane = threadIdx.x / Q;
-  const long long total = (long long)N * H * Wd;
-  const long long p0 = (long long)blockIdx.x * pix_per_cta;
-  const long long p1 = (p0 + pix_per_cta < total) ? p0 + pix_per_cta : total;
+  const int q = threadIdx.x;
+  const unsigned total = (unsigned)N * H * Wd;
+  const unsigned p0 = blockIdx.x * pix_per_cta;
+  const unsigned p1 = (p0 + pix_per_cta < total) ? p0 + pix_per_cta : total;
   float acc[KK][4];
 #pragma unroll
   for (int tp = 0; tp < KK; ++tp) acc[tp][0] = acc[tp][1] = acc[tp][2] = acc[tp][3] = 0.f;
-  if (lane < lanes) {
-    for (long long pix = p0 + lane; pix < p1; pix += lanes) {
-      int x = (int)(pix % Wd);
-      long long t = pix / Wd;
-      int y = (int)(t % H);
-      long long n = t / H;
-      float4 d = *reinterpret_cast<const float4*>(D + pix * ldd + q * 4);
+  for (unsigned pix = p0 + threadIdx.y; pix < p1; pix += blockDim.y) {
+    const int x = pix % (unsigned)Wd;
+    const unsigned t = pix / (unsigned)Wd;
+    const int y = t % (unsigned)H;
+    const float* xb = X + (size_t)(pix - (unsigned)(y * Wd + x)) * ldx + q * 4;
+    float4 d = *reinterpret_cast<const float4*>(D + (size_t)pix * ldd + q * 4);
 #pragma unroll
-      for (int r = 0; r < K; ++r) {
-        int iy = y + r - PAD;
-        if (iy < 0 || iy >= H) continue;
+    for (int r = 0; r < K; ++r) {
+      int iy = y + r - PAD;
+      if (iy < 0 || iy >= H) continue;
 #pragma unroll
-        for (int s = 0; s < K; ++s) {
-          int ix = x + s - PAD;
-          if (ix < 0 || ix >= Wd) continue;
-          float4 v = *reinterpret_cast<const float4*>(X + ((n * H + iy) * Wd + ix) * ldx + q * 4);
-          acc[r * K + s][0] = fmaf(d.x, v.x, acc[r * K + s][0]);
-          acc[r * K + s][1] = fmaf(d.y, v.y, acc[r * K + s][1]);
-          acc[r * K + s][2] = fmaf(d.z, v.z, acc[r * K + s][2]);
-          acc[r * K + s][3] = fmaf(d.w, v.w, acc[r * K + s][3]);
-        }
+      for (int s = 0; s < K; ++s) {
+        int ix = x + s - PAD;
+        if (ix < 0 || ix >= Wd) continue;
+        float4 v = *reinterpret_cast<const float4*>(xb + (size_t)(iy * Wd + ix) * ldx);
+        acc[r * K + s][0] = fmaf(d.x, v.x, acc[r * K + s][0]);
+        acc[r * K + s][1] = fmaf(d.y, v.y, acc[r * K + s][1]);
+        acc[r * K + s][2] = fmaf(d.z, v.z, acc[r * K + s][2]);
+        acc[r * K + s][3] = fmaf(d.w, v.w, acc[r * K + s][3]);
       }
     }
-#pragma unroll
-    for (int tp = 0; tp < KK; ++tp)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) atomicAdd(&sAcc[(q * 4 + j) * KK + tp], acc[tp][j]);
   }
+#pragma unroll
+  for (int tp = 0; tp < KK; ++tp)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(&sAcc[(q * 4 + j) * KK + tp], acc[tp][j]);
   __syncthreads();
-  for (int e = threadIdx.x; e < C * KK; e += 256) atomicAdd(&dW[e], sAcc[e]);
+  for (int e = tid; e < C * KK; e += nthr) atomicAdd(&dW[e], sAcc[e]);
 }
 
 void launch_dw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int N, int H, int Wd, int C, int k,
@@ -265,8 +307,8 @@ void launch_dw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW
   long long per = std::max<long long>(cdivl(total, 148 * 4), 256);
   int grid = cdivl(total, per);
   size_t sm = (size_t)C * k * k * 4;
-  if (k == 3) dw_wgrad_kernel<3><<<grid, 256, sm, s>>>(D, ldd, X, ldx, dW, N, H, Wd, C, per);
-  else dw_wgrad_kernel<5><<<grid, 256, sm, s>>>(D, ldd, X, ldx, dW, N, H, Wd, C, per);
+  if (k == 3) dw_wgrad_kernel<3><<<grid, quad_block(C), sm, s>>>(D, ldd, X, ldx, dW, N, H, Wd, C, (unsigned)per);
+  else dw_wgrad_kernel<5><<<grid, quad_block(C), sm, s>>>(D, ldd, X, ldx, dW, N, H, Wd, C, (unsigned)per);
 }
 
 // =====================================================================================================================
@@ -286,10 +328,11 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict
                                                          int ldb, BnRef bn, int act, double* sums, int C,
                                                          long long rows_per_seg, long long rows_per_cta) {
   extern __shared__ double sred[];   // [2][C]
-  for (int e = threadIdx.x; e < 2 * C; e += 256) sred[e] = 0.0;
+  const int nthr = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int e = tid; e < 2 * C; e += nthr) sred[e] = 0.0;
   __syncthreads();
-  const int Q = C >> 2, lanes = 256 / Q;
-  const int q = threadIdx.x % Q, lane = threadIdx.x / Q;
+  const int lanes = blockDim.y;
+  const int q = threadIdx.x, lane = threadIdx.y;
   const long long seg = blockIdx.y;
   const long long r0 = seg * rows_per_seg + (long long)blockIdx.x * rows_per_cta;
   long long r1 = r0 + rows_per_cta;
@@ -338,7 +381,7 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict
     }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < (MODE <= 1 ? 2 : 1) * C; e += 256) atomicAdd(&sums[seg * 2 * C + e], sred[e]);
+  for (int e = tid; e < (MODE <= 1 ? 2 : 1) * C; e += nthr) atomicAdd(&sums[seg * 2 * C + e], sred[e]);
 }
 
 void launch_col_reduce(int mode, const float* A, int lda, const float* B, int ldb, const BnRef& bn, int act, double* sums,
@@ -348,10 +391,10 @@ void launch_col_reduce(int mode, const float* A, int lda, const float* B, int ld
   dim3 grid(cdivl(rows_per_seg, per), (unsigned)segs);
   size_t sm = (size_t)2 * C * sizeof(double);
   switch (mode) {
-    case 0: col_reduce_kernel<0><<<grid, 256, sm, s>>>(A, lda, B, ldb, bn, act, sums, C, rows_per_seg, per); break;
-    case 1: col_reduce_kernel<1><<<grid, 256, sm, s>>>(A, lda, B, ldb, bn, act, sums, C, rows_per_seg, per); break;
-    case 2: col_reduce_kernel<2><<<grid, 256, sm, s>>>(A, lda, B, ldb, bn, act, sums, C, rows_per_seg, per); break;
-    default: col_reduce_kernel<3><<<grid, 256, sm, s>>>(A, lda, B, ldb, bn, act, sums, C, rows_per_seg, per); break;
+    case 0: col_reduce_kernel<0><<<grid, quad_block(C), sm, s>>>(A, lda, B, ldb, bn, act, sums, C, rows_per_seg, per); break;
+    case 1: col_reduce_kernel<1><<<grid, quad_block(C), sm, s>>>(A, lda, B, ldb, bn, act, sums, C, rows_per_seg, per); break;
+    case 2: col_reduce_kernel<2><<<grid, quad_block(C), sm, s>>>(A, lda, B, ldb, bn, act, sums, C, rows_per_seg, per); break;
+    default: col_reduce_kernel<3><<<grid, quad_block(C), sm, s>>>(A, lda, B, ldb, bn, act, sums, C, rows_per_seg, per); break;
   }
 }
 
@@ -381,18 +424,21 @@ void launch_bn_finalize(const double* sums, int C, long long M, float eps, float
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ Z, int ldz, BnRef bn, int act,
                                                        const float* __restrict__ R, int ldr, float* Y, int ldy, int C,
                                                        long long M) {
-  const int Q = C >> 2;
-  const long long total = M * Q;
-  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-    int q = (int)(e % Q);
-    long long m = e / Q;
+  const int q = threadIdx.x;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {            // y = z*sc + sh
+    int c = q * 4 + j;
+    sc[j] = bn.gamma[c] * bn.invstd[c];
+    sh[j] = bn.beta[c] - bn.mean[c] * sc[j];
+  }
+  for (long long m = (long long)blockIdx.x * blockDim.y + threadIdx.y; m < M; m += (long long)gridDim.x * blockDim.y) {
     float4 z4 = *reinterpret_cast<const float4*>(Z + m * ldz + q * 4);
     float z[4] = {z4.x, z4.y, z4.z, z4.w}, r[4] = {0, 0, 0, 0}, o[4];
     if (R) { float4 r4 = *reinterpret_cast<const float4*>(R + m * ldr + q * 4); r[0] = r4.x; r[1] = r4.y; r[2] = r4.z; r[3] = r4.w; }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int c = q * 4 + j;
-      float t = fmaf(bn.gamma[c], (z[j] - bn.mean[c]) * bn.invstd[c], bn.beta[c]);
+      float t = fmaf(z[j], sc[j], sh[j]);
       o[j] = (act ? t / (1.f + expf(-t)) : t) + r[j];
     }
     *reinterpret_cast<float4*>(Y + m * ldy + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
@@ -401,8 +447,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
 
 void launch_bn_apply(const float* Z, int ldz, const BnRef& bn, int act, const float* R, int ldr, float* Y, int ldy, int C,
                      long long M, cudaStream_t s) {
-  int grid = (int)std::min<long long>(cdivl(M * (C / 4), 256), 148 * 16);
-  bn_apply_kernel<<<grid, 256, 0, s>>>(Z, ldz, bn, act, R, ldr, Y, ldy, C, M);
+  bn_apply_kernel<<<quad_grid(M, C), quad_block(C), 0, s>>>(Z, ldz, bn, act, R, ldr, Y, ldy, C, M);
 }
 
 // dz = gamma*invstd*(dt - S1/M - zhat*S2/M);  block 0 also accumulates dgamma += S2, dbeta += S1.
@@ -410,25 +455,28 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            int ldz, BnRef bn, int act, const double* __restrict__ sums,
                                                            float* DZ, int ldo, float* dgamma, float* dbeta, int C,
                                                            long long M) {
-  const int Q = C >> 2;
-  const long long total = M * Q;
+  const int q = threadIdx.x;
   const double invM = 1.0 / (double)M;
-  if (blockIdx.x == 0)
-    for (int c = threadIdx.x; c < C; c += 256) { dbeta[c] += (float)sums[c]; dgamma[c] += (float)sums[C + c]; }
-  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-    int q = (int)(e % Q);
-    long long m = e / Q;
+  if (blockIdx.x == 0 && threadIdx.y == 0)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { int c = q * 4 + j; dbeta[c] += (float)sums[c]; dgamma[c] += (float)sums[C + c]; }
+  float mu[4], is[4], ga[4], be[4], m1[4], m2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = q * 4 + j;
+    mu[j] = bn.mean[c]; is[j] = bn.invstd[c]; ga[j] = bn.gamma[c]; be[j] = bn.beta[c];
+    m1[j] = (float)(sums[c] * invM); m2[j] = (float)(sums[C + c] * invM);
+  }
+  for (long long m = (long long)blockIdx.x * blockDim.y + threadIdx.y; m < M; m += (long long)gridDim.x * blockDim.y) {
     float4 d4 = *reinterpret_cast<const float4*>(DY + m * ldd + q * 4);
     float4 z4 = *reinterpret_cast<const float4*>(Z + m * ldz + q * 4);
     const float d[4] = {d4.x, d4.y, d4.z, d4.w}, z[4] = {z4.x, z4.y, z4.z, z4.w};
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int c = q * 4 + j;
-      float zh = (z[j] - bn.mean[c]) * bn.invstd[c];
-      float dt = act ? d[j] * silu_grad(fmaf(bn.gamma[c], zh, bn.beta[c])) : d[j];
-      float m1 = (float)(sums[c] * invM), m2 = (float)(sums[C + c] * invM);
-      o[j] = bn.gamma[c] * bn.invstd[c] * (dt - m1 - zh * m2);
+      float zh = (z[j] - mu[j]) * is[j];
+      float dt = act ? d[j] * silu_grad(fmaf(ga[j], zh, be[j])) : d[j];
+      o[j] = ga[j] * is[j] * (dt - m1[j] - zh * m2[j]);
     }
     *reinterpret_cast<float4*>(DZ + m * ldo + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
   }
@@ -436,8 +484,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 
 void launch_bn_bwd_apply(const float* DY, int ldd, const float* Z, int ldz, const BnRef& bn, int act, const double* sums,
                          float* DZ, int ldo, float* dgamma, float* dbeta, int C, long long M, cudaStream_t s) {
-  int grid = (int)std::min<long long>(cdivl(M * (C / 4), 256), 148 * 16);
-  bn_bwd_apply_kernel<<<grid, 256, 0, s>>>(DY, ldd, Z, ldz, bn, act, sums, DZ, ldo, dgamma, dbeta, C, M);
+  bn_bwd_apply_kernel<<<quad_grid(M, C), quad_block(C), 0, s>>>(DY, ldd, Z, ldz, bn, act, sums, DZ, ldo, dgamma, dbeta, C, M);
 }
 
 // g[j] += (float) sum_{f < fold} sums[j*fold + f]   (bias gradients from MODE-2 reductions; fold > 1 when a 1-channel
@@ -478,24 +525,22 @@ void launch_add_copy(const float* A, int lda, const float* B, int ldb, float* O,
 // adjoint: din[j] = .25 do[2j-1] + .75 do[2j] + .75 do[2j+1] + .25 do[2j+2] with the OUTPUT indices clamped.
 __global__ void __launch_bounds__(256) up2_kernel(const float* __restrict__ X, int ldx, float* Y, int ldy, int N, int h,
                                                   int w, int C) {
-  const int Q = C >> 2, H = 2 * h, Wd = 2 * w;
-  const long long total = (long long)N * H * Wd * Q;
-  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-    int q = (int)(e % Q);
-    long long pix = e / Q;
-    int ox = (int)(pix % Wd);
-    long long t = pix / Wd;
-    int oy = (int)(t % H);
-    long long n = t / H;
+  const int H = 2 * h, Wd = 2 * w, q = threadIdx.x;
+  const unsigned total = (unsigned)N * H * Wd;
+  for (unsigned pix = blockIdx.x * blockDim.y + threadIdx.y; pix < total; pix += gridDim.x * blockDim.y) {
+    const int ox = pix % (unsigned)Wd;
+    const unsigned t = pix / (unsigned)Wd;
+    const int oy = t % (unsigned)H;
+    const unsigned n = t / (unsigned)H;
     int jy = oy >> 1, jx = ox >> 1;
     int y0 = (oy & 1) ? jy : max(jy - 1, 0), y1 = (oy & 1) ? min(jy + 1, h - 1) : jy;
     int x0 = (ox & 1) ? jx : max(jx - 1, 0), x1 = (ox & 1) ? min(jx + 1, w - 1) : jx;
     float wy1 = (oy & 1) ? 0.25f : 0.75f, wx1 = (ox & 1) ? 0.25f : 0.75f;   // weight of the higher index
-    const float* b = X + n * h * w * ldx + q * 4;
-    float4 a00 = *reinterpret_cast<const float4*>(b + ((long long)y0 * w + x0) * ldx);
-    float4 a01 = *reinterpret_cast<const float4*>(b + ((long long)y0 * w + x1) * ldx);
-    float4 a10 = *reinterpret_cast<const float4*>(b + ((long long)y1 * w + x0) * ldx);
-    float4 a11 = *reinterpret_cast<const float4*>(b + ((long long)y1 * w + x1) * ldx);
+    const float* b = X + (size_t)n * h * w * ldx + q * 4;
+    float4 a00 = *reinterpret_cast<const float4*>(b + (size_t)(y0 * w + x0) * ldx);
+    float4 a01 = *reinterpret_cast<const float4*>(b + (size_t)(y0 * w + x1) * ldx);
+    float4 a10 = *reinterpret_cast<const float4*>(b + (size_t)(y1 * w + x0) * ldx);
+    float4 a11 = *reinterpret_cast<const float4*>(b + (size_t)(y1 * w + x1) * ldx);
     float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
     float4 o;
     // same association as ATen's upsample_bilinear2d: w_y0*(w_x0*a00 + w_x1*a01) + w_y1*(w_x0*a10 + w_x1*a11)
@@ -503,46 +548,42 @@ __global__ void __launch_bounds__(256) up2_kernel(const float* __restrict__ X, i
     o.y = wy0 * (wx0 * a00.y + wx1 * a01.y) + wy1 * (wx0 * a10.y + wx1 * a11.y);
     o.z = wy0 * (wx0 * a00.z + wx1 * a01.z) + wy1 * (wx0 * a10.z + wx1 * a11.z);
     o.w = wy0 * (wx0 * a00.w + wx1 * a01.w) + wy1 * (wx0 * a10.w + wx1 * a11.w);
-    *reinterpret_cast<float4*>(Y + pix * ldy + q * 4) = o;
+    *reinterpret_cast<float4*>(Y + (size_t)pix * ldy + q * 4) = o;
   }
 }
 void launch_up2(const float* X, int ldx, float* Y, int ldy, int N, int h, int w, int C, cudaStream_t s) {
-  int grid = (int)std::min<long long>(cdivl((long long)N * 4 * h * w * (C / 4), 256), 148 * 16);
-  up2_kernel<<<grid, 256, 0, s>>>(X, ldx, Y, ldy, N, h, w, C);
+  up2_kernel<<<quad_grid((long long)N * 4 * h * w, C), quad_block(C), 0, s>>>(X, ldx, Y, ldy, N, h, w, C);
 }
 
 __global__ void __launch_bounds__(256) up2_bwd_kernel(const float* __restrict__ DY, int ldd, float* DX, int ldx, int N,
                                                       int h, int w, int C) {
-  const int Q = C >> 2, H = 2 * h, Wd = 2 * w;
-  const long long total = (long long)N * h * w * Q;
+  const int H = 2 * h, Wd = 2 * w, q = threadIdx.x;
+  const unsigned total = (unsigned)N * h * w;
   const float wt[4] = {0.25f, 0.75f, 0.75f, 0.25f};
-  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-    int q = (int)(e % Q);
-    long long pix = e / Q;
-    int jx = (int)(pix % w);
-    long long t = pix / w;
-    int jy = (int)(t % h);
-    long long n = t / h;
+  for (unsigned pix = blockIdx.x * blockDim.y + threadIdx.y; pix < total; pix += gridDim.x * blockDim.y) {
+    const int jx = pix % (unsigned)w;
+    const unsigned t = pix / (unsigned)w;
+    const int jy = t % (unsigned)h;
+    const unsigned n = t / (unsigned)h;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* b = DY + n * H * Wd * ldd + q * 4;
+    const float* b = DY + (size_t)n * H * Wd * ldd + q * 4;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       int oy = min(max(2 * jy - 1 + a, 0), H - 1);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         int ox = min(max(2 * jx - 1 + c, 0), Wd - 1);
-        float4 v = *reinterpret_cast<const float4*>(b + ((long long)oy * Wd + ox) * ldd);
+        float4 v = *reinterpret_cast<const float4*>(b + (size_t)(oy * Wd + ox) * ldd);
         float ww = wt[a] * wt[c];
         acc.x = fmaf(ww, v.x, acc.x); acc.y = fmaf(ww, v.y, acc.y);
         acc.z = fmaf(ww, v.z, acc.z); acc.w = fmaf(ww, v.w, acc.w);
       }
     }
-    *reinterpret_cast<float4*>(DX + pix * ldx + q * 4) = acc;
+    *reinterpret_cast<float4*>(DX + (size_t)pix * ldx + q * 4) = acc;
   }
 }
 void launch_up2_bwd(const float* DY, int ldd, float* DX, int ldx, int N, int h, int w, int C, cudaStream_t s) {
-  int grid = (int)std::min<long long>(cdivl((long long)N * h * w * (C / 4), 256), 148 * 16);
-  up2_bwd_kernel<<<grid, 256, 0, s>>>(DY, ldd, DX, ldx, N, h, w, C);
+  up2_bwd_kernel<<<quad_grid((long long)N * h * w, C), quad_block(C), 0, s>>>(DY, ldd, DX, ldx, N, h, w, C);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -62,6 +62,8 @@ struct Ctx {
   float momentum = 0.1f;
   float* dz = nullptr;
   int launches = 0;
+  double bytes = 0;            // ALGORITHMIC HBM bytes of the launched kernels (compulsory reads + writes, fp32)
+  void acct(double floats) { bytes += 4.0 * floats; }
   float* alloc(size_t nfloats) {
     size_t o = (top + 255) & ~(size_t)255;
     top = o + nfloats * 4;
@@ -86,6 +88,7 @@ struct ysp_trainer {
   Lin out;
   size_t ws_bytes = 0, sums_bytes = 0, dz_floats = 0;
   int last_launches = 0;
+  double last_bytes = 0;
 };
 
 namespace {
@@ -168,6 +171,7 @@ void convbn_fwd(Ctx& c, ConvBN& u, const float* x, int ldx, int N, int H, int W,
                      c.S ? c.S + u.rv : nullptr, c.s);
   launch_bn_apply(u.z, u.Cout, bn, u.act, res, ldr, y, ldy, u.Cout, M, c.s);
   c.launches += 4;
+  c.acct((double)M * ((u.dw ? u.Cout : u.Cin) + u.Cout * (4 + (res ? 1 : 0))));   // conv r/w, stats r, apply r/w (+res)
 }
 
 // dy -> parameter gradients (+ input gradient into dx[:, :dx_ch], accumulated when beta)
@@ -186,6 +190,8 @@ void convbn_bwd(Ctx& c, ConvBN& u, const float* dy, int ldd, float* dx, int lddx
     if (dx) launch_pw_gemm(c.dz, u.Cout, c.P + u.w, u.Cin, 1, nullptr, dx, lddx, M, u.Cout, dx_ch, beta, c.s);
   }
   c.launches += dx ? 4 : 3;
+  // reduce (dy, z), apply (dy, z -> dz), wgrad (dz, x), dgrad (dz -> dx [+ dx])
+  c.acct((double)M * (u.Cout * 7 + (u.dw ? u.Cout : u.Cin) + (dx ? dx_ch * (1 + beta) : 0)));
 }
 
 // ---- C3Ghost + ECA -------------------------------------------------------------------------------------------------------
@@ -214,6 +220,7 @@ void ghost_fwd(Ctx& c, Ghost& g, const float* xin, int ldin, int N, int H, int W
   launch_eca_gate(pool, c.P + g.eca_w, g.mean, g.gate, N, g.Cout, HW, c.s);
   launch_scale_rows(g.c, g.Cout, g.gate, nullptr, out, ldo, g.Cout, M, HW, c.s);
   c.launches += 4;
+  c.acct((double)M * (3 * c_ + 3 * g.Cout));
 }
 
 void ghost_bwd(Ctx& c, Ghost& g, const float* dout, int ldd, float* dxin, int lddx, int dx_ch) {
@@ -232,6 +239,7 @@ void ghost_bwd(Ctx& c, Ghost& g, const float* dout, int ldd, float* dxin, int ld
     launch_eca_gate_bwd(dsum, c.P + g.eca_w, g.mean, g.gate, dmean, c.G + g.eca_w, N, g.Cout, HW, c.s);
     launch_scale_rows(dout, ldd, g.gate, dmean, dC, g.Cout, g.Cout, M, HW, c.s);       // dx = dy*gate + dmean/HW
     c.launches += 3;
+    c.acct((double)M * (4 * g.Cout + 2 * c_));
   }
   convbn_bwd(c, g.cv3, dC, g.Cout, dCat, 2 * c_, 0, 2 * c_);
   convbn_bwd(c, g.cv2, dCat + c_, 2 * c_, dxin, lddx, 0, dx_ch);
@@ -256,6 +264,7 @@ void dlc_fwd(Ctx& c, Dlc& d, const float* xl, int ldx, int N, int h, int w, floa
     launch_up2(xl, ldx, d.u, d.Cin, N, h, w, d.Cin, c.s);
     launch_pw_gemm(d.u, d.Cin, c.P + d.r.w, d.Cin, 0, c.P + d.r.b, r, d.C, M, d.Cin, d.C, 0, c.s);   // residual_conv
     c.launches += 2;
+    c.acct((double)M * (d.Cin * 0.25 + d.Cin + d.Cin + d.C));
   }
   convbn_fwd(c, d.p, d.u, d.Cin, N, H, W, pb, d.C, nullptr, 0);
   convbn_fwd(c, d.q, pb, d.C, N, H, W, qb, d.C, nullptr, 0);
@@ -282,6 +291,7 @@ void dlc_bwd(Ctx& c, Dlc& d, const float* dout, int ldd, float* dxl, int lddx) {
   launch_pw_gemm(dout, ldd, c.P + d.r.w, d.Cin, 1, nullptr, dU, d.Cin, M, d.C, d.Cin, 1, c.s);
   launch_up2_bwd(dU, d.Cin, dxl, lddx, N, H / 2, W / 2, d.Cin, c.s);
   c.launches += 5;
+  c.acct((double)M * (d.C + (d.C + d.Cin) + (d.C + 2 * d.Cin) + d.Cin * 1.25));
 }
 
 // ---- whole step -----------------------------------------------------------------------------------------------------------
@@ -316,6 +326,7 @@ void run_step(ysp_trainer* t, Ctx& c, const StepIO& io) {
     launch_add_copy(io.logits, 1, nullptr, 0, in0 + 128, 132, 1, M0, c.s);
     launch_add_copy(io.skipA, 64, nullptr, 0, in2 + 64, 128, 64, M1, c.s);
     c.launches += 3;
+    c.acct((double)M0 * 258 + (double)M1 * 128);
   }
   ghost_fwd(c, t->gh0, in0, 132, B, h8, w8, d0, 96);
   dlc_fwd(c, t->dl1, d0, 96, B, h8, w8, in2, 128);
@@ -340,6 +351,7 @@ void run_step(ysp_trainer* t, Ctx& c, const StepIO& io) {
     launch_pw_wgrad(dlg, 1, d4, 16, c.G + o.w, 16, M3, 16, 1, c.s);
     launch_pw_gemm(dlg, 1, c.P + o.w, 16, 1, nullptr, dD4, 16, M3, 1, 16, 0, c.s);
     c.launches += 7;
+    c.acct((double)M3 * (17 + 2 + 3 + 1 + 17 + 17));
   }
   dlc_bwd(c, t->dl4, dD4, 16, dD3, 32);
   dlc_bwd(c, t->dl3, dD3, 32, dD2, 64);
@@ -397,6 +409,7 @@ int64_t ysp_train_param_count(const ysp_trainer* t) { return t ? t->n_params : 0
 int64_t ysp_train_stat_count(const ysp_trainer* t) { return t ? t->n_stats : 0; }
 size_t ysp_train_workspace_bytes(const ysp_trainer* t) { return t ? t->ws_bytes : 0; }
 int ysp_train_last_launch_count(const ysp_trainer* t) { return t ? t->last_launches : 0; }
+double ysp_train_last_step_bytes(const ysp_trainer* t) { return t ? t->last_bytes : 0; }
 
 int ysp_train_step(ysp_trainer* t, const float* d_skipA, const float* d_skipB, const float* d_logits,
                    const float* d_target, const float* d_params, float* d_grads, float* d_stats, float momentum,
@@ -416,6 +429,7 @@ int ysp_train_step(ysp_trainer* t, const float* d_skipA, const float* d_skipB, c
   StepIO io = {d_skipA, d_skipB, d_logits, d_target, d_loss3, d_mask_logits, loss_kind, grad_scale};
   run_step(t, c, io);
   t->last_launches = c.launches;
+  t->last_bytes = c.bytes;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return tfail(YSP_ECUDA, "ysp_train_step: %s", cudaGetErrorString(e));
   return 0;

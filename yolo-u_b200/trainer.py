@@ -136,6 +136,7 @@ class SegHeadTrainer:
         with torch.cuda.device(self.device):
             check(lib().ysp_encoder_forward(self.engine._h, img.data_ptr(), skipA.data_ptr(), skipB.data_ptr(), B, H, W,
                                             ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+        self._enc_launches = lib().ysp_last_launch_count(self.engine._h)
         return skipA, skipB
 
     def forward_backward(self, img: torch.Tensor, mask: torch.Tensor, heatmaps: torch.Tensor, grad_scale: float = 1.0,
@@ -197,5 +198,11 @@ class SegHeadTrainer:
         return e
 
     @property
+    def bytes_per_step(self) -> float:
+        """ALGORITHMIC HBM bytes of the decoder forward + backward of the last step (libysp's own accounting)"""
+        return lib().ysp_train_last_step_bytes(self._t)
+
+    @property
     def launches_per_step(self) -> int:
-        return lib().ysp_train_last_launch_count(self._t)
+        """kernels of this library one `step()` launches: frozen encoder + decoder forward/backward + AdamW"""
+        return lib().ysp_train_last_launch_count(self._t) + getattr(self, "_enc_launches", 0) + 1
