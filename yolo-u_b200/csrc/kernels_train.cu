@@ -20,92 +20,133 @@ namespace ysp {
 
 static inline int cdivl(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+template <int K, int MODE>
+static void dw_tiled_launch(const float* X, int ldx, const float* W, float* Y, int ldy, const float* D, int ldd, float* dW,
+                            double* sums, int N, int H, int Wd, int C, int beta, cudaStream_t s);
+
 // =====================================================================================================================
 // C[m][j] = beta*C[m][j] + bias[j] + sum_i A[m][i] * Wop(i,j)      Wop(i,j) = trans ? W[i*ldw + j] : W[j*ldw + i]
 //   forward 1x1 conv:   i = ci, j = co, trans = 0 (W = [Cout][Cin]);   input gradient: i = co, j = ci, trans = 1.
 // Thread micro-tile 4x4; BN in {16,32,64} columns per CTA and 4*(256/(BN/4)) rows, so narrow outputs waste nothing.
 // =====================================================================================================================
 template <int BN>
-__global__ void __launch_bounds__(256) pw_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
+__global__ void __launch_bounds__(256, 4) pw_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
                                                       int ldw, int trans, const float* __restrict__ bias, float* C,
-                                                      int ldc, long long M, int I, int J, int beta) {
+                                                      int ldc, long long M, int I, int J, int beta, double* sums) {
   constexpr int BK = 16, TX = BN / 4, TY = 256 / TX, BM = TY * 4;
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
+  __shared__ double sRed[2][BN];
   const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
-  const long long m0 = (long long)blockIdx.x * BM;
   const int j0 = blockIdx.y * BN;
   const bool vecA = ((lda | I) & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
   const bool vecC = ((ldc | J) & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
-  float acc[4][4] = {};
-  for (int i0 = 0; i0 < I; i0 += BK) {
-    if (vecA) {
-      for (int e = tid; e < BM * (BK / 4); e += 256) {
-        int r = e / (BK / 4), i = (e % (BK / 4)) * 4;
-        long long m = m0 + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < M && i0 + i < I) v = *reinterpret_cast<const float4*>(A + m * lda + i0 + i);   // I % 4 == 0
-        As[i][r] = v.x; As[i + 1][r] = v.y; As[i + 2][r] = v.z; As[i + 3][r] = v.w;
+  const long long mtiles = (M + BM - 1) / BM;
+  float cs1[4] = {0.f, 0.f, 0.f, 0.f}, cs2[4] = {0.f, 0.f, 0.f, 0.f};   // column sums of this thread's outputs (BN statistics)
+  for (long long mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+    const long long m0 = mt * BM;
+    float acc[4][4] = {};
+    for (int i0 = 0; i0 < I; i0 += BK) {
+      if (vecA) {
+        for (int e = tid; e < BM * (BK / 4); e += 256) {
+          int r = e / (BK / 4), i = (e % (BK / 4)) * 4;
+          long long m = m0 + r;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < M && i0 + i < I) v = *reinterpret_cast<const float4*>(A + m * lda + i0 + i);   // I % 4 == 0
+          As[i][r] = v.x; As[i + 1][r] = v.y; As[i + 2][r] = v.z; As[i + 3][r] = v.w;
+        }
+      } else {
+        for (int e = tid; e < BM * BK; e += 256) {
+          int r = e / BK, i = e % BK;
+          long long m = m0 + r;
+          As[i][r] = (m < M && i0 + i < I) ? A[m * lda + i0 + i] : 0.f;
+        }
       }
-    } else {
-      for (int e = tid; e < BM * BK; e += 256) {
-        int r = e / BK, i = e % BK;
-        long long m = m0 + r;
-        As[i][r] = (m < M && i0 + i < I) ? A[m * lda + i0 + i] : 0.f;
+      for (int e = tid; e < BK * BN; e += 256) {
+        int i = e / BN, jj = e % BN;
+        int ig = i0 + i, jg = j0 + jj;
+        Bs[i][jj] = (ig < I && jg < J) ? (trans ? W[(size_t)ig * ldw + jg] : W[(size_t)jg * ldw + ig]) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      long long m = m0 + ty * 4 + r;
+      if (m >= M) continue;
+      const int jb = j0 + tx * 4;
+      if (sums) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { cs1[c] += acc[r][c]; cs2[c] = fmaf(acc[r][c], acc[r][c], cs2[c]); }
+      }
+      if (vecC) {
+        if (jb >= J) continue;
+        float4* o = reinterpret_cast<float4*>(C + m * ldc + jb);
+        float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        if (bias) { v.x += bias[jb]; v.y += bias[jb + 1]; v.z += bias[jb + 2]; v.w += bias[jb + 3]; }
+        if (beta) { float4 pv = *o; v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w; }
+        *o = v;
+        continue;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        int jx = jb + c;
+        if (jx >= J) continue;
+        float v = acc[r][c] + (bias ? bias[jx] : 0.f);
+        float* o = C + m * ldc + jx;
+        *o = beta ? *o + v : v;
       }
     }
-    for (int e = tid; e < BK * BN; e += 256) {
-      int i = e / BN, j = e % BN;
-      int ig = i0 + i, jg = j0 + j;
-      Bs[i][j] = (ig < I && jg < J) ? (trans ? W[(size_t)ig * ldw + jg] : W[(size_t)jg * ldw + ig]) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
-    }
-    __syncthreads();
   }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    long long m = m0 + ty * 4 + r;
-    if (m >= M) continue;
-    const int jb = j0 + tx * 4;
-    if (vecC) {
-      if (jb >= J) continue;
-      float4* o = reinterpret_cast<float4*>(C + m * ldc + jb);
-      float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-      if (bias) { v.x += bias[jb]; v.y += bias[jb + 1]; v.z += bias[jb + 2]; v.w += bias[jb + 3]; }
-      if (beta) { float4 p = *o; v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
-      *o = v;
-      continue;
-    }
+  if (sums) {   // BatchNorm statistics of the (bias-free) output: warp shuffles over equal tx, then shared, then global atomics
+    for (int e = tid; e < 2 * BN; e += 256) sRed[e / BN][e % BN] = 0.0;
+    __syncthreads();
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      int j = jb + c;
-      if (j >= J) continue;
-      float v = acc[r][c] + (bias ? bias[j] : 0.f);
-      float* o = C + m * ldc + j;
-      *o = beta ? *o + v : v;
+      double a1 = cs1[c], a2 = cs2[c];
+#pragma unroll
+      for (int m = TX; m < 32; m <<= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, m); a2 += __shfl_xor_sync(0xffffffffu, a2, m); }
+      if ((tid & 31) < TX) { atomicAdd(&sRed[0][tx * 4 + c], a1); atomicAdd(&sRed[1][tx * 4 + c], a2); }
     }
+    __syncthreads();
+    for (int e = tid; e < 2 * BN; e += 256)
+      if (j0 + e % BN < J) atomicAdd(&sums[(e / BN) * J + j0 + e % BN], sRed[e / BN][e % BN]);
   }
 }
 
+// resident CTAs per SM of a kernel (queried once): persistent grids are sized to exactly one full wave
+template <typename Kern>
+static int resident_ctas(Kern kern, int threads, size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem) != cudaSuccess || n < 1) n = 1;
+  return n;
+}
+
+template <int BN>
+static void pw_gemm_launch(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc,
+                           long long M, int I, int J, int beta, cudaStream_t s, double* sums) {
+  constexpr int BM = (256 / (BN / 4)) * 4;
+  static const int occ = resident_ctas(pw_gemm_kernel<BN>, 256, 0);
+  const int jt = cdivl(J, BN);
+  const int cap = std::max(1, 148 * occ / jt);
+  pw_gemm_kernel<BN><<<dim3(std::min(cdivl(M, BM), cap), jt), 256, 0, s>>>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, sums);
+}
+
 void launch_pw_gemm(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc,
-                    long long M, int I, int J, int beta, cudaStream_t s) {
-  if (J <= 16) {
-    pw_gemm_kernel<16><<<dim3(cdivl(M, 256), cdivl(J, 16)), 256, 0, s>>>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta);
-  } else if (J <= 32) {
-    pw_gemm_kernel<32><<<dim3(cdivl(M, 128), cdivl(J, 32)), 256, 0, s>>>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta);
-  } else {
-    pw_gemm_kernel<64><<<dim3(cdivl(M, 64), cdivl(J, 64)), 256, 0, s>>>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta);
-  }
+                    long long M, int I, int J, int beta, cudaStream_t s, double* sums) {
+  if (J <= 16) pw_gemm_launch<16>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums);
+  else if (J <= 32) pw_gemm_launch<32>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums);
+  else pw_gemm_launch<64>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums);
 }
 
 // =====================================================================================================================
@@ -251,6 +292,11 @@ static inline int quad_grid(long long rows, int C, int per_sm = 16) {
 void launch_dw_conv(const float* X, int ldx, const float* W, float* Y, int ldy, int N, int H, int Wd, int C, int k,
                     int flip, int beta, cudaStream_t s) {
   long long total = (long long)N * H * Wd;
+  if (flip && H >= 32 && Wd >= 32 && (k == 3 || k == 5)) {
+    if (k == 3) dw_tiled_launch<3, 1>(X, ldx, W, Y, ldy, nullptr, 0, nullptr, nullptr, N, H, Wd, C, beta, s);
+    else dw_tiled_launch<5, 1>(X, ldx, W, Y, ldy, nullptr, 0, nullptr, nullptr, N, H, Wd, C, beta, s);
+    return;
+  }
   dw_conv_kernel<<<quad_grid(total, C), quad_block(C), (size_t)k * k * C * 4, s>>>(X, ldx, W, Y, ldy, N, H, Wd, C, k, flip, beta);
 }
 
@@ -304,11 +350,189 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const float* __restrict__
 void launch_dw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int N, int H, int Wd, int C, int k,
                      cudaStream_t s) {
   long long total = (long long)N * H * Wd;
+  if (H >= 32 && Wd >= 32 && (k == 3 || k == 5)) {
+    if (k == 3) dw_tiled_launch<3, 2>(X, ldx, nullptr, nullptr, 0, D, ldd, dW, nullptr, N, H, Wd, C, 0, s);
+    else dw_tiled_launch<5, 2>(X, ldx, nullptr, nullptr, 0, D, ldd, dW, nullptr, N, H, Wd, C, 0, s);
+    return;
+  }
   long long per = std::max<long long>(cdivl(total, 148 * 4), 256);
   int grid = cdivl(total, per);
   size_t sm = (size_t)C * k * k * 4;
   if (k == 3) dw_wgrad_kernel<3><<<grid, quad_block(C), sm, s>>>(D, ldd, X, ldx, dW, N, H, Wd, C, (unsigned)per);
   else dw_wgrad_kernel<5><<<grid, quad_block(C), sm, s>>>(D, ldd, X, ldx, dW, N, H, Wd, C, (unsigned)per);
+}
+
+// =====================================================================================================================
+// Tiled depthwise family (the hot depthwise launches: every map >= 32x32).  One CTA = one 16-channel group, looping over
+// 16x16-pixel tiles: input tile + halo staged once in shared memory (pixel pitch 20 floats: conflict-free float4 reads),
+// each thread owns one channel quad of 4 consecutive pixels and slides a K-wide register window over them.
+//   MODE 0  forward, and the BatchNorm batch statistics of its own output (sum, sum of squares -> `sums`, double)
+//   MODE 1  input gradient: flipped taps, optional accumulate into Y
+//   MODE 2  weight gradient: dW[c][tap] += sum D[pix][c] * X[pix + tap][c], accumulated in registers across the tiles
+// Cross-thread reductions: warp shuffles over the lanes that share a quad, then shared, then global atomics per CTA.
+// =====================================================================================================================
+template <int K, int MODE>
+__global__ void __launch_bounds__(256) dw_tiled_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
+                                                       float* Y, int ldy, const float* __restrict__ D, int ldd, float* dW,
+                                                       double* sums, int N, int H, int Wd, int C, int beta) {
+  constexpr int TY = 16, TX = 16, IH = TY + K - 1, IW = TX + K - 1, PS = 20, KK = K * K, PAD = K / 2;
+  extern __shared__ __align__(16) float dsm[];
+  float* sIn = dsm;                      // [IH*IW][PS]
+  float* sW = sIn + IH * IW * PS;        // MODE 0/1: [KK][16] taps;  MODE 2: [16][KK] block accumulators
+  __shared__ double sRed[2][16];
+  const int tid = threadIdx.x;
+  const int tiles_x = (Wd + TX - 1) / TX, tiles_y = (H + TY - 1) / TY;
+  const int ntiles = N * tiles_y * tiles_x;
+  const int cg = blockIdx.y * 16;
+  const int nq = min(4, (C - cg) >> 2);
+  const int q = tid & 3, txi = (tid >> 2) & 3, ty = tid >> 4;
+  if (MODE < 2) {
+    for (int e = tid; e < KK * 16; e += 256) {
+      int tp = e >> 4, c = e & 15;
+      sW[(MODE == 1 ? KK - 1 - tp : tp) * 16 + c] = (cg + c < C) ? W[(size_t)(cg + c) * KK + tp] : 0.f;
+    }
+  } else {
+    for (int e = tid; e < 16 * KK; e += 256) sW[e] = 0.f;
+  }
+  if (tid < 32) sRed[tid >> 4][tid & 15] = 0.0;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  float wacc[MODE == 2 ? KK : 1][4];
+#pragma unroll
+  for (int tp = 0; tp < (MODE == 2 ? KK : 1); ++tp) wacc[tp][0] = wacc[tp][1] = wacc[tp][2] = wacc[tp][3] = 0.f;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int t = tile;
+    const int tx0 = (t % tiles_x) * TX; t /= tiles_x;
+    const int ty0 = (t % tiles_y) * TY;
+    const int n = t / tiles_y;
+    __syncthreads();
+    for (int i = tid; i < IH * IW * 4; i += 256) {
+      const int qq = i & 3, pp = i >> 2;
+      const int iy = ty0 + pp / IW - PAD, ix = tx0 + pp % IW - PAD;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (qq < nq && iy >= 0 && iy < H && ix >= 0 && ix < Wd)
+        v = *reinterpret_cast<const float4*>(X + ((size_t)(n * H + iy) * Wd + ix) * ldx + cg + qq * 4);
+      *reinterpret_cast<float4*>(sIn + pp * PS + qq * 4) = v;
+    }
+    __syncthreads();
+    const int y = ty0 + ty;
+    const bool rowok = y < H && q < nq;
+    if (MODE < 2) {
+      float4 acc[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        const float* rp = sIn + ((ty + r) * IW + txi * 4) * PS + q * 4;
+        float4 v[K + 3], w[K];
+#pragma unroll
+        for (int j = 0; j < K + 3; ++j) v[j] = *reinterpret_cast<const float4*>(rp + j * PS);
+#pragma unroll
+        for (int s2i = 0; s2i < K; ++s2i) w[s2i] = *reinterpret_cast<const float4*>(sW + (r * K + s2i) * 16 + q * 4);
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+          for (int s2i = 0; s2i < K; ++s2i) {
+            acc[o].x = fmaf(v[o + s2i].x, w[s2i].x, acc[o].x); acc[o].y = fmaf(v[o + s2i].y, w[s2i].y, acc[o].y);
+            acc[o].z = fmaf(v[o + s2i].z, w[s2i].z, acc[o].z); acc[o].w = fmaf(v[o + s2i].w, w[s2i].w, acc[o].w);
+          }
+      }
+      if (rowok) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int x = tx0 + txi * 4 + o;
+          if (x >= Wd) break;
+          float4* op = reinterpret_cast<float4*>(Y + ((size_t)(n * H + y) * Wd + x) * ldy + cg + q * 4);
+          float4 a = acc[o];
+          if (MODE == 1 && beta) { float4 pv = *op; a.x += pv.x; a.y += pv.y; a.z += pv.z; a.w += pv.w; }
+          *op = a;
+          if (MODE == 0) {
+            s1[0] += a.x; s1[1] += a.y; s1[2] += a.z; s1[3] += a.w;
+            s2[0] = fmaf(a.x, a.x, s2[0]); s2[1] = fmaf(a.y, a.y, s2[1]);
+            s2[2] = fmaf(a.z, a.z, s2[2]); s2[3] = fmaf(a.w, a.w, s2[3]);
+          }
+        }
+      }
+    } else {
+      float4 d[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int x = tx0 + txi * 4 + o;
+        d[o] = (rowok && x < Wd) ? *reinterpret_cast<const float4*>(D + ((size_t)(n * H + y) * Wd + x) * ldd + cg + q * 4)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        const float* rp = sIn + ((ty + r) * IW + txi * 4) * PS + q * 4;
+        float4 v[K + 3];
+#pragma unroll
+        for (int j = 0; j < K + 3; ++j) v[j] = *reinterpret_cast<const float4*>(rp + j * PS);
+#pragma unroll
+        for (int s2i = 0; s2i < K; ++s2i)
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            wacc[MODE == 2 ? r * K + s2i : 0][0] = fmaf(d[o].x, v[o + s2i].x, wacc[MODE == 2 ? r * K + s2i : 0][0]);
+            wacc[MODE == 2 ? r * K + s2i : 0][1] = fmaf(d[o].y, v[o + s2i].y, wacc[MODE == 2 ? r * K + s2i : 0][1]);
+            wacc[MODE == 2 ? r * K + s2i : 0][2] = fmaf(d[o].z, v[o + s2i].z, wacc[MODE == 2 ? r * K + s2i : 0][2]);
+            wacc[MODE == 2 ? r * K + s2i : 0][3] = fmaf(d[o].w, v[o + s2i].w, wacc[MODE == 2 ? r * K + s2i : 0][3]);
+          }
+      }
+    }
+  }
+  // ---- block reductions (lanes with equal q: xor 4, 8, 16) ----
+  if (MODE == 0) {
+    __syncthreads();
+    double a1[4], a2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a1[j] = s1[j]; a2[j] = s2[j];
+#pragma unroll
+      for (int m = 4; m < 32; m <<= 1) {
+        a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], m);
+        a2[j] += __shfl_xor_sync(0xffffffffu, a2[j], m);
+      }
+    }
+    if ((tid & 31) < 4 && q < nq)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { atomicAdd(&sRed[0][q * 4 + j], a1[j]); atomicAdd(&sRed[1][q * 4 + j], a2[j]); }
+    __syncthreads();
+    if (tid < 32 && cg + (tid & 15) < C) atomicAdd(&sums[(tid >> 4) * C + cg + (tid & 15)], sRed[tid >> 4][tid & 15]);
+  }
+  if (MODE == 2) {
+    __syncthreads();
+#pragma unroll
+    for (int tp = 0; tp < (MODE == 2 ? KK : 1); ++tp)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = wacc[tp][j];
+#pragma unroll
+        for (int m = 4; m < 32; m <<= 1) a += __shfl_xor_sync(0xffffffffu, a, m);
+        if ((tid & 31) < 4) atomicAdd(&sW[(q * 4 + j) * KK + tp], a);
+      }
+    __syncthreads();
+    for (int e = tid; e < 16 * KK; e += 256)
+      if (cg + e / KK < C) atomicAdd(&dW[(size_t)cg * KK + e], sW[e]);
+  }
+}
+
+template <int K, int MODE>
+static void dw_tiled_launch(const float* X, int ldx, const float* W, float* Y, int ldy, const float* D, int ldd, float* dW,
+                            double* sums, int N, int H, int Wd, int C, int beta, cudaStream_t s) {
+  constexpr size_t smem = sizeof(float) * ((16 + K - 1) * (16 + K - 1) * 20 + K * K * 16);
+  const int ngrp = (C + 15) / 16;
+  const int ntiles = N * ((H + 15) / 16) * ((Wd + 15) / 16);
+  static const int occ = resident_ctas(dw_tiled_kernel<K, MODE>, 256, smem);
+  int gx = std::min(ntiles, std::max(1, 148 * occ / ngrp));
+  dw_tiled_kernel<K, MODE><<<dim3(gx, ngrp), 256, smem, s>>>(X, ldx, W, Y, ldy, D, ldd, dW, sums, N, H, Wd, C, beta);
+}
+
+// forward with fused BatchNorm statistics (sums = [2][C] doubles, pre-zeroed) -- returns false if the shape is not tiled
+bool launch_dw_fwd_stats(const float* X, int ldx, const float* W, float* Y, int ldy, double* sums, int N, int H, int Wd,
+                         int C, int k, cudaStream_t s) {
+  if (H < 32 || Wd < 32 || (k != 3 && k != 5)) return false;
+  if (k == 3) dw_tiled_launch<3, 0>(X, ldx, W, Y, ldy, nullptr, 0, nullptr, sums, N, H, Wd, C, 0, s);
+  else dw_tiled_launch<5, 0>(X, ldx, W, Y, ldy, nullptr, 0, nullptr, sums, N, H, Wd, C, 0, s);
+  return true;
 }
 
 // =====================================================================================================================

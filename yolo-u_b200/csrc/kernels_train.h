@@ -7,12 +7,15 @@ namespace ysp {
 
 struct BnRef { const float *gamma, *beta, *mean, *invstd; };
 
+// `sums` (optional, [2][J] doubles, pre-zeroed): per-column sum and sum of squares of the product (BN statistics)
 void launch_pw_gemm(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc,
-                    long long M, int I, int J, int beta, cudaStream_t s);
+                    long long M, int I, int J, int beta, cudaStream_t s, double* sums = nullptr);
 void launch_pw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I, int J,
                      cudaStream_t s);
 void launch_dw_conv(const float* X, int ldx, const float* W, float* Y, int ldy, int N, int H, int Wd, int C, int k,
                     int flip, int beta, cudaStream_t s);
+bool launch_dw_fwd_stats(const float* X, int ldx, const float* W, float* Y, int ldy, double* sums, int N, int H, int Wd,
+                         int C, int k, cudaStream_t s);
 void launch_dw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int N, int H, int Wd, int C, int k,
                      cudaStream_t s);
 void launch_col_reduce(int mode, const float* A, int lda, const float* B, int ldb, const BnRef& bn, int act, double* sums,

@@ -163,14 +163,20 @@ void convbn_fwd(Ctx& c, ConvBN& u, const float* x, int ldx, int N, int H, int W,
   double* sums = c.sums(2 * (size_t)u.Cout);
   c.need_dz((size_t)M * u.Cout);
   if (c.dry) return;
-  if (u.dw) launch_dw_conv(x, ldx, c.P + u.w, u.z, u.Cout, N, H, W, u.Cout, u.k, 0, 0, c.s);
-  else launch_pw_gemm(x, ldx, c.P + u.w, u.Cin, 0, nullptr, u.z, u.Cout, M, u.Cin, u.Cout, 0, c.s);
   BnRef bn = {c.P + u.g, c.P + u.b, u.mean, u.invstd};
-  launch_col_reduce(0, u.z, u.Cout, nullptr, 0, bn, 0, sums, u.Cout, 1, M, c.s);
+  bool stats_done = false;
+  if (u.dw) {
+    stats_done = launch_dw_fwd_stats(x, ldx, c.P + u.w, u.z, u.Cout, sums, N, H, W, u.Cout, u.k, c.s);   // conv + BN statistics
+    if (!stats_done) launch_dw_conv(x, ldx, c.P + u.w, u.z, u.Cout, N, H, W, u.Cout, u.k, 0, 0, c.s);
+  } else {
+    launch_pw_gemm(x, ldx, c.P + u.w, u.Cin, 0, nullptr, u.z, u.Cout, M, u.Cin, u.Cout, 0, c.s, sums);     // conv + BN statistics
+    stats_done = true;
+  }
+  if (!stats_done) { launch_col_reduce(0, u.z, u.Cout, nullptr, 0, bn, 0, sums, u.Cout, 1, M, c.s); c.launches += 1; }
   launch_bn_finalize(sums, u.Cout, M, kBnEps, c.momentum, u.mean, u.invstd, c.S ? c.S + u.rm : nullptr,
                      c.S ? c.S + u.rv : nullptr, c.s);
   launch_bn_apply(u.z, u.Cout, bn, u.act, res, ldr, y, ldy, u.Cout, M, c.s);
-  c.launches += 4;
+  c.launches += 3;
   c.acct((double)M * ((u.dw ? u.Cout : u.Cin) + u.Cout * (4 + (res ? 1 : 0))));   // conv r/w, stats r, apply r/w (+res)
 }
 
