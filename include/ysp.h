@@ -128,6 +128,14 @@ typedef struct ysp_pipeline_io {
 int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, void* d_ws, size_t ws_bytes,
                  void* stream);
 
+/* -- slice ingest (dataset.py:59-70) ---------------------------------------------------------------------
+ * cv2.resize on decoded uint8 slices + transforms.ToTensor, on device and bit-exact with OpenCV's generic uint8 path:
+ * interp 1 = INTER_LINEAR (image, dataset.py:63), 0 = INTER_NEAREST (mask, dataset.py:65).  src u8 [B,h,w,C], C = 4
+ * (cv2 BGRA order, IMREAD_UNCHANGED) or 1; outputs (either may be NULL): dst_u8 [B,dh,dw,C] (feeds ysp_pipeline's
+ * uint8 input) and dst_f32 [B,C,dh,dw] = value / 255 (what ToTensor returns, dataset.py:68-70). */
+int ysp_resize_u8(const uint8_t* d_src, int B, int h, int w, int C, int dh, int dw, int interp, uint8_t* d_dst_u8,
+                  float* d_dst_f32, void* stream);
+
 /* -- seg-head training step (reference train.py:241-360, non-AMP branch) -------------------------
  * Trainable = everything of YOLOSegPlusPlus outside `encoder.*` and the unused `param` scalar (train.py:256-267).
  * The trainer owns no tensors: the caller (yolo_u_b200/trainer.py) allocates flat fp32 DEVICE buffers

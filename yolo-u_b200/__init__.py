@@ -9,4 +9,4 @@ from .nms import non_max_suppression, TorchNMS  # noqa: F401
 from .predictor import Predictor, HostPipeline, predict  # noqa: F401
 from .metrics import mask_counts, dice_from_counts, SegMetrics  # noqa: F401
 from .sharding import shard_volumes, shard_slices, batches  # noqa: F401
-from .formats import objectmap_transform, save_objectmaps, scale_boxes  # noqa: F401
+from .formats import ingest, objectmap_transform, resize_u8, save_objectmaps, scale_boxes  # noqa: F401

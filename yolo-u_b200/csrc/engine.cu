@@ -1041,6 +1041,18 @@ int ysp_encoder_forward(ysp_handle* h, const float* d_x, float* d_skipA, float* 
   return 0;
 }
 
+int ysp_resize_u8(const uint8_t* d_src, int B, int h, int w, int C, int dh, int dw, int interp, uint8_t* d_dst_u8,
+                  float* d_dst_f32, void* stream) {
+  if (!d_src || (!d_dst_u8 && !d_dst_f32) || B < 0 || h <= 0 || w <= 0 || dh <= 0 || dw <= 0)
+    return fail(YSP_EINVAL, "ysp_resize_u8: bad arguments");
+  if (C != 1 && C != 4) return fail(YSP_EINVAL, "ysp_resize_u8: C must be 1 (mask) or 4 (slice), got %d", C);
+  if (interp != 0 && interp != 1) return fail(YSP_EINVAL, "ysp_resize_u8: interp must be 0 (INTER_NEAREST) or 1 (INTER_LINEAR)");
+  if (B == 0) return 0;
+  launch_resize_u8(d_src, B, h, w, C, dh, dw, interp, d_dst_u8, d_dst_f32, (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 size_t ysp_nms_workspace_bytes(int B, int C, int A, int max_det) { return nms_workspace_bytes(B, C, A, max_det); }
 
 int ysp_nms(const float* d_pred, int B, int C, int A, int nc, float conf_thres, float iou_thres, int max_det,

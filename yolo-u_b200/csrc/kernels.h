@@ -35,6 +35,8 @@ void launch_mask_dice(const float* logits, const float* target, int B, int HW, i
 void launch_nhwc_to_nchw_f32(const void* in, float* out, int N, int H, int W, int C, int in_cs, int dt, cudaStream_t s);
 
 void launch_objectmap_transform(const float* in, float* out, int B, int n, cudaStream_t s);
+void launch_resize_u8(const uint8_t* src, int B, int sh, int sw, int C, int dh, int dw, int interp, uint8_t* dst_u8,
+                      float* dst_f32, cudaStream_t s);
 void launch_scale_boxes(float* boxes, long long n, int row, float gain, float pad_x, float pad_y, float w0, float h0, cudaStream_t s);
 
 // kernels_stem_attn.cu

@@ -3,6 +3,8 @@
 // These are (a) the whole fp32 "parity mode" (YSP_MODE_FP32) and (b) everything in bf16 "throughput mode" that is
 // not a tensor-core GEMM: depthwise convs, resampling, ECA, area-attention core, head decode, layout conversion,
 // mask/Dice counters.  All activations are NHWC views (common.cuh).  Reference semantics cited per kernel.
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace ysp {
@@ -723,4 +725,83 @@ void launch_scale_boxes(float* boxes, long long n, int row, float gain, float pa
   if (n > 0) scale_boxes_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(boxes, n, row, gain, pad_x, pad_y, w0, h0);
 }
 
+}  // namespace ysp
+
+namespace ysp {
+// =====================================================================================================================
+// Slice ingest: cv2.resize on uint8 + transforms.ToTensor (dataset.py:59-70), bit-exact with OpenCV's
+// generic uint8 path.  INTER_LINEAR: per-axis source index / weight from float((d + .5) * scale - .5) (double product,
+// no FMA contraction), weights rounded to 11-bit fixed point, horizontal pass in int32, vertical pass
+// (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2.  An exact 2x downscale is the rounded 2x2 mean (cv2 reroutes it to
+// INTER_AREA).  INTER_NEAREST: min(floor(d * (1/(dn/sn))), sn-1).  One thread per output pixel, C in {1, 4}.
+// =====================================================================================================================
+struct AxisTap { int i0, i1, w0, w1; };
+
+__device__ __forceinline__ AxisTap linear_tap(int d, double scale, int sn, bool clamp_weight) {
+  float f = __double2float_rn(__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5));
+  int s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  AxisTap t;
+  if (clamp_weight) {                       // x axis: cv2 resets the weight at the borders
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= sn - 1) { f = 0.f; s = sn - 1; }
+    t.i0 = s; t.i1 = min(s + 1, sn - 1);
+  } else {                                  // y axis: rows are clamped, weights kept
+    t.i0 = min(max(s, 0), sn - 1); t.i1 = min(max(s + 1, 0), sn - 1);
+  }
+  t.w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  t.w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  return t;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) resize_u8_kernel(const uint8_t* __restrict__ src, int B, int sh, int sw, int dh,
+                                                        int dw, int interp, double sx, double sy, uint8_t* dst_u8,
+                                                        float* dst_f32) {
+  const long long total = (long long)B * dh * dw;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    const int x = (int)(e % dw);
+    const long long t = e / dw;
+    const int y = (int)(t % dh);
+    const long long n = t / dh;
+    const uint8_t* img = src + (size_t)n * sh * sw * C;
+    int out[C];
+    if (interp == 0) {
+      int ix = min((int)floor(__dmul_rn((double)x, sx)), sw - 1), iy = min((int)floor(__dmul_rn((double)y, sy)), sh - 1);
+#pragma unroll
+      for (int c = 0; c < C; ++c) out[c] = img[((size_t)iy * sw + ix) * C + c];
+    } else if (sh == 2 * dh && sw == 2 * dw) {
+      const uint8_t* p = img + ((size_t)(2 * y) * sw + 2 * x) * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) out[c] = (p[c] + p[C + c] + p[(size_t)sw * C + c] + p[(size_t)sw * C + C + c] + 2) >> 2;
+    } else {
+      const AxisTap tx = linear_tap(x, sx, sw, true), ty = linear_tap(y, sy, sh, false);
+      const uint8_t* r0 = img + (size_t)ty.i0 * sw * C;
+      const uint8_t* r1 = img + (size_t)ty.i1 * sw * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        int h0 = r0[tx.i0 * C + c] * tx.w0 + r0[tx.i1 * C + c] * tx.w1;
+        int h1 = r1[tx.i0 * C + c] * tx.w0 + r1[tx.i1 * C + c] * tx.w1;
+        int v = (((ty.w0 * (h0 >> 4)) >> 16) + ((ty.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        out[c] = min(max(v, 0), 255);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if (dst_u8) dst_u8[(size_t)e * C + c] = (uint8_t)out[c];
+      if (dst_f32) dst_f32[(((size_t)n * C + c) * dh + y) * dw + x] = __fdiv_rn((float)out[c], 255.f);
+    }
+  }
+}
+
+void launch_resize_u8(const uint8_t* src, int B, int sh, int sw, int C, int dh, int dw, int interp, uint8_t* dst_u8,
+                      float* dst_f32, cudaStream_t s) {
+  double sx, sy;
+  if (interp == 0) { sx = 1.0 / ((double)dw / sw); sy = 1.0 / ((double)dh / sh); }
+  else { sx = (double)sw / dw; sy = (double)sh / dh; }
+  long long total = (long long)B * dh * dw;
+  int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  if (C == 4) resize_u8_kernel<4><<<grid, 256, 0, s>>>(src, B, sh, sw, dh, dw, interp, sx, sy, dst_u8, dst_f32);
+  else resize_u8_kernel<1><<<grid, 256, 0, s>>>(src, B, sh, sw, dh, dw, interp, sx, sy, dst_u8, dst_f32);
+}
 }  // namespace ysp

@@ -68,3 +68,36 @@ def scale_boxes(img1_shape, boxes: torch.Tensor, img0_shape, ratio_pad=None, pad
         check(lib().ysp_scale_boxes(boxes.data_ptr(), n, row, float(gain), float(pad_x), float(pad_y), float(img0_shape[1]),
                                     float(img0_shape[0]), torch.cuda.current_stream(boxes.device).cuda_stream))
     return boxes
+
+
+INTER_NEAREST, INTER_LINEAR = 0, 1          # cv2's values
+
+
+def resize_u8(src: torch.Tensor, size, interpolation: int = INTER_LINEAR, to_tensor: bool = False):
+    """`cv2.resize(src, (W, H), interpolation=...)` for a BATCH of decoded uint8 slices on the device, bit-exact with
+    OpenCV (/root/reference/dataset.py:59-65).  src uint8 [B,h,w,4] / [B,h,w,1] / [B,h,w]; `size` int or (H, W).
+    Returns uint8 in the input's layout, or with `to_tensor=True` what `transforms.ToTensor()` makes of it
+    (dataset.py:68-70): float32 [B,C,H,W] = value / 255."""
+    require_cuda(src, "resize_u8")
+    if src.dtype != torch.uint8:
+        raise TypeError(f"resize_u8 expects uint8 (decoded PNG), got {src.dtype}")
+    squeeze = src.dim() == 3
+    s4 = (src.unsqueeze(-1) if squeeze else src).contiguous()
+    if s4.dim() != 4 or s4.shape[-1] not in (1, 4):
+        raise ValueError(f"expected [B,h,w,4], [B,h,w,1] or [B,h,w], got {tuple(src.shape)}")
+    B, h, w, C = s4.shape
+    H, W = (size, size) if isinstance(size, int) else size
+    stream = torch.cuda.current_stream(src.device).cuda_stream
+    with torch.cuda.device(src.device):
+        if to_tensor:
+            out = torch.empty(B, C, H, W, dtype=torch.float32, device=src.device)
+            check(lib().ysp_resize_u8(s4.data_ptr(), B, h, w, C, H, W, interpolation, None, out.data_ptr(), stream))
+            return out
+        out = torch.empty(B, H, W, C, dtype=torch.uint8, device=src.device)
+        check(lib().ysp_resize_u8(s4.data_ptr(), B, h, w, C, H, W, interpolation, out.data_ptr(), None, stream))
+    return out.squeeze(-1) if squeeze else out
+
+
+def ingest(img_u8: torch.Tensor, mask_u8: torch.Tensor, size: int):
+    """dataset.py:59-70 for a batch of decoded slices: (img float32 [B,4,S,S], mask float32 [B,1,S,S])."""
+    return (resize_u8(img_u8, size, INTER_LINEAR, to_tensor=True), resize_u8(mask_u8, size, INTER_NEAREST, to_tensor=True))
