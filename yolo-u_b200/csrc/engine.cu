@@ -323,23 +323,28 @@ struct Builder {
     bool has_res = res != nullptr;
     int in_dt = in.dt, out_dt = out.dt;
     TcConvPlan* tcp = nullptr;
+    bool halo = false;
+    const void* w_tc = dc->w_tc; const int Ktc = dc->Ktc;
     if (h->mode == YSP_MODE_BF16 && dc->w_tc && in_dt == DT_BF16 && getenv("YSP_NO_TC") == nullptr) {
       ConvP q = p; q.K = dc->Ktc;
       const char* only = getenv("YSP_TC_ONLY");       // debugging aid: tensor-core path only for matching layers
-      if ((!only || prefix.find(only) != std::string::npos) && tc_conv_supported(q)) {
+      halo = getenv("YSP_NO_HALO") == nullptr && conv_halo_supported(q, in_dt, out_dt);
+      if (halo) {
+      } else if ((!only || prefix.find(only) != std::string::npos) && tc_conv_supported(q)) {
         tcp = tc_conv_plan_create(q, dc->w_tc, out_dt);
         if (tcp) pl->tc_plans.push_back(tcp);
       }
     }
-    if ((in.pw || in.ph) && !tcp) { rc = fail(YSP_EINVAL, "conv %s: pitched input needs the tensor-core path", prefix.c_str()); return; }
+    if ((in.pw || in.ph) && !tcp && !halo) { rc = fail(YSP_EINVAL, "conv %s: pitched input needs the tensor-core path", prefix.c_str()); return; }
     emit([=](RunCtx& c) {
       ConvP q = p;
       q.in = pl->ptr(c, in); q.out = pl->ptr(c, out); q.res = has_res ? pl->ptr(c, rres) : nullptr;
-      if (tcp) launch_conv_tc(tcp, q, c.s);
+      if (halo) launch_conv_halo(q, w_tc, Ktc, c.s);
+      else if (tcp) launch_conv_tc(tcp, q, c.s);
       else launch_conv_dense(q, in_dt, out_dt, c.s);
     }, {&in, &out, res}, 1,
-    StepInfo{prefix, std::string(tcp ? "tc_conv" : "conv") + std::to_string(k) + "x" + std::to_string(k) + (s == 2 ? "s2" : ""),
-             tbytes(in) + tbytes(out) + (res ? tbytes(*res) : 0.0) + (double)dc->K * dc->Cout * (tcp ? 2 : 4),
+    StepInfo{prefix, std::string(halo ? "halo_conv" : tcp ? "tc_conv" : "conv") + std::to_string(k) + "x" + std::to_string(k) + (s == 2 ? "s2" : ""),
+             tbytes(in) + tbytes(out) + (res ? tbytes(*res) : 0.0) + (double)dc->K * dc->Cout * ((tcp || halo) ? 2 : 4),
              2.0 * p.M * (double)dc->K * dc->Cout, 1});
   }
 

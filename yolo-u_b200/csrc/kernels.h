@@ -61,6 +61,10 @@ void tc_conv_plan_destroy(TcConvPlan*);
 void launch_conv_tc(const TcConvPlan* plan, const ConvP& p, cudaStream_t s);
 bool tc_conv_supported(const ConvP& p);
 
+// conv_halo.cu (tcgen05, halo tile + shifted descriptor views: small-channel 3x3 stride-1 convs on maps <= 64 wide)
+bool conv_halo_supported(const ConvP& p, int in_dt, int out_dt);
+void launch_conv_halo(const ConvP& p, const void* w_bf16_kmajor, int Ktc, cudaStream_t s);
+
 }  // namespace ysp
 
 namespace ysp {
