@@ -404,12 +404,72 @@ __global__ void __launch_bounds__(256) eca_scale_kernel(T* x, int HW, int C, int
   }
   store4<T>(x + (size_t)pix * cs + c, v);
 }
+// bf16 fast path: one CTA per slice pools with 16-byte loads (8 channels per thread) and finishes the whole gate
+// (mean -> conv1d k3 -> sigmoid) itself, so the scale pass is a pure 16-byte read-multiply-write stream.
+__global__ void __launch_bounds__(512) eca_gate_bf16_kernel(const bf16* __restrict__ x, int HW, int C, int cs,
+                                                            const float* __restrict__ w3, float* gate) {
+  pdl_sync();
+  extern __shared__ float esm[];               // [lanes][C] partial sums, then [C] means
+  const int G = C >> 3, lanes = blockDim.x / G;
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  const bf16* xb = x + (size_t)blockIdx.x * HW * cs + g * 8;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (lane < lanes) {
+    for (int i = lane; i < HW; i += lanes) {
+      const uint4 v = *reinterpret_cast<const uint4*>(xb + (size_t)i * cs);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[2 * j] += __low2float(h[j]); a[2 * j + 1] += __high2float(h[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) esm[lane * C + g * 8 + j] = a[j];
+  }
+  __syncthreads();
+  float* mean = esm + lanes * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += esm[l * C + c];
+    mean[c] = t / (float)HW;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float z = w3[1] * mean[c];
+    if (c > 0) z += w3[0] * mean[c - 1];
+    if (c + 1 < C) z += w3[2] * mean[c + 1];
+    gate[(size_t)blockIdx.x * C + c] = sigmoid_f(z);
+  }
+}
+__global__ void __launch_bounds__(256) eca_scale_bf16_kernel(bf16* x, int HW, int C, int cs, const float* __restrict__ gate,
+                                                             unsigned total) {
+  pdl_sync();
+  const unsigned e = blockIdx.x * 256u + threadIdx.x;
+  if (e >= total) return;
+  const unsigned G = (unsigned)C >> 3;
+  const unsigned pix = e / G, g = e - pix * G;
+  const unsigned n = pix / (unsigned)HW;
+  const float* gt = gate + (size_t)n * C + g * 8;
+  const float4 g0 = *reinterpret_cast<const float4*>(gt), g1 = *reinterpret_cast<const float4*>(gt + 4);
+  uint4* px = reinterpret_cast<uint4*>(x + (size_t)pix * cs + g * 8);
+  uint4 v = *px;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+  h[0] = __floats2bfloat162_rn(__low2float(h[0]) * g0.x, __high2float(h[0]) * g0.y);
+  h[1] = __floats2bfloat162_rn(__low2float(h[1]) * g0.z, __high2float(h[1]) * g0.w);
+  h[2] = __floats2bfloat162_rn(__low2float(h[2]) * g1.x, __high2float(h[2]) * g1.y);
+  h[3] = __floats2bfloat162_rn(__low2float(h[3]) * g1.z, __high2float(h[3]) * g1.w);
+  *px = v;
+}
+
 void launch_eca(void* x, int N, int HW, int C, int cs, const float* w3, float* mean_ws, int dt, cudaStream_t s) {
   dim3 g(N, cdiv(C, 32));
   long long total = (long long)N * HW * (C >> 2);
   if (dt == DT_F32) {
     launch_pdl(eca_mean_kernel<float>, g, dim3(256), 0, s, (const float*)x, HW, C, cs, mean_ws);
     launch_pdl(eca_scale_kernel<float>, dim3(cdiv(total, 256)), dim3(256), 0, s, (float*)x, HW, C, cs, (const float*)mean_ws, w3, total);
+  } else if (C % 8 == 0 && cs % 8 == 0 && C <= 512 && (long long)N * HW * (C >> 3) < (1ll << 32)) {
+    const int G = C >> 3, lanes = 512 / G;
+    launch_pdl(eca_gate_bf16_kernel, dim3(N), dim3(512), (size_t)(lanes + 1) * C * 4, s, (const bf16*)x, HW, C, cs, w3, mean_ws);
+    const unsigned tot8 = (unsigned)((long long)N * HW * G);
+    launch_pdl(eca_scale_bf16_kernel, dim3(cdiv(tot8, 256)), dim3(256), 0, s, (bf16*)x, HW, C, cs, (const float*)mean_ws, tot8);
   } else {
     launch_pdl(eca_mean_kernel<bf16>, g, dim3(256), 0, s, (const bf16*)x, HW, C, cs, mean_ws);
     launch_pdl(eca_scale_kernel<bf16>, dim3(cdiv(total, 256)), dim3(256), 0, s, (bf16*)x, HW, C, cs, (const float*)mean_ws, w3, total);
@@ -640,12 +700,23 @@ __global__ void __launch_bounds__(256) mask_dice_kernel(const float* __restrict_
   const float* x = lg + (size_t)b * HW;
   const float* t = tg ? tg + (size_t)b * HW : nullptr;
   int ci = 0, cp = 0, ct = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    float s = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x[i])));
+  auto one = [&](float xv, float tv, size_t idx) {
+    float s = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-xv)));
     int pi = s > 0.5f;
-    int ti = t ? (t[i] > 0.5f) : 0;
+    int ti = tv > 0.5f;
     ci += pi & ti; cp += pi; ct += ti;
-    if (mask) mask[(size_t)b * HW + i] = (uint8_t)pi;
+    if (mask) mask[idx] = (uint8_t)pi;
+  };
+  if ((HW & 3) == 0) {                     // 16-byte loads (HW = 57600 on the hot path)
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < HW; i += gridDim.x * blockDim.x * 4) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + i);
+      const float4 tv = t ? *reinterpret_cast<const float4*>(t + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const size_t o = (size_t)b * HW + i;
+      one(xv.x, tv.x, o); one(xv.y, tv.y, o + 1); one(xv.z, tv.z, o + 2); one(xv.w, tv.w, o + 3);
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
+      one(x[i], t ? t[i] : 0.f, (size_t)b * HW + i);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
