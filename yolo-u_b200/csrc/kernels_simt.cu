@@ -4,6 +4,7 @@
 // not a tensor-core GEMM: depthwise convs, resampling, ECA, area-attention core, head decode, layout conversion,
 // mask/Dice counters.  All activations are NHWC views (common.cuh).  Reference semantics cited per kernel.
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -285,8 +286,91 @@ static void conv_dw_tiled_launch(const DwP& p, cudaStream_t s) {
   launch_pdl(conv_dw_tiled_kernel<T, K, TY, TX>, dim3(tiles), dim3(TY * TX), smem, s, p);
 }
 
+// bf16 variant for maps >= 30 wide (Ghost 5x5, Detect 3x3): the tiled kernel above is bound by shared-memory wavefronts
+// (13 LDS.128 per 80 FMAs).  Here the 8 x 32-pixel tile is staged as packed bf16 (pixel pitch 9 words: a warp = one row =
+// 8 channel pairs x 4 strips reads 32 distinct banks per LDS.32), a thread owns ONE channel pair of an 8-pixel strip,
+// and slides a K-wide window over it: K+7 one-wavefront loads + K weight loads per 16K FMAs.
+template <int K>
+__global__ void __launch_bounds__(256) conv_dw_row_kernel(DwP p) {
+  constexpr int TYR = 8, TXR = 32, IH = TYR + K - 1, IW = TXR + K - 1, PSW = 9;
+  pdl_sync();
+  __shared__ uint32_t sIn[IH * IW * PSW];
+  __shared__ __align__(8) float sW[K * K * 16];
+  const int tid = threadIdx.x;
+  const int tiles_x = (p.W + TXR - 1) / TXR, tiles_y = (p.H + TYR - 1) / TYR;
+  int t = blockIdx.x;
+  const int tx0 = (t % tiles_x) * TXR; t /= tiles_x;
+  const int ty0 = (t % tiles_y) * TYR; t /= tiles_y;
+  const int ngrp = (p.C + 15) >> 4;
+  const int cg = (t % ngrp) << 4;
+  const int n = t / ngrp;
+  const int nq = min(4, (p.C - cg) >> 2);            // valid channel quads in this group
+  const bf16* __restrict__ in = reinterpret_cast<const bf16*>(p.in);
+  const int cin = (cg / p.grp) * p.grp_stride + (cg % p.grp);
+  for (int i = tid; i < K * K * 16; i += 256) sW[i] = ((i & 15) >> 2) < nq ? p.w[(size_t)(i >> 4) * p.C + cg + (i & 15)] : 0.f;
+  for (int i = tid; i < IH * IW * 4; i += 256) {
+    const int q = i & 3, pp = i >> 2;
+    const int iy = ty0 + pp / IW - K / 2, ix = tx0 + pp % IW - K / 2;
+    uint2 v = make_uint2(0u, 0u);
+    if (q < nq && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+      v = *reinterpret_cast<const uint2*>(in + ((size_t)(n * p.H + iy) * p.W + ix) * p.in_cs + cin + q * 4);
+    sIn[pp * PSW + q * 2] = v.x;
+    sIn[pp * PSW + q * 2 + 1] = v.y;
+  }
+  __syncthreads();
+  const int cp = tid & 7, strip = (tid >> 3) & 3, ty = tid >> 5;
+  float2 acc[8];
+  const float2 bias = (cp >> 1) < nq ? *reinterpret_cast<const float2*>(p.bias + cg + cp * 2) : make_float2(0.f, 0.f);
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = bias;
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    const uint32_t* rp = sIn + ((ty + r) * IW + strip * 8) * PSW + cp;
+    float2 v[K + 7], w[K];
+#pragma unroll
+    for (int j = 0; j < K + 7; ++j) {
+      const uint32_t u = rp[j * PSW];
+      v[j] = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < K; ++s2) w[s2] = *reinterpret_cast<const float2*>(sW + (r * K + s2) * 16 + cp * 2);
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+      for (int s2 = 0; s2 < K; ++s2) {
+        acc[o].x = fmaf(v[o + s2].x, w[s2].x, acc[o].x);
+        acc[o].y = fmaf(v[o + s2].y, w[s2].y, acc[o].y);
+      }
+  }
+  const int y = ty0 + ty;
+  if (y >= p.H || (cp >> 1) >= nq) return;
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const int x = tx0 + strip * 8 + o;
+    if (x >= p.W) break;
+    const size_t pix = (size_t)(n * p.H + y) * p.W + x;
+    float a = apply_act(acc[o].x, p.act), b = apply_act(acc[o].y, p.act);
+    if (p.res) {
+      const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const bf16*>(p.res) + pix * p.res_cs + cg + cp * 2);
+      a += __low2float(rv); b += __high2float(rv);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<bf16*>(p.out) + pix * p.out_cs + cg + cp * 2) = __floats2bfloat162_rn(a, b);
+  }
+}
+
+template <int K>
+static void conv_dw_row_launch(const DwP& p, cudaStream_t s) {
+  const int tiles = ((p.W + 31) / 32) * ((p.H + 7) / 8) * ((p.C + 15) >> 4) * p.N;
+  launch_pdl(conv_dw_row_kernel<K>, dim3(tiles), dim3(256), 0, s, p);
+}
+
 template <typename T>
 static void conv_dw_dispatch(const DwP& p, long long total, int g, cudaStream_t s) {
+  if (sizeof(T) == 2 && p.W >= 30 && (p.C % 4 == 0) && (p.grp % 16 == 0 || p.grp == p.C) && (p.k == 3 || p.k == 5) &&
+      getenv("YSP_NO_DWROW") == nullptr) {
+    if (p.k == 3) conv_dw_row_launch<3>(p, s); else conv_dw_row_launch<5>(p, s);
+    return;
+  }
   const bool tileable = (p.C % 4 == 0) && (p.grp % 16 == 0 || p.grp == p.C);
   if (tileable && (p.k == 3 || p.k == 5 || p.k == 7)) {
     const bool small = p.H <= 8 && p.W <= 8;
@@ -350,9 +434,42 @@ __global__ void __launch_bounds__(256) ew_kernel(EwP p, long long total) {
   store4<T>(reinterpret_cast<T*>(p.out) + (size_t)pix * p.out_cs + c, o);
 }
 
+// bf16 fast path for add / nearest x2: 16-byte vectors (8 channels), 32-bit index arithmetic
+template <int MODE>
+__global__ void __launch_bounds__(256) ew8_bf16_kernel(EwP p, unsigned total) {
+  pdl_sync();
+  const unsigned e = blockIdx.x * 256u + threadIdx.x;
+  if (e >= total) return;
+  const unsigned G = (unsigned)p.C >> 3;
+  const unsigned pix = e / G, c = (e - pix * G) << 3;
+  const bf16* a = reinterpret_cast<const bf16*>(p.a);
+  uint4 o;
+  if (MODE == 0) {
+    const uint4 x = *reinterpret_cast<const uint4*>(a + (size_t)pix * p.a_cs + c);
+    const uint4 y = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.b) + (size_t)pix * p.b_cs + c);
+    const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&x);
+    const __nv_bfloat162* hy = reinterpret_cast<const __nv_bfloat162*>(&y);
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)      // fp32 add, one rounding: same result as the generic kernel
+      ho[i] = __floats2bfloat162_rn(__low2float(hx[i]) + __low2float(hy[i]), __high2float(hx[i]) + __high2float(hy[i]));
+  } else {
+    const unsigned ox = pix % (unsigned)p.OW, t = pix / (unsigned)p.OW;
+    const unsigned oy = t % (unsigned)p.OH, n = t / (unsigned)p.OH;
+    o = *reinterpret_cast<const uint4*>(a + ((size_t)(n * p.H + (oy >> 1)) * p.W + (ox >> 1)) * p.a_cs + c);
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (size_t)pix * p.out_cs + c) = o;
+}
+
 template <int MODE>
 static void ew_launch(const EwP& p, int dt, cudaStream_t s) {
   long long total = (long long)p.N * p.OH * p.OW * (p.C >> 2);
+  if (dt == DT_BF16 && MODE < 2 && p.C % 8 == 0 && p.a_cs % 8 == 0 && p.out_cs % 8 == 0 && (MODE == 1 || p.b_cs % 8 == 0) &&
+      total / 2 < (1ll << 32)) {
+    const unsigned t8 = (unsigned)(total / 2);
+    launch_pdl(ew8_bf16_kernel<MODE>, dim3(cdiv(t8, 256)), dim3(256), 0, s, p, t8);
+    return;
+  }
   int g = cdiv(total, 256);
   if (dt == DT_F32) launch_pdl(ew_kernel<float, MODE>, dim3(g), dim3(256), 0, s, p, total);
   else launch_pdl(ew_kernel<bf16, MODE>, dim3(g), dim3(256), 0, s, p, total);
