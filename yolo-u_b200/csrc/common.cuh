@@ -43,6 +43,18 @@ template <> __device__ __forceinline__ void store4<bf16>(bf16* p, const F4& r) {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float apply_act(float x, int act) { return act == ACT_SILU ? silu_f(x) : x; }
+// SiLU(x) = h + h*tanh(h), h = x/2: one MUFU op (tanh.approx, rel. error ~2^-11 -- below bf16 resolution).  Used wherever
+// the result is stored as bf16 (throughput mode); the fp32 parity mode keeps the exact expf form above.
+__device__ __forceinline__ float silu_approx(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+template <typename T> __device__ __forceinline__ float silu_for(float x);
+template <> __device__ __forceinline__ float silu_for<float>(float x) { return silu_f(x); }
+template <> __device__ __forceinline__ float silu_for<bf16>(float x) { return silu_approx(x); }
+template <typename T> __device__ __forceinline__ float apply_act_for(float x, int act) { return act == ACT_SILU ? silu_for<T>(x) : x; }
 
 // ---- parameter blocks ----------------------------------------------------------------------------------------------
 // Activations are NHWC "views": base pointer already advanced to the first channel of the view, `cs` = pixel stride

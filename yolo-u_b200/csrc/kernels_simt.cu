@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(256) conv_dw_kernel(DwP p, long long total) {
   }
   float4 b = *reinterpret_cast<const float4*>(p.bias + c);
   F4 o;
-  o.v[0] = apply_act(a0 + b.x, p.act); o.v[1] = apply_act(a1 + b.y, p.act);
-  o.v[2] = apply_act(a2 + b.z, p.act); o.v[3] = apply_act(a3 + b.w, p.act);
+  o.v[0] = apply_act_for<T>(a0 + b.x, p.act); o.v[1] = apply_act_for<T>(a1 + b.y, p.act);
+  o.v[2] = apply_act_for<T>(a2 + b.z, p.act); o.v[3] = apply_act_for<T>(a3 + b.w, p.act);
   if (p.res) {
     F4 rv = load4<T>(reinterpret_cast<const T*>(p.res) + (size_t)pix * p.res_cs + c);
 #pragma unroll
@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(TY * TX) conv_dw_tiled_kernel(DwP p) {
     if (x >= p.W) break;
     const size_t pix = (size_t)(n * p.H + y) * p.W + x;
     F4 ov;
-    ov.v[0] = apply_act(acc[o].x, p.act); ov.v[1] = apply_act(acc[o].y, p.act);
-    ov.v[2] = apply_act(acc[o].z, p.act); ov.v[3] = apply_act(acc[o].w, p.act);
+    ov.v[0] = apply_act_for<T>(acc[o].x, p.act); ov.v[1] = apply_act_for<T>(acc[o].y, p.act);
+    ov.v[2] = apply_act_for<T>(acc[o].z, p.act); ov.v[3] = apply_act_for<T>(acc[o].w, p.act);
     if (p.res) {
       F4 rv = load4<T>(reinterpret_cast<const T*>(p.res) + pix * p.res_cs + cg + q * 4);
 #pragma unroll
@@ -308,14 +308,21 @@ __global__ void __launch_bounds__(256) conv_dw_row_kernel(DwP p) {
   const bf16* __restrict__ in = reinterpret_cast<const bf16*>(p.in);
   const int cin = (cg / p.grp) * p.grp_stride + (cg % p.grp);
   for (int i = tid; i < K * K * 16; i += 256) sW[i] = ((i & 15) >> 2) < nq ? p.w[(size_t)(i >> 4) * p.C + cg + (i & 15)] : 0.f;
-  for (int i = tid; i < IH * IW * 4; i += 256) {
-    const int q = i & 3, pp = i >> 2;
-    const int iy = ty0 + pp / IW - K / 2, ix = tx0 + pp % IW - K / 2;
-    uint2 v = make_uint2(0u, 0u);
-    if (q < nq && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-      v = *reinterpret_cast<const uint2*>(in + ((size_t)(n * p.H + iy) * p.W + ix) * p.in_cs + cin + q * 4);
-    sIn[pp * PSW + q * 2] = v.x;
-    sIn[pp * PSW + q * 2 + 1] = v.y;
+  {
+    const int q = tid & 3;
+    int pp = tid >> 2, ry = pp / IW, rx = pp - ry * IW;              // 64 pixels per pass: (ry, rx) advance incrementally
+    const bf16* base = in + (size_t)n * p.H * p.W * p.in_cs + cin + q * 4;
+#pragma unroll 2
+    for (; pp < IH * IW; pp += 64) {
+      const int iy = ty0 + ry - K / 2, ix = tx0 + rx - K / 2;
+      uint2 v = make_uint2(0u, 0u);
+      if (q < nq && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+        v = *reinterpret_cast<const uint2*>(base + (size_t)(iy * p.W + ix) * p.in_cs);
+      sIn[pp * PSW + q * 2] = v.x;
+      sIn[pp * PSW + q * 2 + 1] = v.y;
+      rx += 64 % IW; ry += 64 / IW;
+      if (rx >= IW) { rx -= IW; ++ry; }
+    }
   }
   __syncthreads();
   const int cp = tid & 7, strip = (tid >> 3) & 3, ty = tid >> 5;
@@ -349,7 +356,7 @@ __global__ void __launch_bounds__(256) conv_dw_row_kernel(DwP p) {
     const int x = tx0 + strip * 8 + o;
     if (x >= p.W) break;
     const size_t pix = (size_t)(n * p.H + y) * p.W + x;
-    float a = apply_act(acc[o].x, p.act), b = apply_act(acc[o].y, p.act);
+    float a = apply_act_for<bf16>(acc[o].x, p.act), b = apply_act_for<bf16>(acc[o].y, p.act);
     if (p.res) {
       const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const bf16*>(p.res) + pix * p.res_cs + cg + cp * 2);
       a += __low2float(rv); b += __high2float(rv);

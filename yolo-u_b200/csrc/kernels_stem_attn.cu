@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const void* __restrict__
     for (int j4 = 0; j4 < 4; ++j4) {
       F4 v;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v.v[j] = silu_f(acc[q][j4 * 4 + j]);
+      for (int j = 0; j < 4; ++j) v.v[j] = silu_for<T>(acc[q][j4 * 4 + j]);
       store4<T>(o + j4 * 4, v);
     }
   }
