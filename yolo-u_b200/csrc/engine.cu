@@ -634,6 +634,9 @@ static void assign_offsets(Plan* plan, bool keep_all) {
   plan->ws_bytes = top;
 }
 
+static cudaEvent_t sync_event(ysp_handle* h, size_t i);
+enum { EV_BOTT = 53 };   // recorded by the detector plan when the bottleneck logits are written (see ysp_pipeline)
+
 static void input_step(Builder& g, TRef x, int B, int H, int W) {
   Plan* pl = g.plan; int dt = g.dt;
   g.emit([=](RunCtx& c) {
@@ -670,32 +673,51 @@ static int build_detector(ysp_handle* h, Plan* plan, int B, int H, int W) {
   TRef t11 = Builder::slice(cat16, 64, 128);   g.a2c2f("model.11", cat10, t11, 1, false, -1); g.name("model.11", t11);
   g.ew(1, t11, nullptr, Builder::slice(cat13, 0, 128));                                      // 12, 13
   TRef t14 = g.alloc(B, h8, w8, 64);   g.a2c2f("model.14", cat13, t14, 1, false, -1);       g.name("model.14", t14);
+  // Detect (nc=1): raw maps NHWC fp32 [.., 65] (row stride 68).  The P3 class branch only needs layer 14, and its last
+  // channel is the seg head's bottleneck (evaluate_model.py:142-144): it runs on a side lane NEXT TO layers 15-20 and
+  // publishes the bottleneck (event EV_BOTT) so that the decoder can start a millisecond before the detector is done.
+  TRef raws[3];
+  raws[0] = g.alloc(B, t14.H, t14.W, 65, DT_F32, 68);
+  auto cls_branch = [&](int i, const TRef& f) {
+    std::string s = std::to_string(i);
+    TRef d1 = g.alloc(B, f.H, f.W, f.C), p1 = g.alloc(B, f.H, f.W, 64), d2 = g.alloc(B, f.H, f.W, 64),
+         p2 = g.alloc(B, f.H, f.W, 64);
+    g.dw("model.21.cv3." + s + ".0.0", f, d1, 3, ACT_SILU);
+    g.conv("model.21.cv3." + s + ".0.1", d1, p1, 1, 1, ACT_SILU);
+    g.dw("model.21.cv3." + s + ".1.0", p1, d2, 3, ACT_SILU);
+    g.conv("model.21.cv3." + s + ".1.1", d2, p2, 1, 1, ACT_SILU);
+    g.conv("model.21.cv3." + s + ".2", p2, Builder::slice(raws[i], 64, 1), 1, 1, ACT_NONE);
+  };
+  g.fork();
+  g.lane(1);
+  cls_branch(0, t14);
+  {
+    Plan* pl0 = plan; TRef r0 = raws[0]; ysp_handle* hh = h;
+    const int bh = H / 8, bw = W / 8;
+    g.emit([=](RunCtx& c) {
+      if (c.ext[X_BOTT]) launch_bottleneck_nhwc((const float*)pl0->ptr(c, r0), 68, 64, B, r0.H, r0.W, (float*)c.ext[X_BOTT], bh, bw, c.s);
+      cudaEventRecord(sync_event(hh, EV_BOTT), c.s);
+    }, {&r0}, 1, StepInfo{"bottleneck", "bottleneck", (double)B * bh * bw * 8, 0.0, 1});
+  }
+  g.lane(0);
   g.conv("model.15", t14, Builder::slice(cat16, 0, 64), 3, 2, ACT_SILU);                     // 15, 16
   TRef t17 = g.alloc(B, h16, w16, 128); g.a2c2f("model.17", cat16, t17, 1, false, -1);      g.name("model.17", t17);
   g.conv("model.18", t17, Builder::slice(cat19, 0, 128), 3, 2, ACT_SILU);                    // 18, 19
   TRef t20 = g.alloc(B, h32, w32, 256); g.c3k2("model.20", cat19, t20, true, 0.5, true);    g.name("model.20", t20);
-  // Detect (nc=1): raw maps NHWC fp32 [.., 65] (row stride 68)
+  g.join();
   TRef feats[3] = {t14, t17, t20};
-  TRef raws[3];
-  g.fork();                                   // 3 levels x (box branch, class branch) = 6 independent chains
+  g.fork();                                   // the remaining 5 chains: 3 box branches + class branches of P4, P5
   for (int i = 0; i < 3; ++i) {
     TRef f = feats[i];
     std::string s = std::to_string(i);
-    TRef raw = g.alloc(B, f.H, f.W, 65, DT_F32, 68);
-    raws[i] = raw;
+    if (i > 0) raws[i] = g.alloc(B, f.H, f.W, 65, DT_F32, 68);
+    TRef raw = raws[i];
     TRef a = g.alloc(B, f.H, f.W, 64), b = g.alloc(B, f.H, f.W, 64);
     g.lane(2 * i);
     g.conv("model.21.cv2." + s + ".0", f, a, 3, 1, ACT_SILU);
     g.conv("model.21.cv2." + s + ".1", a, b, 3, 1, ACT_SILU);
     g.conv("model.21.cv2." + s + ".2", b, Builder::slice(raw, 0, 64), 1, 1, ACT_NONE);
-    TRef d1 = g.alloc(B, f.H, f.W, f.C), p1 = g.alloc(B, f.H, f.W, 64), d2 = g.alloc(B, f.H, f.W, 64),
-         p2 = g.alloc(B, f.H, f.W, 64);
-    g.lane(2 * i + 1);
-    g.dw("model.21.cv3." + s + ".0.0", f, d1, 3, ACT_SILU);
-    g.conv("model.21.cv3." + s + ".0.1", d1, p1, 1, 1, ACT_SILU);
-    g.dw("model.21.cv3." + s + ".1.0", p1, d2, 3, ACT_SILU);
-    g.conv("model.21.cv3." + s + ".1.1", d2, p2, 1, 1, ACT_SILU);
-    g.conv("model.21.cv3." + s + ".2", p2, Builder::slice(raw, 64, 1), 1, 1, ACT_NONE);
+    if (i > 0) { g.lane(2 * i + 1); cls_branch(i, f); }
   }
   g.join();
   if (g.rc) return g.rc;
@@ -711,7 +733,7 @@ static int build_detector(ysp_handle* h, Plan* plan, int B, int H, int W) {
     DecodeP q = dp;
     q.raw[0] = (const float*)pl->ptr(c, r0); q.raw[1] = (const float*)pl->ptr(c, r1); q.raw[2] = (const float*)pl->ptr(c, r2);
     q.y = (float*)c.ext[X_Y]; q.p[0] = (float*)c.ext[X_P3]; q.p[1] = (float*)c.ext[X_P4]; q.p[2] = (float*)c.ext[X_P5];
-    q.bott = (float*)c.ext[X_BOTT];
+    q.bott = nullptr;                             // already published by the "bottleneck" step above
     launch_detect_decode(q, c.s);
   }, {&r0, &r1, &r2}, 1, StepInfo{"detect_decode", "detect_decode", (double)B * dp.A * (65 * 4 * 2 + 5 * 4), (double)B * dp.A * 200.0, 1});
   assign_offsets(plan, h->keep_all);
@@ -1157,28 +1179,35 @@ int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, 
       cudaStreamWaitEvent(s2, sync_event(h, EV_E1), 0);
     }
     if ((rc = run_plan(h, ps, c2, 0, ps->split, 24))) return rc;                         // seg encoder on the aux stream
-    cudaEventRecord(sync_event(h, EV_ENC), s2);
   }
   if ((rc = run_plan(h, pd, c, det_lo))) return rc;                                     // evaluate_model.py:141-144
   cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
   if (h->profiling) { for (auto& e : pe) cudaEventCreate(&e); cudaEventRecord(pe[0], s); }
-  if (overlap) {                                                                         // NMS on aux, concurrent with the decoder
-    cudaEventRecord(sync_event(h, EV_DET), s);
-    cudaStreamWaitEvent(s2, sync_event(h, EV_DET), 0);
+  if (overlap) {
+    // aux stream: the decoder starts as soon as the detector plan has published the bottleneck (EV_BOTT, recorded on the
+    // P3 class-branch lane), i.e. concurrently with detector layers 15-20, the rest of the Detect head, decode and NMS
+    cudaStreamWaitEvent(s2, sync_event(h, EV_BOTT), 0);
+    if ((rc = run_plan(h, ps, c2, ps->split, -1, 24))) return rc;                        // :156
+    launch_mask_dice(io->d_mask_logits, io->d_target, B, H * W, io->d_counts, io->d_mask, s2);   // :157-174
+    cudaEventRecord(sync_event(h, EV_ENC), s2);
+    if (launch_nms(y, B, 5, A, 1, io->conf_thres, io->iou_thres, max_det, 30000, 7680.f, 0, nullptr, 0, io->d_det_boxes,
+                   io->d_det_idx, io->d_det_count, ws + off_n, ws_bytes - off_n, s))     // :147
+      return fail(YSP_ESTATE, "nms workspace");
+    cudaStreamWaitEvent(s, sync_event(h, EV_ENC), 0);
+    h->last_launches += 3;
+    CUDA_OK(cudaGetLastError());
+    return 0;
   }
   if (launch_nms(y, B, 5, A, 1, io->conf_thres, io->iou_thres, max_det, 30000, 7680.f, 0, nullptr, 0, io->d_det_boxes,
-                 io->d_det_idx, io->d_det_count, ws + off_n, ws_bytes - off_n, s2))      // :147
+                 io->d_det_idx, io->d_det_count, ws + off_n, ws_bytes - off_n, s))       // :147
     return fail(YSP_ESTATE, "nms workspace");
-  if (overlap) cudaEventRecord(sync_event(h, EV_NMS), s2);
   if (h->profiling) cudaEventRecord(pe[1], s);
   h->last_launches += 2;
   c2.s = s;
-  if (overlap) cudaStreamWaitEvent(s, sync_event(h, EV_ENC), 0);
-  if ((rc = run_plan(h, ps, c2, overlap ? ps->split : 0, -1, 24))) return rc;           // :156
+  if ((rc = run_plan(h, ps, c2, 0, -1, 24))) return rc;                                  // :156
   if (h->profiling) cudaEventRecord(pe[2], s);
   launch_mask_dice(io->d_mask_logits, io->d_target, B, H * W, io->d_counts, io->d_mask, s);   // :157-174
   h->last_launches += 1;
-  if (overlap) cudaStreamWaitEvent(s, sync_event(h, EV_NMS), 0);
   if (h->profiling) {
     cudaEventRecord(pe[3], s);
     cudaStreamSynchronize(s);

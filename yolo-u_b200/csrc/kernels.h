@@ -29,6 +29,7 @@ struct DecodeP {
   float* bott; int bh, bw;     // sigmoid(raw0[..., 64+nc-1]) cropped to bh x bw (fp32 [B,1,bh,bw]) or NULL
 };
 void launch_detect_decode(const DecodeP& p, cudaStream_t s);
+void launch_bottleneck_nhwc(const float* raw, int cs, int ch, int B, int Hs, int Ws, float* logits, int h, int w, cudaStream_t s);
 void launch_bottleneck(const float* p3, int B, int C, int Hs, int Ws, float* logits, int h, int w, cudaStream_t s);
 void launch_mask_dice(const float* logits, const float* target, int B, int HW, int32_t* counts, uint8_t* mask,
                       cudaStream_t s);

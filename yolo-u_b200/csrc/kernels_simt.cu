@@ -808,6 +808,20 @@ __global__ void __launch_bounds__(256) bottleneck_kernel(const float* __restrict
   long long b = t / h;
   out[e] = sigmoid_f(p3[(((size_t)b * C + (C - 1)) * Hs + y) * Ws + x]);
 }
+// same op on the engine's NHWC raw P3 map (fp32, pixel stride cs, class logit at channel ch): lets the pipeline publish
+// the bottleneck as soon as the P3 class branch is done, before the rest of the Detect head
+__global__ void __launch_bounds__(256) bottleneck_nhwc_kernel(const float* __restrict__ raw, int cs, int ch, int Hs, int Ws,
+                                                              float* __restrict__ out, int h, int w, int total) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int x = e % w, t = e / w;
+  const int y = t % h, b = t / h;
+  out[e] = sigmoid_f(raw[((size_t)(b * Hs + y) * Ws + x) * cs + ch]);
+}
+void launch_bottleneck_nhwc(const float* raw, int cs, int ch, int B, int Hs, int Ws, float* logits, int h, int w, cudaStream_t s) {
+  const int total = B * h * w;
+  bottleneck_nhwc_kernel<<<cdiv(total, 256), 256, 0, s>>>(raw, cs, ch, Hs, Ws, logits, h, w, total);
+}
 void launch_bottleneck(const float* p3, int B, int C, int Hs, int Ws, float* logits, int h, int w, cudaStream_t s) {
   long long total = (long long)B * h * w;
   bottleneck_kernel<<<cdiv(total, 256), 256, 0, s>>>(p3, C, Hs, Ws, logits, h, w, total);
