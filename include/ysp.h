@@ -128,6 +128,12 @@ typedef struct ysp_pipeline_io {
 int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, void* d_ws, size_t ws_bytes,
                  void* stream);
 
+/* The detection-confidence gate sketched (commented out) at evaluate_model.py:149-155, applied to the outputs of
+ * ysp_pipeline / ysp_nms + ysp_mask_dice: a slice with no detection, or whose best detection has conf <= conf_gate, gets an
+ * all-zero predicted mask: counts[b] = (0, 0, |T|), d_mask[b] zeroed (optional), d_gated[b] = 1 (optional). */
+int ysp_conf_gate(const float* d_det_boxes, const int32_t* d_det_count, int B, int max_det, int row, float conf_gate,
+                  int32_t* d_counts, uint8_t* d_mask, int HW, uint8_t* d_gated, void* stream);
+
 /* -- slice ingest (dataset.py:59-70) ---------------------------------------------------------------------
  * cv2.resize on decoded uint8 slices + transforms.ToTensor, on device and bit-exact with OpenCV's generic uint8 path:
  * interp 1 = INTER_LINEAR (image, dataset.py:63), 0 = INTER_NEAREST (mask, dataset.py:65).  src u8 [B,h,w,C], C = 4

@@ -152,3 +152,29 @@ def test_shared_stem_is_exact(ysp, models, monkeypatch):
     assert P2.engine.launches_total > 0
     assert torch.equal(a["mask_logits"], b["mask_logits"]) and torch.equal(a["counts"], b["counts"])
     assert torch.equal(a["det_idx"], b["det_idx"]) and torch.equal(a["y"], b["y"])
+
+
+def test_confidence_gate_matches_sketch():
+    """evaluate_model.py:149-155 (commented-out sketch): no detection, or best conf <= gate -> all-zero predicted mask."""
+    import torch
+    import yolo_u_b200 as ysp
+    from oracle.model import build_models, synth_inputs
+    pred, seg = build_models(0)
+    P = ysp.Predictor.from_modules(pred, seg, device="cuda:0", mode="fp32")
+    x, _, tg = synth_inputs(4, 240)
+    x[1] = 0.0                                   # a blank slice: few / weak detections
+    _, dets0, _, counts0 = P.predict(x.cuda(), tg.cuda())
+    counts0 = counts0.clone()
+    best = torch.tensor([float(d[0, 4]) if len(d) else -1.0 for d in dets0])
+    gate = float(best.sort().values[1:3].mean())  # between the 2nd and 3rd best confidence: gates some, keeps some
+    _, dets, _, counts = P.predict(x.cuda(), tg.cuda(), conf_gate=gate)
+    want_gated = (best <= gate)
+    assert want_gated.any() and not want_gated.all()
+    assert torch.equal(P.gated.cpu().bool(), want_gated)
+    for b in range(4):
+        if want_gated[b]:
+            assert counts[b, 0] == 0 and counts[b, 1] == 0 and counts[b, 2] == counts0[b, 2]
+            assert int(P._out["mask"][b].sum()) == 0
+        else:
+            assert torch.equal(counts[b], counts0[b])
+            assert int(P._out["mask"][b].sum()) == int(counts0[b, 1])

@@ -146,3 +146,44 @@ def test_bf16_mode_bounds(ysp, models, ref240):
     assert flips <= TOL_FLIP_BF16
     assert (d - d_ref).abs().max().item() <= TOL_DICE_BF16
     assert torch.equal(counts.cpu().long(), mask_counts(ml, ref240["tg"]))   # counters exact on our own logits
+
+
+def test_no_logit_ablation_variant():
+    """`_YOLOSegPlusPlus.py` (reference ablation: decoder.0 = C3Ghost(128, 96), input = skip only): the engine detects
+    it from the checkpoint's decoder.0.0.cv1 shape; parity vs the same modification of the oracle module."""
+    import torch
+    import yolo_u_b200 as ysp
+    from oracle.model import build_models, synth_init_, synth_inputs
+    from oracle.modules import C3Ghost
+    pred, seg = build_models(0)
+    seg.decoder[0][0] = C3Ghost(128, 96, n=1)
+    synth_init_(seg.decoder[0][0], 11, lin_gain=2.0)
+    seg.eval()
+
+    def ref_forward(x):
+        skips = []
+        for idx, m in enumerate(seg.encoder):
+            x = m(x)
+            if idx in (2, 4):
+                skips.append(x)
+        for idx, m in enumerate(seg.decoder):
+            if idx == 0:
+                x = skips.pop()
+            elif idx == 2:
+                x = torch.cat([x, skips.pop()], 1)
+            x = m(x)
+        return seg.output(x)
+
+    x, lg, _ = synth_inputs(2, 96)
+    with torch.no_grad():
+        want = ref_forward(x)
+    m = ysp.YOLOSegPlusPlus(pred, mode="fp32", use_logits=False)
+    m.load_state_dict(seg.state_dict(), strict=True)
+    got = m(x.cuda())
+    assert (got.cpu() - want).abs().max().item() <= 1e-3
+    got2 = m(x.cuda(), lg.cuda())                       # a logits argument is accepted and ignored
+    assert torch.equal(got, got2)
+    mb = ysp.YOLOSegPlusPlus(pred, mode="bf16", use_logits=False)
+    mb.load_state_dict(seg.state_dict(), strict=True)
+    # bf16 storage: the synthetic head of this variant is not re-calibrated, so bound the error relative to the logit scale
+    assert (mb(x.cuda()).cpu() - want).abs().max().item() <= 0.05 * want.abs().max().item() + 0.05

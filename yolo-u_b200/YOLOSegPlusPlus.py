@@ -91,7 +91,7 @@ class YOLOSegPlusPlus(nn.Module):
     """
 
     def __init__(self, predictor, verbose: bool = False, target_modules_indices: List[int] = [2, 4, 6],
-                 mode: str = "fp32"):
+                 mode: str = "fp32", use_logits: bool = True):
         super().__init__()
         self.encoder = nn.ModuleList(module for module in predictor.model.model.model[0:5])
         for param in self.encoder.parameters():
@@ -99,7 +99,8 @@ class YOLOSegPlusPlus(nn.Module):
         self.encoder.eval()
         self.upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=False)
         self.decoder = nn.ModuleList([
-            nn.Sequential(C3Ghost(128 + 1, 96, n=1), ECA()),
+            # use_logits=False = the reference's ablation module `_YOLOSegPlusPlus.py` (no bottleneck channel, :157)
+            nn.Sequential(C3Ghost(128 + (1 if use_logits else 0), 96, n=1), ECA()),
             nn.Sequential(self.upsample, DoubleLightConv(96, 64)),
             nn.Sequential(C3Ghost(64 + 64, 64), ECA()),
             nn.Sequential(self.upsample, DoubleLightConv(64, 32)),
@@ -112,6 +113,7 @@ class YOLOSegPlusPlus(nn.Module):
         self.skip_connections = []
         self._indices = {"upsample": {2, 5, 6}, "skip_connections_encoder": {2, 4}, "skip_connections_decoder": {0, 2}}
         self.mode = mode
+        self.use_logits = use_logits
         self._engine: Optional[Engine] = None
         self._engine_key = None
 
@@ -133,6 +135,11 @@ class YOLOSegPlusPlus(nn.Module):
         return None
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, logits: torch.Tensor) -> torch.Tensor:
-        """x [B,4,H,W] fp32, logits [B,1,H/8,W/8] -> [B,1,H,W] mask logits (YOLOSegPlusPlus.py:242-272)."""
+    def forward(self, x: torch.Tensor, logits: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x [B,4,H,W] fp32, logits [B,1,H/8,W/8] -> [B,1,H,W] mask logits (YOLOSegPlusPlus.py:242-272).
+        With `use_logits=False` (ablation checkpoint) `logits` is ignored, as `_YOLOSegPlusPlus.forward(x)` has none."""
+        if logits is None or not self.use_logits:
+            if self.use_logits:
+                raise TypeError("forward() missing the `logits` bottleneck [B,1,H/8,W/8]")
+            logits = torch.zeros(x.shape[0], 1, x.shape[2] // 8, x.shape[3] // 8, device=x.device)
         return self.engine(x.device).segpp_forward(x, logits)

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "ysp_objectmap_transform": (i32, [vp, vp, i32, i32, vp]),
     "ysp_scale_boxes": (i32, [vp, C.c_longlong, i32, f32, f32, f32, f32, f32, vp]),
     "ysp_pipeline": (i32, [vp, C.POINTER(PipelineIO), i32, i32, i32, vp, sz, vp]),
+    "ysp_conf_gate": (i32, [vp, vp, i32, i32, i32, f32, vp, vp, i32, vp, vp]),
     "ysp_resize_u8": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "ysp_train_create": (i32, [C.POINTER(vp), i32, i32, i32, i32]),
     "ysp_train_destroy": (None, [vp]),

@@ -764,13 +764,21 @@ static int build_seg(ysp_handle* h, Plan* plan, int B, int H, int W, bool shared
   TRef cat2 = g.alloc(B, h4, w4, 128);          // dec2 input: [dec1 out 64 | skipA 64]
   TRef skipA = Builder::slice(cat2, 64, 64);    g.c3k2("encoder.2", e1, skipA, false, 0.25, true);   g.name("encoder.2", skipA);
   TRef e3 = g.alloc(B, h8, w8, 64);  g.conv("encoder.3", skipA, e3, 3, 2, ACT_SILU);        g.name("encoder.3", e3);
-  const int c0 = 129, c0s = g.dt == DT_F32 ? 132 : 144;
+  // The reference's ablation variant `_YOLOSegPlusPlus.py` (:157, :264-268) has no bottleneck channel: decoder.0 is
+  // C3Ghost(128, 96) and its input is the skip alone.  Detected from the checkpoint (Cin of decoder.0.0.cv1); the
+  // `logits` argument is then ignored.
+  bool use_logits = true;
+  {
+    auto it = h->host.find("seg.decoder.0.0.cv1.conv.weight");
+    if (it != h->host.end() && it->second.shape.size() >= 2 && it->second.shape[1] == 128) use_logits = false;
+  }
+  const int c0 = use_logits ? 129 : 128, c0s = use_logits ? (g.dt == DT_F32 ? 132 : 144) : 128;
   TRef cat0 = g.alloc(B, h8, w8, c0, -1, c0s);  // dec0 input: [skipB 128 | logits 1 | zero pad]
-  cat0.zpad = g.dt == DT_BF16;
+  cat0.zpad = use_logits && g.dt == DT_BF16;
   TRef skipB = Builder::slice(cat0, 0, 128);    g.c3k2("encoder.4", e3, skipB, false, 0.25, true);   g.name("encoder.4", skipB);
   g.bn_eps = 1e-5;
   plan->split = (int)plan->steps.size();       // everything above is independent of the detector
-  {
+  if (use_logits) {
     TRef lg = Builder::slice(cat0, 128, 1);
     Plan* pl = plan; int dt = g.dt; int zp = c0s - 129;
     g.emit([=](RunCtx& c) {
@@ -1120,6 +1128,16 @@ int ysp_mask_dice(const float* d_logits, const float* d_target, int B, int HW, i
   if (!d_logits || !d_counts || B < 0 || HW < 0) return fail(YSP_EINVAL, "ysp_mask_dice: bad arguments");
   if (B == 0) return 0;
   launch_mask_dice(d_logits, d_target, B, HW, d_counts, d_mask, (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int ysp_conf_gate(const float* d_det_boxes, const int32_t* d_det_count, int B, int max_det, int row, float conf_gate,
+                  int32_t* d_counts, uint8_t* d_mask, int HW, uint8_t* d_gated, void* stream) {
+  if (!d_det_boxes || !d_det_count || !d_counts || B < 0 || max_det <= 0 || row < 5 || HW < 0)
+    return fail(YSP_EINVAL, "ysp_conf_gate: bad arguments");
+  if (B == 0) return 0;
+  launch_conf_gate(d_det_boxes, d_det_count, B, max_det, row, conf_gate, d_counts, d_mask, HW, d_gated, (cudaStream_t)stream);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -873,6 +873,26 @@ __global__ void __launch_bounds__(256) mask_dice_kernel(const float* __restrict_
     if (s) atomicAdd(&counts[b * 3 + threadIdx.x], s);
   }
 }
+// The detection-confidence gate sketched (commented out) at evaluate_model.py:149-155: a slice whose best detection is
+// missing or not above `thres` gets an all-zero predicted mask.  Applied after NMS + mask/Dice: zeroes |P&T| and |P| of
+// the gated slices (|T| stays) and, if given, their binary mask.  det rows are [x1,y1,x2,y2,conf,cls], best first.
+__global__ void __launch_bounds__(256) conf_gate_kernel(const float* __restrict__ det_boxes, const int32_t* __restrict__ det_count,
+                                                        int max_det, int row, float thres, int32_t* counts, uint8_t* mask,
+                                                        int HW, uint8_t* gated) {
+  const int b = blockIdx.y;
+  const bool keep = det_count[b] > 0 && det_boxes[(size_t)b * max_det * row + 4] > thres;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (gated) gated[b] = keep ? 0 : 1;
+    if (!keep) { counts[b * 3] = 0; counts[b * 3 + 1] = 0; }
+  }
+  if (keep || !mask) return;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < HW; i += gridDim.x * 256) mask[(size_t)b * HW + i] = 0;
+}
+void launch_conf_gate(const float* det_boxes, const int32_t* det_count, int B, int max_det, int row, float thres, int32_t* counts,
+                      uint8_t* mask, int HW, uint8_t* gated, cudaStream_t s) {
+  conf_gate_kernel<<<dim3(mask ? 8 : 1, B), 256, 0, s>>>(det_boxes, det_count, max_det, row, thres, counts, mask, HW, gated);
+}
+
 void launch_mask_dice(const float* logits, const float* target, int B, int HW, int32_t* counts, uint8_t* mask,
                       cudaStream_t s) {
   cudaMemsetAsync(counts, 0, sizeof(int32_t) * 3 * (size_t)B, s);

@@ -39,9 +39,22 @@ class Predictor:
 
     @torch.no_grad()
     def predict(self, img: torch.Tensor, target: Optional[torch.Tensor] = None, conf_thres: float = 0.25,
-                iou_thres: float = 0.45, max_det: int = 300):
-        """Returns (mask_logits [B,1,H,W], dets list[[n_i,6]], keep_idx list[int64 [n_i]], counts int32 [B,3])."""
-        o = self.predict_raw(img, target, conf_thres, iou_thres, max_det)
+                iou_thres: float = 0.45, max_det: int = 300, conf_gate: Optional[float] = None):
+        """Returns (mask_logits [B,1,H,W], dets list[[n_i,6]], keep_idx list[int64 [n_i]], counts int32 [B,3]).
+        `conf_gate` (off by default, like the commented-out block at evaluate_model.py:149-155): slices without a detection
+        above it count as an empty predicted mask; the gated flags are left in `self.gated` (uint8 [B])."""
+        o = self.predict_raw(img, target, conf_thres, iou_thres, max_det, want_mask=conf_gate is not None)
+        if conf_gate is not None:
+            from ._lib import check, lib
+            B = o["det_count"].shape[0]
+            self.gated = torch.empty(B, dtype=torch.uint8, device=o["counts"].device)
+            mask = o.get("mask")
+            with torch.cuda.device(o["counts"].device):
+                check(lib().ysp_conf_gate(o["det_boxes"].data_ptr(), o["det_count"].data_ptr(), B, o["det_boxes"].shape[1],
+                                          o["det_boxes"].shape[2], float(conf_gate), o["counts"].data_ptr(),
+                                          mask.data_ptr() if mask is not None else None,
+                                          o["mask_logits"].shape[-1] * o["mask_logits"].shape[-2], self.gated.data_ptr(),
+                                          torch.cuda.current_stream(o["counts"].device).cuda_stream))
         n = o["det_count"].tolist()
         dets = [o["det_boxes"][b, :k] for b, k in enumerate(n)]
         keep = [o["det_idx"][b, :k] for b, k in enumerate(n)]
