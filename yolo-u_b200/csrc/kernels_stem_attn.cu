@@ -13,6 +13,15 @@ static inline int cdiv2(long long a, long long b) { return (int)((a + b - 1) / b
 // NHWC activations.  Reads beyond H/W are zero: conv padding and the bottom/right zero-pad of decision D1.
 // One thread = 2 horizontally adjacent output pixels x 16 output channels (weights broadcast from shared memory).
 // =====================================================================================================================
+// byte / 255.f, correctly rounded (= ToTensor's true division) in three FP ops instead of an IEEE divide:
+// q0 = x*r, q = fma(fma(-q0, 255, x), r, q0) with r = fl(1/255); equal to x / 255.f for all 256 byte values (checked
+// exhaustively on the host and, end to end, by the u8-vs-fp32 input equality test).
+__device__ __forceinline__ float div255(unsigned char b) {
+  const float x = (float)b, r = 1.0f / 255.0f;
+  const float q0 = x * r;
+  return fmaf(fmaf(-q0, 255.0f, x), r, q0);
+}
+
 template <typename T, bool U8>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const void* __restrict__ in, T* __restrict__ out,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
@@ -46,7 +55,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const void* __restrict__
       if (ix >= 0 && ix < W) {
         if (U8) {
           uchar4 v = reinterpret_cast<const uchar4*>(in)[((size_t)n * H + iy) * W + ix];
-          x[c5][0] = v.x / 255.f; x[c5][1] = v.y / 255.f; x[c5][2] = v.z / 255.f; x[c5][3] = v.w / 255.f;
+          x[c5][0] = div255(v.x); x[c5][1] = div255(v.y); x[c5][2] = div255(v.z); x[c5][3] = div255(v.w);
         } else {
           const float* p = reinterpret_cast<const float*>(in) + (size_t)n * 4 * HW + (size_t)iy * W + ix;
           x[c5][0] = p[0]; x[c5][1] = p[HW]; x[c5][2] = p[2 * HW]; x[c5][3] = p[3 * HW];
