@@ -22,7 +22,7 @@ static inline int cdivl(long long a, long long b) { return (int)((a + b - 1) / b
 
 template <int K, int MODE>
 static void dw_tiled_launch(const float* X, int ldx, const float* W, float* Y, int ldy, const float* D, int ldd, float* dW,
-                            double* sums, int N, int H, int Wd, int C, int beta, cudaStream_t s);
+                            double* sums, int N, int H, int Wd, int C, int beta, cudaStream_t s, InTf tf = InTf());
 
 // =====================================================================================================================
 // C[m][j] = beta*C[m][j] + bias[j] + sum_i A[m][i] * Wop(i,j)      Wop(i,j) = trans ? W[i*ldw + j] : W[j*ldw + i]
@@ -32,12 +32,21 @@ static void dw_tiled_launch(const float* X, int ldx, const float* W, float* Y, i
 template <int BN>
 __global__ void __launch_bounds__(256, 4) pw_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
                                                       int ldw, int trans, const float* __restrict__ bias, float* C,
-                                                      int ldc, long long M, int I, int J, int beta, double* sums) {
+                                                      int ldc, long long M, int I, int J, int beta, double* sums, InTf tf) {
   constexpr int BK = 16, TX = BN / 4, TY = 256 / TX, BM = TY * 4;
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   __shared__ double sRed[2][BN];
+  __shared__ float sSc[144], sSh[144];                 // input transform x = act(z*sc + sh), I <= 144
   const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+  const bool tfon = tf.gamma != nullptr;
+  if (tfon) {
+    for (int i = tid; i < I; i += 256) {
+      const float sc = tf.gamma[i] * tf.invstd[i];
+      sSc[i] = sc; sSh[i] = tf.beta[i] - tf.mean[i] * sc;
+    }
+    __syncthreads();
+  }
   const int j0 = blockIdx.y * BN;
   const bool vecA = ((lda | I) & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
   const bool vecC = ((ldc | J) & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
@@ -52,14 +61,27 @@ __global__ void __launch_bounds__(256, 4) pw_gemm_kernel(const float* __restrict
           int r = e / (BK / 4), i = (e % (BK / 4)) * 4;
           long long m = m0 + r;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < M && i0 + i < I) v = *reinterpret_cast<const float4*>(A + m * lda + i0 + i);   // I % 4 == 0
+          if (m < M && i0 + i < I) {                                                               // I % 4 == 0
+            v = *reinterpret_cast<const float4*>(A + m * lda + i0 + i);
+            if (tfon) {
+              const int ig = i0 + i;
+              v.x = fmaf(v.x, sSc[ig], sSh[ig]); v.y = fmaf(v.y, sSc[ig + 1], sSh[ig + 1]);
+              v.z = fmaf(v.z, sSc[ig + 2], sSh[ig + 2]); v.w = fmaf(v.w, sSc[ig + 3], sSh[ig + 3]);
+              if (tf.act) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w)); }
+            }
+          }
           As[i][r] = v.x; As[i + 1][r] = v.y; As[i + 2][r] = v.z; As[i + 3][r] = v.w;
         }
       } else {
         for (int e = tid; e < BM * BK; e += 256) {
           int r = e / BK, i = e % BK;
           long long m = m0 + r;
-          As[i][r] = (m < M && i0 + i < I) ? A[m * lda + i0 + i] : 0.f;
+          float v = 0.f;
+          if (m < M && i0 + i < I) {
+            v = A[m * lda + i0 + i];
+            if (tfon) { v = fmaf(v, sSc[i0 + i], sSh[i0 + i]); if (tf.act) v = v / (1.f + expf(-v)); }
+          }
+          As[i][r] = v;
         }
       }
       for (int e = tid; e < BK * BN; e += 256) {
@@ -134,19 +156,19 @@ static int resident_ctas(Kern kern, int threads, size_t smem) {
 
 template <int BN>
 static void pw_gemm_launch(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc,
-                           long long M, int I, int J, int beta, cudaStream_t s, double* sums) {
+                           long long M, int I, int J, int beta, cudaStream_t s, double* sums, InTf tf) {
   constexpr int BM = (256 / (BN / 4)) * 4;
   static const int occ = resident_ctas(pw_gemm_kernel<BN>, 256, 0);
   const int jt = cdivl(J, BN);
   const int cap = std::max(1, 148 * occ / jt);
-  pw_gemm_kernel<BN><<<dim3(std::min(cdivl(M, BM), cap), jt), 256, 0, s>>>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, sums);
+  pw_gemm_kernel<BN><<<dim3(std::min(cdivl(M, BM), cap), jt), 256, 0, s>>>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, sums, tf);
 }
 
 void launch_pw_gemm(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc,
-                    long long M, int I, int J, int beta, cudaStream_t s, double* sums) {
-  if (J <= 16) pw_gemm_launch<16>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums);
-  else if (J <= 32) pw_gemm_launch<32>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums);
-  else pw_gemm_launch<64>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums);
+                    long long M, int I, int J, int beta, cudaStream_t s, double* sums, InTf tf) {
+  if (J <= 16) pw_gemm_launch<16>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums, tf);
+  else if (J <= 32) pw_gemm_launch<32>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums, tf);
+  else pw_gemm_launch<64>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums, tf);
 }
 
 // =====================================================================================================================
@@ -157,8 +179,10 @@ void launch_pw_gemm(const float* A, int lda, const float* W, int ldw, int trans,
 template <int TJ, int TI>
 __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__ D, int ldd, const float* __restrict__ X,
                                                        int ldx, float* dW, int ldw, long long M, int I, int J,
-                                                       int rows_per_cta) {
+                                                       int rows_per_cta, InTf tf) {
   constexpr int TPG = (TJ / 4) * (TI / 4), G = 256 / TPG;
+  __shared__ float sSc[TI], sSh[TI];
+  const bool tfon = tf.gamma != nullptr;
   constexpr int RS = (TJ + TI <= 48) ? 128 : (TJ + TI <= 96 ? 64 : 32);                       // rows staged per pass
   __shared__ __align__(16) float sD[RS][TJ + 4];
   __shared__ __align__(16) float sX[RS][TI + 4];
@@ -171,10 +195,16 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
   const bool vecD = (ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0;
   const bool vecX = (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
   for (int e = tid; e < TJ * TI; e += 256) sAcc[e] = 0.f;
+  if (tfon)
+    for (int e = tid; e < TI; e += 256) {
+      const int i = i0 + e;
+      const float sc = i < I ? tf.gamma[i] * tf.invstd[i] : 0.f;
+      sSc[e] = sc; sSh[e] = i < I ? tf.beta[i] - tf.mean[i] * sc : 0.f;
+    }
   float acc[4][4] = {};
   // one staged tile: rows [rb, rb+RS) x columns [c0, c0+TC) of a row-major matrix, zero-filled outside
   auto stage = [&](const float* __restrict__ src, int ld, int c0, int cols, bool vec, float* dst, int dld, int TC,
-                   long long rb) {
+                   long long rb, bool xf) {
     const int q4 = TC / 4;
     for (int e = tid; e < RS * q4; e += 256) {
       int r = e / q4, c = (e % q4) * 4;
@@ -188,14 +218,19 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
           if (c0 + c + 2 < cols) v.z = p[2];
           if (c0 + c + 3 < cols) v.w = p[3];
         }
+        if (xf) {       // columns beyond `cols` have sc = sh = 0 and stay 0 (SiLU(0) = 0)
+          v.x = fmaf(v.x, sSc[c], sSh[c]); v.y = fmaf(v.y, sSc[c + 1], sSh[c + 1]);
+          v.z = fmaf(v.z, sSc[c + 2], sSh[c + 2]); v.w = fmaf(v.w, sSc[c + 3], sSh[c + 3]);
+          if (tf.act) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w)); }
+        }
       }
       *reinterpret_cast<float4*>(dst + r * dld + c) = v;
     }
   };
   for (long long rb = r0; rb < r1; rb += RS) {
     __syncthreads();
-    stage(D, ldd, j0, J, vecD, &sD[0][0], TJ + 4, TJ, rb);
-    stage(X, ldx, i0, I, vecX, &sX[0][0], TI + 4, TI, rb);
+    stage(D, ldd, j0, J, vecD, &sD[0][0], TJ + 4, TJ, rb, false);
+    stage(X, ldx, i0, I, vecX, &sX[0][0], TI + 4, TI, rb, tfon);
     __syncthreads();
 #pragma unroll 4
     for (int r = g; r < RS; r += G) {
@@ -222,20 +257,20 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
 
 template <int TJ, int TI>
 static void pw_wgrad_launch(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I,
-                            int J, cudaStream_t s) {
+                            int J, cudaStream_t s, InTf tf) {
   int tiles = cdivl(J, TJ) * cdivl(I, TI);
   long long want = (148 * 4 + tiles - 1) / tiles;                       // ~4 CTAs per SM in total
   long long rows = (M + want - 1) / want;
   rows = ((rows + 127) / 128) * 128;
   if (rows < 256) rows = 256;
   pw_wgrad_kernel<TJ, TI><<<dim3(cdivl(M, rows), cdivl(J, TJ), cdivl(I, TI)), 256, 0, s>>>(D, ldd, X, ldx, dW, ldw, M, I,
-                                                                                          J, (int)rows);
+                                                                                          J, (int)rows, tf);
 }
 
 void launch_pw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I, int J,
-                     cudaStream_t s) {
+                     cudaStream_t s, InTf tf) {
   const int cj = J <= 16 ? 16 : J <= 32 ? 32 : 64, ci = I <= 16 ? 16 : I <= 32 ? 32 : 64;
-#define YSP_WG(a, b) if (cj == a && ci == b) return pw_wgrad_launch<a, b>(D, ldd, X, ldx, dW, ldw, M, I, J, s)
+#define YSP_WG(a, b) if (cj == a && ci == b) return pw_wgrad_launch<a, b>(D, ldd, X, ldx, dW, ldw, M, I, J, s, tf)
   YSP_WG(16, 16); YSP_WG(16, 32); YSP_WG(16, 64); YSP_WG(32, 16); YSP_WG(32, 32); YSP_WG(32, 64);
   YSP_WG(64, 16); YSP_WG(64, 32); YSP_WG(64, 64);
 #undef YSP_WG
@@ -348,11 +383,11 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const float* __restrict__
 }
 
 void launch_dw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int N, int H, int Wd, int C, int k,
-                     cudaStream_t s) {
+                     cudaStream_t s, InTf tf) {
   long long total = (long long)N * H * Wd;
-  if (H >= 32 && Wd >= 32 && (k == 3 || k == 5)) {
-    if (k == 3) dw_tiled_launch<3, 2>(X, ldx, nullptr, nullptr, 0, D, ldd, dW, nullptr, N, H, Wd, C, 0, s);
-    else dw_tiled_launch<5, 2>(X, ldx, nullptr, nullptr, 0, D, ldd, dW, nullptr, N, H, Wd, C, 0, s);
+  if (dw_tiled_shape(H, Wd, k)) {
+    if (k == 3) dw_tiled_launch<3, 2>(X, ldx, nullptr, nullptr, 0, D, ldd, dW, nullptr, N, H, Wd, C, 0, s, tf);
+    else dw_tiled_launch<5, 2>(X, ldx, nullptr, nullptr, 0, D, ldd, dW, nullptr, N, H, Wd, C, 0, s, tf);
     return;
   }
   long long per = std::max<long long>(cdivl(total, 148 * 4), 256);
@@ -374,12 +409,14 @@ void launch_dw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW
 template <int K, int MODE>
 __global__ void __launch_bounds__(256) dw_tiled_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
                                                        float* Y, int ldy, const float* __restrict__ D, int ldd, float* dW,
-                                                       double* sums, int N, int H, int Wd, int C, int beta) {
+                                                       double* sums, int N, int H, int Wd, int C, int beta, InTf tf) {
   constexpr int TY = 16, TX = 16, IH = TY + K - 1, IW = TX + K - 1, PS = 20, KK = K * K, PAD = K / 2;
   extern __shared__ __align__(16) float dsm[];
   float* sIn = dsm;                      // [IH*IW][PS]
   float* sW = sIn + IH * IW * PS;        // MODE 0/1: [KK][16] taps;  MODE 2: [16][KK] block accumulators
   __shared__ double sRed[2][16];
+  __shared__ __align__(16) float sSc[16], sSh[16];     // input transform of this CTA's 16 channels
+  const bool tfon = MODE != 1 && tf.gamma != nullptr;
   const int tid = threadIdx.x;
   const int tiles_x = (Wd + TX - 1) / TX, tiles_y = (H + TY - 1) / TY;
   const int ntiles = N * tiles_y * tiles_x;
@@ -395,6 +432,12 @@ __global__ void __launch_bounds__(256) dw_tiled_kernel(const float* __restrict__
     for (int e = tid; e < 16 * KK; e += 256) sW[e] = 0.f;
   }
   if (tid < 32) sRed[tid >> 4][tid & 15] = 0.0;
+  if (tfon && tid < 16) {
+    const int ch = cg + tid;
+    const float sc = ch < C ? tf.gamma[ch] * tf.invstd[ch] : 0.f;
+    sSc[tid] = sc; sSh[tid] = ch < C ? tf.beta[ch] - tf.mean[ch] * sc : 0.f;
+  }
+  if (tfon) __syncthreads();
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   float wacc[MODE == 2 ? KK : 1][4];
 #pragma unroll
@@ -410,8 +453,14 @@ __global__ void __launch_bounds__(256) dw_tiled_kernel(const float* __restrict__
       const int qq = i & 3, pp = i >> 2;
       const int iy = ty0 + pp / IW - PAD, ix = tx0 + pp % IW - PAD;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (qq < nq && iy >= 0 && iy < H && ix >= 0 && ix < Wd)
+      if (qq < nq && iy >= 0 && iy < H && ix >= 0 && ix < Wd) {
         v = *reinterpret_cast<const float4*>(X + ((size_t)(n * H + iy) * Wd + ix) * ldx + cg + qq * 4);
+        if (tfon) {        // the conv zero-pads the TRANSFORMED tensor: only in-image pixels are mapped
+          const float4 sc = *reinterpret_cast<const float4*>(sSc + qq * 4), sh = *reinterpret_cast<const float4*>(sSh + qq * 4);
+          v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+          if (tf.act) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w)); }
+        }
+      }
       *reinterpret_cast<float4*>(sIn + pp * PS + qq * 4) = v;
     }
     __syncthreads();
@@ -517,21 +566,23 @@ __global__ void __launch_bounds__(256) dw_tiled_kernel(const float* __restrict__
 
 template <int K, int MODE>
 static void dw_tiled_launch(const float* X, int ldx, const float* W, float* Y, int ldy, const float* D, int ldd, float* dW,
-                            double* sums, int N, int H, int Wd, int C, int beta, cudaStream_t s) {
+                            double* sums, int N, int H, int Wd, int C, int beta, cudaStream_t s, InTf tf) {
   constexpr size_t smem = sizeof(float) * ((16 + K - 1) * (16 + K - 1) * 20 + K * K * 16);
   const int ngrp = (C + 15) / 16;
   const int ntiles = N * ((H + 15) / 16) * ((Wd + 15) / 16);
   static const int occ = resident_ctas(dw_tiled_kernel<K, MODE>, 256, smem);
   int gx = std::min(ntiles, std::max(1, 148 * occ / ngrp));
-  dw_tiled_kernel<K, MODE><<<dim3(gx, ngrp), 256, smem, s>>>(X, ldx, W, Y, ldy, D, ldd, dW, sums, N, H, Wd, C, beta);
+  dw_tiled_kernel<K, MODE><<<dim3(gx, ngrp), 256, smem, s>>>(X, ldx, W, Y, ldy, D, ldd, dW, sums, N, H, Wd, C, beta, tf);
 }
 
 // forward with fused BatchNorm statistics (sums = [2][C] doubles, pre-zeroed) -- returns false if the shape is not tiled
+bool dw_tiled_shape(int H, int Wd, int k) { return H >= 32 && Wd >= 32 && (k == 3 || k == 5); }
+
 bool launch_dw_fwd_stats(const float* X, int ldx, const float* W, float* Y, int ldy, double* sums, int N, int H, int Wd,
-                         int C, int k, cudaStream_t s) {
-  if (H < 32 || Wd < 32 || (k != 3 && k != 5)) return false;
-  if (k == 3) dw_tiled_launch<3, 0>(X, ldx, W, Y, ldy, nullptr, 0, nullptr, sums, N, H, Wd, C, 0, s);
-  else dw_tiled_launch<5, 0>(X, ldx, W, Y, ldy, nullptr, 0, nullptr, sums, N, H, Wd, C, 0, s);
+                         int C, int k, cudaStream_t s, InTf tf) {
+  if (!dw_tiled_shape(H, Wd, k)) return false;
+  if (k == 3) dw_tiled_launch<3, 0>(X, ldx, W, Y, ldy, nullptr, 0, nullptr, sums, N, H, Wd, C, 0, s, tf);
+  else dw_tiled_launch<5, 0>(X, ldx, W, Y, ldy, nullptr, 0, nullptr, sums, N, H, Wd, C, 0, s, tf);
   return true;
 }
 

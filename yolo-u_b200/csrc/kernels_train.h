@@ -6,18 +6,22 @@
 namespace ysp {
 
 struct BnRef { const float *gamma, *beta, *mean, *invstd; };
+// Optional transform applied to a kernel's INPUT as it is loaded: x = act(gamma*(z - mean)*invstd + beta).  It lets a
+// consumer read its producer's raw conv output z, so the producer's normalised tensor is never written (gamma == NULL: off).
+struct InTf { const float *gamma = nullptr, *beta = nullptr, *mean = nullptr, *invstd = nullptr; int act = 0; };
 
 // `sums` (optional, [2][J] doubles, pre-zeroed): per-column sum and sum of squares of the product (BN statistics)
 void launch_pw_gemm(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc,
-                    long long M, int I, int J, int beta, cudaStream_t s, double* sums = nullptr);
+                    long long M, int I, int J, int beta, cudaStream_t s, double* sums = nullptr, InTf tf = InTf());
 void launch_pw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I, int J,
-                     cudaStream_t s);
+                     cudaStream_t s, InTf tf = InTf());
 void launch_dw_conv(const float* X, int ldx, const float* W, float* Y, int ldy, int N, int H, int Wd, int C, int k,
                     int flip, int beta, cudaStream_t s);
 bool launch_dw_fwd_stats(const float* X, int ldx, const float* W, float* Y, int ldy, double* sums, int N, int H, int Wd,
-                         int C, int k, cudaStream_t s);
+                         int C, int k, cudaStream_t s, InTf tf = InTf());
 void launch_dw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int N, int H, int Wd, int C, int k,
-                     cudaStream_t s);
+                     cudaStream_t s, InTf tf = InTf());
+bool dw_tiled_shape(int H, int Wd, int k);   // true when the tiled depthwise family (the one that takes an InTf) handles it
 void launch_col_reduce(int mode, const float* A, int lda, const float* B, int ldb, const BnRef& bn, int act, double* sums,
                        int C, long long segs, long long rows_per_seg, cudaStream_t s);
 void launch_bn_finalize(const double* sums, int C, long long M, float eps, float momentum, float* mean, float* invstd,

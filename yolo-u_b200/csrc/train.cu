@@ -36,6 +36,7 @@ struct ConvBN {               // ultralytics Conv / DWConv: conv(bias=False) -> 
   // saved by the forward for the backward
   const float* x = nullptr; int ldx = 0; float* z = nullptr; float *mean = nullptr, *invstd = nullptr;
   int N = 0, H = 0, W = 0;
+  const ConvBN* src = nullptr;   // non-null: x is src->z and src's BN + activation is applied as x is loaded (InTf)
 };
 struct Lin { int Cin = 0, Cout = 0; int64_t w = 0, b = 0; };   // nn.Conv2d(k=1, bias=True)
 
@@ -153,10 +154,18 @@ Dlc make_dlc(ysp_trainer* t, const std::string& pre, int Cin, int C) {
 // ---- unit forward / backward -------------------------------------------------------------------------------------------
 constexpr float kBnEps = 1e-5f;    // decoder BNs keep PyTorch's default eps
 
+InTf tf_of(const Ctx& c, const ConvBN* src) {
+  InTf t;
+  if (src) { t.gamma = c.P + src->g; t.beta = c.P + src->b; t.mean = src->mean; t.invstd = src->invstd; t.act = src->act; }
+  return t;
+}
+
+// y == nullptr: "lazy" unit -- only z and the batch statistics are produced; the consumer passes this unit as `src` and
+// applies BN + activation while loading (saves writing and re-reading the normalised tensor).
 void convbn_fwd(Ctx& c, ConvBN& u, const float* x, int ldx, int N, int H, int W, float* y, int ldy, const float* res,
-                int ldr) {
+                int ldr, const ConvBN* src = nullptr) {
   const long long M = (long long)N * H * W;
-  u.x = x; u.ldx = ldx; u.N = N; u.H = H; u.W = W;
+  u.x = src ? src->z : x; u.ldx = src ? src->Cout : ldx; u.N = N; u.H = H; u.W = W; u.src = src;
   u.z = c.alloc((size_t)M * u.Cout);
   u.mean = c.alloc(u.Cout);
   u.invstd = c.alloc(u.Cout);
@@ -164,20 +173,25 @@ void convbn_fwd(Ctx& c, ConvBN& u, const float* x, int ldx, int N, int H, int W,
   c.need_dz((size_t)M * u.Cout);
   if (c.dry) return;
   BnRef bn = {c.P + u.g, c.P + u.b, u.mean, u.invstd};
+  const InTf tf = tf_of(c, src);
   bool stats_done = false;
   if (u.dw) {
-    stats_done = launch_dw_fwd_stats(x, ldx, c.P + u.w, u.z, u.Cout, sums, N, H, W, u.Cout, u.k, c.s);   // conv + BN statistics
-    if (!stats_done) launch_dw_conv(x, ldx, c.P + u.w, u.z, u.Cout, N, H, W, u.Cout, u.k, 0, 0, c.s);
+    stats_done = launch_dw_fwd_stats(u.x, u.ldx, c.P + u.w, u.z, u.Cout, sums, N, H, W, u.Cout, u.k, c.s, tf);   // conv + BN statistics
+    if (!stats_done) launch_dw_conv(u.x, u.ldx, c.P + u.w, u.z, u.Cout, N, H, W, u.Cout, u.k, 0, 0, c.s);
   } else {
-    launch_pw_gemm(x, ldx, c.P + u.w, u.Cin, 0, nullptr, u.z, u.Cout, M, u.Cin, u.Cout, 0, c.s, sums);     // conv + BN statistics
+    launch_pw_gemm(u.x, u.ldx, c.P + u.w, u.Cin, 0, nullptr, u.z, u.Cout, M, u.Cin, u.Cout, 0, c.s, sums, tf);     // conv + BN statistics
     stats_done = true;
   }
   if (!stats_done) { launch_col_reduce(0, u.z, u.Cout, nullptr, 0, bn, 0, sums, u.Cout, 1, M, c.s); c.launches += 1; }
   launch_bn_finalize(sums, u.Cout, M, kBnEps, c.momentum, u.mean, u.invstd, c.S ? c.S + u.rm : nullptr,
                      c.S ? c.S + u.rv : nullptr, c.s);
-  launch_bn_apply(u.z, u.Cout, bn, u.act, res, ldr, y, ldy, u.Cout, M, c.s);
-  c.launches += 3;
-  c.acct((double)M * ((u.dw ? u.Cout : u.Cin) + u.Cout * (4 + (res ? 1 : 0))));   // conv r/w, stats r, apply r/w (+res)
+  c.launches += 2;
+  c.acct((double)M * ((u.dw ? u.Cout : u.Cin) + u.Cout));                          // conv read / write
+  if (y) {
+    launch_bn_apply(u.z, u.Cout, bn, u.act, res, ldr, y, ldy, u.Cout, M, c.s);
+    c.launches += 1;
+    c.acct((double)M * u.Cout * (2 + (res ? 1 : 0)));
+  }
 }
 
 // dy -> parameter gradients (+ input gradient into dx[:, :dx_ch], accumulated when beta)
@@ -189,10 +203,10 @@ void convbn_bwd(Ctx& c, ConvBN& u, const float* dy, int ldd, float* dx, int lddx
   launch_col_reduce(1, dy, ldd, u.z, u.Cout, bn, u.act, sums, u.Cout, 1, M, c.s);
   launch_bn_bwd_apply(dy, ldd, u.z, u.Cout, bn, u.act, sums, c.dz, u.Cout, c.G + u.g, c.G + u.b, u.Cout, M, c.s);
   if (u.dw) {
-    launch_dw_wgrad(c.dz, u.Cout, u.x, u.ldx, c.G + u.w, u.N, u.H, u.W, u.Cout, u.k, c.s);
+    launch_dw_wgrad(c.dz, u.Cout, u.x, u.ldx, c.G + u.w, u.N, u.H, u.W, u.Cout, u.k, c.s, tf_of(c, u.src));
     if (dx) launch_dw_conv(c.dz, u.Cout, c.P + u.w, dx, lddx, u.N, u.H, u.W, u.Cout, u.k, 1, beta, c.s);
   } else {
-    launch_pw_wgrad(c.dz, u.Cout, u.x, u.ldx, c.G + u.w, u.Cin, M, u.Cin, u.Cout, c.s);
+    launch_pw_wgrad(c.dz, u.Cout, u.x, u.ldx, c.G + u.w, u.Cin, M, u.Cin, u.Cout, c.s, tf_of(c, u.src));
     if (dx) launch_pw_gemm(c.dz, u.Cout, c.P + u.w, u.Cin, 1, nullptr, dx, lddx, M, u.Cout, dx_ch, beta, c.s);
   }
   c.launches += dx ? 4 : 3;
@@ -263,19 +277,28 @@ void dlc_fwd(Ctx& c, Dlc& d, const float* xl, int ldx, int N, int h, int w, floa
   const long long M = (long long)N * H * W;
   d.u = c.alloc((size_t)M * d.Cin);
   float* r = c.alloc((size_t)M * d.C);
-  float* pb = c.alloc((size_t)M * d.C);
-  float* qb = c.alloc((size_t)M * d.C);
-  float* p2b = c.alloc((size_t)M * d.C);
   if (!c.dry) {
     launch_up2(xl, ldx, d.u, d.Cin, N, h, w, d.Cin, c.s);
     launch_pw_gemm(d.u, d.Cin, c.P + d.r.w, d.Cin, 0, c.P + d.r.b, r, d.C, M, d.Cin, d.C, 0, c.s);   // residual_conv
     c.launches += 2;
     c.acct((double)M * (d.Cin * 0.25 + d.Cin + d.Cin + d.C));
   }
-  convbn_fwd(c, d.p, d.u, d.Cin, N, H, W, pb, d.C, nullptr, 0);
-  convbn_fwd(c, d.q, pb, d.C, N, H, W, qb, d.C, nullptr, 0);
-  convbn_fwd(c, d.p2, qb, d.C, N, H, W, p2b, d.C, nullptr, 0);
-  convbn_fwd(c, d.q2, p2b, d.C, N, H, W, out, ldo, r, d.C);                                          // out = conv(x) + residual
+  // the three inner normalised tensors are never written: each consumer applies its producer's BN (+SiLU) on load
+  const bool lazy = dw_tiled_shape(H, W, 3);
+  if (lazy) {
+    convbn_fwd(c, d.p, d.u, d.Cin, N, H, W, nullptr, 0, nullptr, 0);
+    convbn_fwd(c, d.q, nullptr, 0, N, H, W, nullptr, 0, nullptr, 0, &d.p);
+    convbn_fwd(c, d.p2, nullptr, 0, N, H, W, nullptr, 0, nullptr, 0, &d.q);
+    convbn_fwd(c, d.q2, nullptr, 0, N, H, W, out, ldo, r, d.C, &d.p2);                               // out = conv(x) + residual
+  } else {
+    float* pb = c.alloc((size_t)M * d.C);
+    float* qb = c.alloc((size_t)M * d.C);
+    float* p2b = c.alloc((size_t)M * d.C);
+    convbn_fwd(c, d.p, d.u, d.Cin, N, H, W, pb, d.C, nullptr, 0);
+    convbn_fwd(c, d.q, pb, d.C, N, H, W, qb, d.C, nullptr, 0);
+    convbn_fwd(c, d.p2, qb, d.C, N, H, W, p2b, d.C, nullptr, 0);
+    convbn_fwd(c, d.q2, p2b, d.C, N, H, W, out, ldo, r, d.C);                                        // out = conv(x) + residual
+  }
 }
 
 void dlc_bwd(Ctx& c, Dlc& d, const float* dout, int ldd, float* dxl, int lddx) {
