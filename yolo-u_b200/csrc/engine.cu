@@ -503,10 +503,35 @@ struct Builder {
     TRef cat = slice(buf, 0, 2 * c_), a = slice(buf, 2 * c_, c_);
     conv(p + ".cv2+" + p + ".cv1", x, slice(buf, c_, 2 * c_), 1, 1, ACT_SILU);
     // GhostBottleneck(c_, c_), stride 1: GhostConv(c_, c_/2) -> Identity -> GhostConv(c_/2, c_, act=False); + x
-    TRef g1 = alloc(x.N, x.H, x.W, c_ / 2);
-    ghostconv(p + ".m.0.conv.0", a, g1, ACT_SILU, nullptr);
     TRef dst = slice(buf, 0, c_);
-    ghostconv(p + ".m.0.conv.2", g1, dst, ACT_NONE, &a);
+    if (dt == DT_BF16 && getenv("YSP_NO_GHOSTFUSE") == nullptr && ghost_fused_supported(c_, a.cs, dst.cs)) {
+      DevConv *k1 = nullptr, *d1 = nullptr, *k3 = nullptr, *d2 = nullptr;   // the four convs as ONE kernel (kernels_ghost.cu)
+      if ((rc = pack_conv(h, ns + "." + p + ".m.0.conv.0.cv1", bn_eps, &k1))) return;
+      if ((rc = pack_conv(h, ns + "." + p + ".m.0.conv.0.cv2", bn_eps, &d1))) return;
+      if ((rc = pack_conv(h, ns + "." + p + ".m.0.conv.2.cv1", bn_eps, &k3))) return;
+      if ((rc = pack_conv(h, ns + "." + p + ".m.0.conv.2.cv2", bn_eps, &d2))) return;
+      if (k1->dw || k3->dw || !d1->dw || !d2->dw || k1->Cin != c_ || k1->Cout != c_ / 4 || d1->Cout != c_ / 4 || d1->kh != 5 ||
+          k3->Cin != c_ / 2 || k3->Cout != c_ / 2 || d2->Cout != c_ / 2 || d2->kh != 5 || k1->kh != 1 || k3->kh != 1) {
+        rc = fail(YSP_EINVAL, "c3ghost %s: unexpected GhostBottleneck weight shapes", p.c_str());
+        return;
+      }
+      GhostP q = {};
+      q.w1 = k1->w; q.b1 = k1->bias; q.w1ld = k1->wld; q.dw1 = d1->w; q.bd1 = d1->bias;
+      q.w3 = k3->w; q.b3 = k3->bias; q.w3ld = k3->wld; q.dw2 = d2->w; q.bd2 = d2->bias;
+      q.N = x.N; q.H = x.H; q.W = x.W; q.a_cs = a.cs; q.out_cs = dst.cs;
+      Plan* pl = plan;
+      const double px = (double)x.N * x.H * x.W;
+      emit([=](RunCtx& c) {
+        GhostP r = q;
+        r.a = (const bf16*)pl->ptr(c, a); r.out = (bf16*)pl->ptr(c, dst);
+        launch_ghost_fused(r, c_, c.s);
+      }, {&a, &dst}, 1,
+      StepInfo{p + ".m.0.fused", "ghost_fused", 2.0 * tbytes(a), 2.0 * px * (c_ * c_ / 4.0 + 25.0 * c_ / 4 + c_ * c_ / 4.0 + 25.0 * c_ / 2), 1});
+    } else {
+      TRef g1 = alloc(x.N, x.H, x.W, c_ / 2);
+      ghostconv(p + ".m.0.conv.0", a, g1, ACT_SILU, nullptr);
+      ghostconv(p + ".m.0.conv.2", g1, dst, ACT_NONE, &a);
+    }
     conv(p + ".cv3", cat, out, 1, 1, ACT_SILU);
   }
   // bilinear x2 + DoubleLightConv [+ output head] fused (kernels_fused.cu): the two 1x1 convs that read the upsampled

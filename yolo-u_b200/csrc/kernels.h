@@ -102,3 +102,15 @@ void launch_dlc_tc_prepare(const DlcTcPrep& q, void* out, cudaStream_t s);
 bool dlc_tc_supported(int Cin, int C, bool head);
 void launch_dlc_tc(const DlcTcP& p, cudaStream_t s);
 }  // namespace ysp
+
+namespace ysp {
+// kernels_ghost.cu -- GhostBottleneck(c, c, s=1) of the decoder's C3Ghost blocks as one kernel (bf16 mode, c = 32 or 48)
+struct GhostP {
+  const bf16* a; bf16* out;                 // NHWC views [N,H,W,c] (pixel strides a_cs / out_cs)
+  const float *w1, *b1, *dw1, *bd1;         // conv.0.cv1 dense [c][ld] (c -> c/4, SiLU), conv.0.cv2 depthwise [25][c/4] (SiLU)
+  const float *w3, *b3, *dw2, *bd2;         // conv.2.cv1 dense [c/2][ld] (c/2 -> c/2), conv.2.cv2 depthwise [25][c/2] (linear)
+  int w1ld, w3ld, N, H, W, a_cs, out_cs;
+};
+bool ghost_fused_supported(int c, int a_cs, int out_cs);
+void launch_ghost_fused(const GhostP& p, int c, cudaStream_t s);
+}  // namespace ysp
