@@ -58,37 +58,50 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
   for (int i = tid; i < 25 * HC; i += 256) sD2[i] = p.dw2[i];
   for (int i = tid; i < G; i += 256) { sB[i] = p.b1[i]; sB[G + i] = p.bd1[i]; }
   for (int i = tid; i < HC; i += 256) { sB[2 * G + i] = p.b3[i]; sB[2 * G + HC + i] = p.bd2[i]; }
-  // ---- stage 0: a patch (24x24, zero outside the image) ----
+  // ---- stage 0: a patch (24x24, zero outside the image).  All of a thread's 16-byte loads are issued before the first
+  //      store, so the ~10 L2 round trips overlap instead of queueing behind each other ----
   {
     constexpr int V = CA / 8;                                           // 16-byte vectors per pixel
+    constexpr int NIT = (GRA * GRA * V + 255) / 256;
     const bf16* base = p.a + (size_t)n * p.H * p.W * p.a_cs;
-    for (int i = tid; i < GRA * GRA * V; i += 256) {
+    uint4 d[NIT];
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      const int i = tid + k * 256;
       const int v = i % V, pp = i / V;
       const int y = Y0 - 4 + pp / GRA, x = X0 - 4 + pp % GRA;
-      uint4 d = make_uint4(0u, 0u, 0u, 0u);
-      if (y >= 0 && y < p.H && x >= 0 && x < p.W) d = *reinterpret_cast<const uint4*>(base + ((size_t)y * p.W + x) * p.a_cs + v * 8);
-      uint32_t* o = sA + pp * PA + v * 4;
-      o[0] = d.x; o[1] = d.y; o[2] = d.z; o[3] = d.w;
+      d[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < GRA * GRA * V && y >= 0 && y < p.H && x >= 0 && x < p.W)
+        d[k] = *reinterpret_cast<const uint4*>(base + ((size_t)y * p.W + x) * p.a_cs + v * 8);
+    }
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      const int i = tid + k * 256;
+      if (i < GRA * GRA * V) {
+        uint32_t* o = sA + (i / V) * PA + (i % V) * 4;
+        o[0] = d[k].x; o[1] = d[k].y; o[2] = d[k].z; o[3] = d[k].w;
+      }
     }
   }
   __syncthreads();
-  // ---- stage A: g1 = SiLU(W1 a + b1) on the 24x24 region ----
+  // ---- stage A: g1 = SiLU(W1 a + b1) on the 24x24 region.  Strip width chosen so that all items fit ONE pass of the
+  //      256 threads (G=8: 6-pixel strips -> 192 items; G=12: 8-pixel strips -> 216 items) ----
   {
-    constexpr int Q = G / 4, SPR = GRA / 4;
+    constexpr int Q = G / 4, SW = G == 8 ? 6 : 8, SPR = GRA / SW;
     for (int i = tid; i < GRA * SPR * Q; i += 256) {
       const int q = i % Q, st = i / Q;
-      const int ry = st / SPR, rx = (st % SPR) * 4;
+      const int ry = st / SPR, rx = (st % SPR) * SW;
       const int pp0 = ry * GRA + rx;
-      float acc[4][4];
+      float acc[SW][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { acc[j][0] = sB[q * 4]; acc[j][1] = sB[q * 4 + 1]; acc[j][2] = sB[q * 4 + 2]; acc[j][3] = sB[q * 4 + 3]; }
+      for (int j = 0; j < SW; ++j) { acc[j][0] = sB[q * 4]; acc[j][1] = sB[q * 4 + 1]; acc[j][2] = sB[q * 4 + 2]; acc[j][3] = sB[q * 4 + 3]; }
       const uint32_t* ap = sA + pp0 * PA;
-#pragma unroll 4
+#pragma unroll 2
       for (int k2 = 0; k2 < CA / 2; ++k2) {
         const float4 w0 = *reinterpret_cast<const float4*>(sW1 + (2 * k2) * G + q * 4);
         const float4 w1 = *reinterpret_cast<const float4*>(sW1 + (2 * k2 + 1) * G + q * 4);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < SW; ++j) {
           const float2 av = bf2(ap[j * PA + k2]);
           acc[j][0] = fmaf(av.x, w0.x, acc[j][0]); acc[j][1] = fmaf(av.x, w0.y, acc[j][1]);
           acc[j][2] = fmaf(av.x, w0.z, acc[j][2]); acc[j][3] = fmaf(av.x, w0.w, acc[j][3]);
@@ -98,7 +111,7 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
       }
       const int y = Y0 - 4 + ry;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < SW; ++j) {
         const int x = X0 - 4 + rx + j;
         const bool in = y >= 0 && y < p.H && x >= 0 && x < p.W;
         uint32_t* o = sG + (pp0 + j) * PG + q * 2;
