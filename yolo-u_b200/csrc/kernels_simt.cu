@@ -226,15 +226,26 @@ __global__ void __launch_bounds__(TY * TX) conv_dw_tiled_kernel(DwP p) {
   for (int i = tid; i < K * K * 4; i += NT)
     *reinterpret_cast<float4*>(sW + (i >> 2) * 16 + (i & 3) * 4) =
         (i & 3) < nq ? *reinterpret_cast<const float4*>(p.w + (size_t)(i >> 2) * p.C + cg + (i & 3) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = tid; i < IH * IW * 4; i += NT) {
-    const int q = i & 3, pp = i >> 2;
-    const int iy = ty0 + pp / IW - K / 2, ix = tx0 + pp % IW - K / 2;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q < nq && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-      F4 f = load4<T>(in + ((size_t)(n * p.H + iy) * p.W + ix) * p.in_cs + cin + q * 4);
-      v = make_float4(f.v[0], f.v[1], f.v[2], f.v[3]);
+  {
+    // batches of 4 loads are issued before their shared-memory stores so the L2 round trips overlap
+    constexpr int TOT = IH * IW * 4, UB = 4;
+    for (int i0 = tid; i0 < TOT; i0 += NT * UB) {
+      F4 f[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int i = i0 + u * NT;
+        const int q = i & 3, pp = i >> 2;
+        const int iy = ty0 + pp / IW - K / 2, ix = tx0 + pp % IW - K / 2;
+        f[u].v[0] = f[u].v[1] = f[u].v[2] = f[u].v[3] = 0.f;
+        if (i < TOT && q < nq && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+          f[u] = load4<T>(in + ((size_t)(n * p.H + iy) * p.W + ix) * p.in_cs + cin + q * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int i = i0 + u * NT;
+        if (i < TOT) *reinterpret_cast<float4*>(sIn + (i >> 2) * PS + (i & 3) * 4) = make_float4(f[u].v[0], f[u].v[1], f[u].v[2], f[u].v[3]);
+      }
     }
-    *reinterpret_cast<float4*>(sIn + pp * PS + q * 4) = v;
   }
   __syncthreads();
   const int q = tid & 3, txi = (tid >> 2) % (TX / 4), ty = tid / TX;
@@ -309,19 +320,25 @@ __global__ void __launch_bounds__(256) conv_dw_row_kernel(DwP p) {
   const int cin = (cg / p.grp) * p.grp_stride + (cg % p.grp);
   for (int i = tid; i < K * K * 16; i += 256) sW[i] = ((i & 15) >> 2) < nq ? p.w[(size_t)(i >> 4) * p.C + cg + (i & 15)] : 0.f;
   {
+    // all of a thread's 8-byte loads are issued before its first shared-memory store: the L2 round trips overlap
+    constexpr int NIT = (IH * IW + 63) / 64;                            // 64 pixels (x 4 quads) per pass
     const int q = tid & 3;
-    int pp = tid >> 2, ry = pp / IW, rx = pp - ry * IW;              // 64 pixels per pass: (ry, rx) advance incrementally
+    const int pp0 = tid >> 2;
     const bf16* base = in + (size_t)n * p.H * p.W * p.in_cs + cin + q * 4;
-#pragma unroll 2
-    for (; pp < IH * IW; pp += 64) {
+    uint2 d[NIT];
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      const int pp = pp0 + k * 64;
+      const int ry = pp / IW, rx = pp - ry * IW;
       const int iy = ty0 + ry - K / 2, ix = tx0 + rx - K / 2;
-      uint2 v = make_uint2(0u, 0u);
-      if (q < nq && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-        v = *reinterpret_cast<const uint2*>(base + (size_t)(iy * p.W + ix) * p.in_cs);
-      sIn[pp * PSW + q * 2] = v.x;
-      sIn[pp * PSW + q * 2 + 1] = v.y;
-      rx += 64 % IW; ry += 64 / IW;
-      if (rx >= IW) { rx -= IW; ++ry; }
+      d[k] = make_uint2(0u, 0u);
+      if (pp < IH * IW && q < nq && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+        d[k] = *reinterpret_cast<const uint2*>(base + (size_t)(iy * p.W + ix) * p.in_cs);
+    }
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      const int pp = pp0 + k * 64;
+      if (pp < IH * IW) { sIn[pp * PSW + q * 2] = d[k].x; sIn[pp * PSW + q * 2 + 1] = d[k].y; }
     }
   }
   __syncthreads();
