@@ -93,11 +93,29 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
   //      which is exactly torch's index clamping for align_corners=False) -> smem ----
   if (!FAST) for (int i = tid; i < C * C; i += 256) sW2[i] = p.w2[(i / C) * p.w2ld + (i % C)];
   for (int i = tid; i < C; i += 256) sB2[i] = p.b2[i];
-  for (int i = tid; i < PH * PW * (2 * C4); i += 256) {
-    int c4 = i % (2 * C4), pp = i / (2 * C4);
-    int gx = min(max(px0 + pp % PW, 0), p.w - 1), gy = min(max(py0 + pp / PW, 0), p.h - 1);
-    F4 v = load4<T>(P + ((size_t)(n * p.h + gy) * p.w + gx) * p.p_cs + c4 * 4);
-    *reinterpret_cast<float4*>(sP + (c4 / C4) * (PH * PW * C) + pp * C + (c4 % C4) * 4) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+  {
+    // batches of 4 global loads are issued before their shared-memory stores so the L2 round trips overlap
+    constexpr int TOT = PH * PW * (2 * C4), UB = 4;
+    for (int i0 = tid; i0 < TOT; i0 += 256 * UB) {
+      F4 v[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int i = i0 + u * 256;
+        if (i < TOT) {
+          const int c4 = i % (2 * C4), pp = i / (2 * C4);
+          const int gx = min(max(px0 + pp % PW, 0), p.w - 1), gy = min(max(py0 + pp / PW, 0), p.h - 1);
+          v[u] = load4<T>(P + ((size_t)(n * p.h + gy) * p.w + gx) * p.p_cs + c4 * 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int i = i0 + u * 256;
+        if (i < TOT) {
+          const int c4 = i % (2 * C4), pp = i / (2 * C4);
+          *reinterpret_cast<float4*>(sP + (c4 / C4) * (PH * PW * C) + pp * C + (c4 % C4) * 4) = make_float4(v[u].v[0], v[u].v[1], v[u].v[2], v[u].v[3]);
+        }
+      }
+    }
   }
   __syncthreads();
 
