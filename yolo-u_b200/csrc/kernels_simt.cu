@@ -739,9 +739,23 @@ __global__ void __launch_bounds__(256) logits_to_nhwc_kernel(const float* __rest
   o[0] = from_f<T>(lg[e]);
   for (int i = 1; i <= zero_pad; ++i) o[i] = from_f<T>(0.f);
 }
+// bf16 fast path: logit + 15 zero channels = one 32-byte record per pixel, written as two 16-byte stores
+__global__ void __launch_bounds__(256) logits_to_nhwc16_kernel(const float* __restrict__ lg, bf16* __restrict__ out, int out_cs,
+                                                               int total) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= total) return;
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lg[e], 0.f);
+  uint4* o = reinterpret_cast<uint4*>(out + (size_t)e * out_cs);
+  o[0] = make_uint4(*reinterpret_cast<const uint32_t*>(&h), 0u, 0u, 0u);
+  o[1] = make_uint4(0u, 0u, 0u, 0u);
+}
 void launch_logits_to_nhwc(const float* logits, void* out, int N, int h, int w, int out_cs, int zero_pad, int dt,
                            cudaStream_t s) {
   long long total = (long long)N * h * w;
+  if (dt == DT_BF16 && zero_pad == 15 && out_cs % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && total < (1ll << 31)) {
+    logits_to_nhwc16_kernel<<<cdiv(total, 256), 256, 0, s>>>(logits, (bf16*)out, out_cs, (int)total);
+    return;
+  }
   if (dt == DT_F32) logits_to_nhwc_kernel<float><<<cdiv(total, 256), 256, 0, s>>>(logits, (float*)out, out_cs, zero_pad, total);
   else logits_to_nhwc_kernel<bf16><<<cdiv(total, 256), 256, 0, s>>>(logits, (bf16*)out, out_cs, zero_pad, total);
 }
