@@ -799,7 +799,12 @@ __global__ void __launch_bounds__(128) detect_decode_kernel(DecodeP p) {
   for (int sd = 0; sd < 4; ++sd) {
     float v[16], mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { v[i] = r[sd * 16 + i]; mx = fmaxf(mx, v[i]); }
+    for (int i4 = 0; i4 < 4; ++i4) {                    // rows are 16-byte aligned (cs % 4 == 0): 16-byte loads
+      const float4 t = *reinterpret_cast<const float4*>(r + sd * 16 + i4 * 4);
+      v[i4 * 4] = t.x; v[i4 * 4 + 1] = t.y; v[i4 * 4 + 2] = t.z; v[i4 * 4 + 3] = t.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
     float se = 0.f, sw = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) { float ex = expf(v[i] - mx); se += ex; sw = fmaf((float)i, ex, sw); }
