@@ -22,7 +22,7 @@ namespace ysp {
 
 namespace {
 
-constexpr int HR = 18;                       // staged rows: 16 output rows + halo
+constexpr int HR1 = 18, HR2 = 33;            // staged rows for 16 output rows: stride 1 (+ halo) / stride 2
 
 __device__ __forceinline__ uint32_t hs32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void h_umma(uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
@@ -61,6 +61,12 @@ struct HaloP {
   const bf16* in; bf16* out; const bf16* res; const bf16* w; const float* bias;
   int N, H, W, in_cs, out_cs, res_cs, Cout, Ktc, act;
   int nblk, AP, plane, tcols, nbuf;          // column blocks, tile pitch (pixels), bytes per plane, TMEM columns, tile buffers
+  // stride 2 (3x3, pad 1): a staged row holds the ODD input columns (x = 2j-1, j = 0..8*nblk) followed by the EVEN ones
+  // (x = 2j), so the 8 output pixels of a core matrix are again 8 adjacent 16-byte slots for every tap; consecutive output
+  // rows are two staged rows apart (SBO = 2 * row pitch).
+  int stride, OH, OW, rows, sbo16;           // rows = staged rows per tile; sbo16 = SBO in 16-byte units
+  int tiles_x;                               // column tiles of 8 * nblk output pixels
+  int tap_off[9];                            // descriptor start offset of tap (r, s) in 16-byte units
 };
 
 template <int CIN, int NOUT>
@@ -74,8 +80,8 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(HaloP p) {
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tiles_y = (p.H + 15) >> 4;
-  const int total = tiles_y * p.N;
+  const int tiles_y = (p.OH + 15) >> 4;
+  const int total = tiles_y * p.tiles_x * p.N;
   const int tile_bytes = KP * p.plane;
 
   if (tid == 0) {
@@ -99,13 +105,18 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(HaloP p) {
 
   auto stage = [&](int tl, int buf) {                        // cp.async the input tile (zero-filled outside the image)
     if (tl >= total) return;
-    const int n = tl / tiles_y, Y0 = (tl % tiles_y) << 4;
+    const int owb = 8 * p.nblk;
+    const int X0 = (tl % p.tiles_x) * owb;
+    const int tr = tl / p.tiles_x;
+    const int n = tr / tiles_y, Y0 = (tr % tiles_y) << 4;
     uint8_t* dst = sT + (size_t)buf * tile_bytes;
-    const int per_plane = HR * p.AP;
+    const int per_plane = p.rows * p.AP;
     for (int i = tid; i < per_plane * KP; i += 256) {
       const int kc = i % KP, pp = i / KP;
       const int rr = pp / p.AP, cc = pp - rr * p.AP;
-      const int y = Y0 - 1 + rr, x = cc - 1;
+      int y, x;
+      if (p.stride == 1) { y = Y0 - 1 + rr; x = X0 + cc - 1; }
+      else { y = 2 * Y0 - 1 + rr; x = 2 * X0 + (cc <= owb ? 2 * cc - 1 : 2 * (cc - owb - 1)); }
       const bool ok = y >= 0 && y < p.H && x >= 0 && x < p.W;
       const bf16* src = p.in + ((size_t)(n * p.H + (ok ? y : 0)) * p.W + (ok ? x : 0)) * p.in_cs + kc * 8;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(hs32(dst + kc * p.plane + pp * 16)), "l"(src),
@@ -119,13 +130,14 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(HaloP p) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_s;
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const uint32_t a_hi = ((uint32_t)(p.AP * 16) >> 4) | (1u << 14);      // SBO = row pitch, version 1
+  const uint32_t a_hi = (uint32_t)p.sbo16 | (1u << 14);                  // SBO = (stride x) row pitch, version 1
   const uint32_t b_hi = (128u >> 4) | (1u << 14);                        // SBO = 8 rows x 16 B
   uint32_t par = 0;
   int buf = 0;
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const int n = tile / tiles_y, Y0 = (tile % tiles_y) << 4;
+    const int X0 = (tile % p.tiles_x) * 8 * p.nblk;
+    const int n = (tile / p.tiles_x) / tiles_y, Y0 = ((tile / p.tiles_x) % tiles_y) << 4;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // cp.async writes -> visible to the tensor core
     __syncthreads();
@@ -141,7 +153,7 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(HaloP p) {
       for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
         for (int ks = 0; ks < CIN / 16; ++ks) {
-          const uint32_t a_t = t_lo + (uint32_t)((2 * ks * p.plane) >> 4) + (tap / 3) * p.AP + (tap % 3);
+          const uint32_t a_t = t_lo + (uint32_t)((2 * ks * p.plane) >> 4) + (uint32_t)p.tap_off[tap];
           const uint32_t b_t = w_lo + (((tap * KP + 2 * ks) * NOUT * 16) >> 4);
           for (int h = 0; h < p.nblk; ++h) h_umma(tmem + h * NOUT, a_t + 8 * h, a_hi, b_t, b_hi, idesc, (tap | ks) != 0);
         }
@@ -155,9 +167,9 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(HaloP p) {
       const int by = row >> 3, bxl = row & 7;
       const int Y = Y0 + by;
       for (int h = warp >> 2; h < p.nblk; h += 2) {
-        const int X = 8 * h + bxl;
-        const bool valid = Y < p.H && X < p.W;
-        const size_t pix = ((size_t)n * p.H + Y) * p.W + X;
+        const int X = X0 + 8 * h + bxl;
+        const bool valid = Y < p.OH && X < p.OW;
+        const size_t pix = ((size_t)n * p.OH + Y) * p.OW + X;
 #pragma unroll
         for (int c0 = 0; c0 < NOUT; c0 += 16) {
           uint32_t v[16];
@@ -210,12 +222,16 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(HaloP p) {
 
 bool conv_halo_supported(const ConvP& p, int in_dt, int out_dt) {
   if (in_dt != DT_BF16 || out_dt != DT_BF16) return false;
-  if (p.kh != 3 || p.kw != 3 || p.stride != 1 || p.pad != 1 || p.in_pw || p.in_ph) return false;
-  if (p.H != p.OH || p.W != p.OW || p.W > 64 || p.W < 8) return false;
+  if (p.kh != 3 || p.kw != 3 || p.pad != 1 || p.in_pw || p.in_ph) return false;
+  if (p.stride == 1) { if (p.H != p.OH || p.W != p.OW) return false; }
+  else if (p.stride == 2) { if (p.H != 2 * p.OH || p.W != 2 * p.OW || p.res_cs) return false; }
+  else return false;
+  if (p.OW > 64 || p.OW < 8) return false;
   const int cin = (p.Cin + 15) / 16 * 16;
   // measured (profiles/r3_layers.md): with 64 input channels the staged tile + resident weights leave one CTA per SM
   // and the TMA kernel is as fast or faster; the halo path wins for 16 / 32 channels (2.0-3.0x on the 60x60 / 64x64 maps)
   if (cin != 16 && cin != 32) return false;
+  if (p.stride == 2 && cin != 16) return false;                     // the stride-2 tile is 4x larger: 16 channels only
   if (p.Cin != cin && !p.in_zpad) return false;                     // padded input channels must really be zeros
   const int nout = p.cout_store;
   if (nout != 16 && nout != 32 && nout != 64) return false;
@@ -229,9 +245,20 @@ static void conv_halo_launch(const ConvP& p, const void* w_tc, int Ktc, cudaStre
   q.in = (const bf16*)p.in; q.out = (bf16*)p.out; q.res = (const bf16*)p.res; q.w = (const bf16*)w_tc; q.bias = p.bias;
   q.N = p.N; q.H = p.H; q.W = p.W; q.in_cs = p.in_cs; q.out_cs = p.out_cs; q.res_cs = p.res_cs; q.Cout = p.Cout; q.Ktc = Ktc;
   q.act = p.act;
-  q.nblk = (p.W + 7) / 8;
-  q.AP = 8 * q.nblk + 2;
-  q.plane = HR * q.AP * 16;
+  q.stride = p.stride; q.OH = p.OH; q.OW = p.OW;
+  q.nblk = (p.OW + 7) / 8;
+  q.tiles_x = 1;
+  if (p.stride == 2 && q.nblk > 4) { q.tiles_x = (q.nblk + 3) / 4; q.nblk = 4; }   // stride-2 tiles are 4x larger: 32 columns each
+  const int owb = 8 * q.nblk;
+  if (p.stride == 1) {
+    q.AP = owb + 2; q.rows = HR1; q.sbo16 = q.AP;
+    for (int t = 0; t < 9; ++t) q.tap_off[t] = (t / 3) * q.AP + (t % 3);
+  } else {
+    q.AP = 2 * owb + 1; q.rows = HR2; q.sbo16 = 2 * q.AP;
+    const int col[3] = {0, owb + 1, 1};                              // s = 0: odd[ox], s = 1: even[ox], s = 2: odd[ox + 1]
+    for (int t = 0; t < 9; ++t) q.tap_off[t] = (t / 3) * q.AP + col[t % 3];
+  }
+  q.plane = q.rows * q.AP * 16;
   int cols = q.nblk * NOUT;
   q.tcols = 32;
   while (q.tcols < cols) q.tcols <<= 1;
@@ -241,7 +268,7 @@ static void conv_halo_launch(const ConvP& p, const void* w_tc, int Ktc, cudaStre
   const size_t smem = fixed + q.nbuf * tile;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(conv_halo_kernel<CIN, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-  const int total = ((p.H + 15) / 16) * p.N;
+  const int total = ((p.OH + 15) / 16) * q.tiles_x * p.N;
   int per_sm = (int)std::min<size_t>(std::min<size_t>(512 / q.tcols, (220 * 1024) / (smem + 1024)), 4);
   if (per_sm < 1) per_sm = 1;
   const int grid = std::min(total, 148 * per_sm);
