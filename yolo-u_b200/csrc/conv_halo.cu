@@ -111,9 +111,14 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(HaloP p) {
     const int n = tr / tiles_y, Y0 = (tr % tiles_y) << 4;
     uint8_t* dst = sT + (size_t)buf * tile_bytes;
     const int per_plane = p.rows * p.AP;
-    for (int i = tid; i < per_plane * KP; i += 256) {
-      const int kc = i % KP, pp = i / KP;
-      const int rr = pp / p.AP, cc = pp - rr * p.AP;
+    // 256 % KP == 0: a thread keeps its channel plane; its pixel slot advances by 256/KP per pass, tracked as (rr, cc)
+    // incrementally instead of dividing by the runtime pitch for every 16-byte copy
+    const int kc = tid % KP;
+    constexpr int STEP = 256 / KP;
+    const int drr = STEP / p.AP, dcc = STEP - drr * p.AP;
+    int pp = tid / KP, rr = pp / p.AP, cc = pp - rr * p.AP;
+    for (; pp < per_plane; pp += STEP, rr += drr, cc += dcc) {
+      if (cc >= p.AP) { cc -= p.AP; ++rr; }
       int y, x;
       if (p.stride == 1) { y = Y0 - 1 + rr; x = X0 + cc - 1; }
       else { y = 2 * Y0 - 1 + rr; x = 2 * X0 + (cc <= owb ? 2 * cc - 1 : 2 * (cc - owb - 1)); }
