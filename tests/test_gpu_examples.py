@@ -28,3 +28,11 @@ def test_train_example(tmp_path):
     import torch
     sd = torch.load(ck)
     assert "decoder.0.0.cv1.conv.weight" in sd and "encoder.0.conv.weight" in sd and "output.bias" in sd
+
+
+def test_overlapped_schedule_is_bit_identical_to_serial():
+    """tools/soak.py: multi-stream + lanes + PDL pipeline vs the serial schedule, repeated with alternating inputs."""
+    env = dict(os.environ, SOAK_B="48", SOAK_ITERS="12")
+    r = subprocess.run([sys.executable, "tools/soak.py"], cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "bit-identical" in r.stdout
