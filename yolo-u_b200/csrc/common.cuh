@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace ysp {
 
@@ -90,6 +91,19 @@ struct EwP {                // generic elementwise / resampling ops over NHWC vi
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE property of a kernel: remember which devices have it (a
+// process normally drives one GPU, but a handle per device in one process must work too).  `done` = one static per site.
+template <typename Kern>
+inline void ensure_dyn_smem(Kern kernel, size_t bytes, unsigned long long& done, const char* name) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done & bit) return;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) fprintf(stderr, "libysp: cudaFuncSetAttribute(%s, %zu): %s\n", name, bytes, cudaGetErrorString(e));
+  done |= bit;
 }
 
 template <typename... KArgs, typename... Args>

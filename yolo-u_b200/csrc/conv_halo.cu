@@ -271,8 +271,8 @@ static void conv_halo_launch(const ConvP& p, const void* w_tc, int Ktc, cudaStre
   const size_t tile = (size_t)(CIN / 8) * q.plane;
   q.nbuf = (fixed + 2 * tile <= 100 * 1024) ? 2 : 1;               // double-buffer when two CTAs still fit per SM
   const size_t smem = fixed + q.nbuf * tile;
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(conv_halo_kernel<CIN, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  static unsigned long long attr_done = 0;
+  ensure_dyn_smem(conv_halo_kernel<CIN, NOUT>, 200 * 1024, attr_done, "conv_halo_kernel");
   const int total = ((p.OH + 15) / 16) * q.tiles_x * p.N;
   int per_sm = (int)std::min<size_t>(std::min<size_t>(512 / q.tcols, (220 * 1024) / (smem + 1024)), 4);
   if (per_sm < 1) per_sm = 1;

@@ -448,12 +448,8 @@ TcConvPlan* tc_conv_plan_create(const ConvP& c, const void* w_bf16, int out_dt) 
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { fprintf(stderr, "libysp: cuTensorMapEncodeTiled(W) failed: %d\n", (int)r); delete pl; return nullptr; }
   }
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
-    if (e != cudaSuccess) fprintf(stderr, "libysp: cudaFuncSetAttribute(conv_tc_kernel): %s\n", cudaGetErrorString(e));
-    attr = true;
-  }
+  static unsigned long long attr_done = 0;
+  ensure_dyn_smem(conv_tc_kernel, 208 * 1024, attr_done, "conv_tc_kernel");
   return pl;
 }
 

@@ -390,12 +390,8 @@ template <int CIN, int C, bool HEAD>
 static void dlc_tc_launch(const DlcTcP& p, cudaStream_t s) {
   constexpr size_t smem = (size_t)(CIN / 8 + C / 8) * PLANE + (size_t)XR * XC * CIN * 2 +
                           (size_t)(9 * (CIN / 8) * C * 8 + 9 * (C / 8) * C * 8 + (CIN / 8) * C * 8) * 2 + (size_t)20 * C * 4 + 128;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(dlc_tc_kernel<CIN, C, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) fprintf(stderr, "libysp: cudaFuncSetAttribute(dlc_tc_kernel): %s\n", cudaGetErrorString(e));
-    attr = true;
-  }
+  static unsigned long long attr_done = 0;
+  ensure_dyn_smem(dlc_tc_kernel<CIN, C, HEAD>, smem, attr_done, "dlc_tc_kernel");
   const int H = 2 * p.h, W = 2 * p.w;
   const int tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH) * p.N;
   static int sms = 0;

@@ -322,8 +322,8 @@ static void dlc_launch(const DlcP& p, cudaStream_t s) {
   constexpr int SB_FLOATS = FAST ? (NB16 * CSH + 1) / 2 : NB * CS;
   constexpr size_t smem = sizeof(float) * (PH * PW * 2 * C + AH * AW * C + SB_FLOATS + (FAST ? 0 : C * C) + C);
   static_assert(((TH / S4) * TW * (C / 4)) % 256 == 0, "stage 4 must keep warps converged for the head shuffle");
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(dlc_fused_kernel<T, C, TH, TW, S2, S4, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  static unsigned long long attr_done = 0;
+  ensure_dyn_smem(dlc_fused_kernel<T, C, TH, TW, S2, S4, FAST>, smem, attr_done, "dlc_fused_kernel");
   const int H = 2 * p.h, W = 2 * p.w;
   const int tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH) * p.N;
   launch_pdl(dlc_fused_kernel<T, C, TH, TW, S2, S4, FAST>, dim3(tiles), dim3(256), smem, s, p);

@@ -252,12 +252,12 @@ void launch_ghost_fused(const GhostP& p, int c, cudaStream_t s) {
   const int G = c / 4;
   const size_t smem = ghost_smem(G);
   if (G == 8) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(ghost_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    static unsigned long long attr_done = 0;
+    ensure_dyn_smem(ghost_fused_kernel<8>, smem, attr_done, "ghost_fused_kernel<8>");
     launch_pdl(ghost_fused_kernel<8>, dim3(tiles), dim3(256), smem, s, p);
   } else {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(ghost_fused_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    static unsigned long long attr_done = 0;
+    ensure_dyn_smem(ghost_fused_kernel<12>, smem, attr_done, "ghost_fused_kernel<12>");
     launch_pdl(ghost_fused_kernel<12>, dim3(tiles), dim3(256), smem, s, p);
   }
 }

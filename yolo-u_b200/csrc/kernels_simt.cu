@@ -291,8 +291,8 @@ __global__ void __launch_bounds__(TY * TX) conv_dw_tiled_kernel(DwP p) {
 template <typename T, int K, int TY, int TX>
 static void conv_dw_tiled_launch(const DwP& p, cudaStream_t s) {
   constexpr size_t smem = sizeof(float) * ((TY + K - 1) * (TX + K - 1) * 20 + K * K * 16);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(conv_dw_tiled_kernel<T, K, TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  static unsigned long long attr_done = 0;
+  ensure_dyn_smem(conv_dw_tiled_kernel<T, K, TY, TX>, smem, attr_done, "conv_dw_tiled_kernel");
   const int tiles = ((p.W + TX - 1) / TX) * ((p.H + TY - 1) / TY) * ((p.C + 15) >> 4) * p.N;
   launch_pdl(conv_dw_tiled_kernel<T, K, TY, TX>, dim3(tiles), dim3(TY * TX), smem, s, p);
 }

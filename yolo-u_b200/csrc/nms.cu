@@ -216,11 +216,8 @@ static int nms_common(NmsP p, void* ws, size_t ws_bytes, cudaStream_t s) {
   p.gkeys = p.use_gkeys ? reinterpret_cast<unsigned long long*>(w) : nullptr;
   if (p.B == 0) return 0;
   size_t smem = p.use_gkeys ? 0 : (size_t)p.A_pad * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;
+  ensure_dyn_smem(nms_sort_kernel, 16384 * 8, attr_done, "nms_sort_kernel");
   int threads = p.A_pad >= 2048 ? 1024 : (p.A_pad >= 512 ? 256 : 64);
   nms_sort_kernel<<<p.B, threads, smem, s>>>(p);
   nms_scan_kernel<<<p.B, 256, 0, s>>>(p);
