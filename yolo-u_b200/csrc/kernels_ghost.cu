@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
   float* sB = sD2 + 25 * HC;                           // b1[G] bd1[G] b3[HC] bd2[HC]
   uint32_t* sA = reinterpret_cast<uint32_t*>(sB + 2 * G + 2 * HC);   // [GRA*GRA][PA]
   uint32_t* sG = sA + GRA * GRA * PA;                  // [GRA*GRA][PG]   g1 everywhere, g2 inside the GRB region
-  uint32_t* sH = sG + GRA * GRA * PG;                  // [GRB*GRB][PH]
+  uint32_t* sH = sA;                                   // [GRB*GRB][PH]   aliases the a tile: `a` is dead after stage A (the
+                                                       // residual is re-read from global/L2 in stage D) -> 3 CTAs per SM for G = 8
   pdl_sync();
   const int tid = threadIdx.x;
   const int tiles_x = (p.W + GT - 1) / GT, tiles_y = (p.H + GT - 1) / GT;
@@ -226,10 +227,11 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
         const int x = X0 + tx + j;
         if (x >= p.W) break;
         const uint32_t* hc = sH + ((ty + 2) * GRB + tx + j + 2) * PH + q * 2;           // h1 at the output pixel
-        const uint32_t* ac = sA + ((ty + 4) * GRA + tx + j + 4) * PA;                   // a at the output pixel
+        const bf16* ag = p.a + ((size_t)(n * p.H + y) * p.W + x) * p.a_cs;              // a at the output pixel (L2-resident)
+        const uint2 alo = *reinterpret_cast<const uint2*>(ag + q * 4), ahi = *reinterpret_cast<const uint2*>(ag + HC + q * 4);
         const float2 h0 = bf2(hc[0]), h1v = bf2(hc[1]);
-        const float2 a0 = bf2(ac[q * 2]), a1 = bf2(ac[q * 2 + 1]);                      // a[4q .. 4q+3]
-        const float2 a2 = bf2(ac[G + q * 2]), a3 = bf2(ac[G + q * 2 + 1]);              // a[HC + 4q ..]
+        const float2 a0 = bf2(alo.x), a1 = bf2(alo.y);                                  // a[4q .. 4q+3]
+        const float2 a2 = bf2(ahi.x), a3 = bf2(ahi.y);                                  // a[HC + 4q ..]
         bf16* op = obase + ((size_t)y * p.W + x) * p.out_cs;
         // rounding points of the unfused chain: h1 is a bf16 tensor, h2 + a is rounded once
         *reinterpret_cast<uint2*>(op + q * 4) = make_uint2(pack2(h0.x + a0.x, h0.y + a0.y), pack2(h1v.x + a1.x, h1v.y + a1.y));
@@ -241,7 +243,8 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
 
 static size_t ghost_smem(int G) {
   const int CA = 4 * G, HC = 2 * G, PA = CA / 2 + 1, PG = G + 1, PH = G + 1;
-  return 4 * ((size_t)GRA * GRA * PA + (size_t)GRA * GRA * PG + (size_t)GRB * GRB * PH) +
+  (void)PH;                                            // the h1 tile aliases the (larger) a tile
+  return 4 * ((size_t)GRA * GRA * PA + (size_t)GRA * GRA * PG) +
          4 * ((size_t)CA * G + 2 * G * HC + 25 * G + 25 * HC + 2 * G + 2 * HC);
 }
 
