@@ -57,18 +57,27 @@ __global__ void __launch_bounds__(256, 4) pw_gemm_kernel(const float* __restrict
     float acc[4][4] = {};
     for (int i0 = 0; i0 < I; i0 += BK) {
       if (vecA) {
-        for (int e = tid; e < BM * (BK / 4); e += 256) {
-          int r = e / (BK / 4), i = (e % (BK / 4)) * 4;
-          long long m = m0 + r;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < M && i0 + i < I) {                                                               // I % 4 == 0
-            v = *reinterpret_cast<const float4*>(A + m * lda + i0 + i);
-            if (tfon) {
-              const int ig = i0 + i;
-              v.x = fmaf(v.x, sSc[ig], sSh[ig]); v.y = fmaf(v.y, sSc[ig + 1], sSh[ig + 1]);
-              v.z = fmaf(v.z, sSc[ig + 2], sSh[ig + 2]); v.w = fmaf(v.w, sSc[ig + 3], sSh[ig + 3]);
-              if (tf.act) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w)); }
-            }
+        // all of this thread's 16-byte loads of the chunk are issued before the first shared-memory store
+        constexpr int NL = BM * (BK / 4) / 256;
+        float4 va[NL];
+#pragma unroll
+        for (int u = 0; u < NL; ++u) {
+          const int e = tid + u * 256;
+          const int r = e / (BK / 4), i = (e % (BK / 4)) * 4;
+          const long long m = m0 + r;
+          va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < M && i0 + i < I) va[u] = *reinterpret_cast<const float4*>(A + m * lda + i0 + i);      // I % 4 == 0
+        }
+#pragma unroll
+        for (int u = 0; u < NL; ++u) {
+          const int e = tid + u * 256;
+          const int r = e / (BK / 4), i = (e % (BK / 4)) * 4;
+          float4 v = va[u];
+          if (tfon && m0 + r < M && i0 + i < I) {
+            const int ig = i0 + i;
+            v.x = fmaf(v.x, sSc[ig], sSh[ig]); v.y = fmaf(v.y, sSc[ig + 1], sSh[ig + 1]);
+            v.z = fmaf(v.z, sSc[ig + 2], sSh[ig + 2]); v.w = fmaf(v.w, sSc[ig + 3], sSh[ig + 3]);
+            if (tf.act) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w)); }
           }
           As[i][r] = v.x; As[i + 1][r] = v.y; As[i + 2][r] = v.z; As[i + 3][r] = v.w;
         }
@@ -203,34 +212,46 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
     }
   float acc[4][4] = {};
   // one staged tile: rows [rb, rb+RS) x columns [c0, c0+TC) of a row-major matrix, zero-filled outside
-  auto stage = [&](const float* __restrict__ src, int ld, int c0, int cols, bool vec, float* dst, int dld, int TC,
-                   long long rb, bool xf) {
-    const int q4 = TC / 4;
-    for (int e = tid; e < RS * q4; e += 256) {
-      int r = e / q4, c = (e % q4) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rb + r < r1) {
-        const float* p = src + (rb + r) * ld + c0 + c;
-        if (vec && c0 + c + 3 < cols) v = *reinterpret_cast<const float4*>(p);
-        else {
-          if (c0 + c < cols) v.x = p[0];
-          if (c0 + c + 1 < cols) v.y = p[1];
-          if (c0 + c + 2 < cols) v.z = p[2];
-          if (c0 + c + 3 < cols) v.w = p[3];
-        }
-        if (xf) {       // columns beyond `cols` have sc = sh = 0 and stay 0 (SiLU(0) = 0)
-          v.x = fmaf(v.x, sSc[c], sSh[c]); v.y = fmaf(v.y, sSc[c + 1], sSh[c + 1]);
-          v.z = fmaf(v.z, sSc[c + 2], sSh[c + 2]); v.w = fmaf(v.w, sSc[c + 3], sSh[c + 3]);
-          if (tf.act) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w)); }
-        }
+  // one staged tile: rows [rb, rb+RS) x columns [c0, c0+TC) of a row-major matrix, zero-filled outside.  `fetch` issues
+  // the global loads into registers, `put` (transform +) stores them: both matrices are fetched before anything is stored,
+  // so a thread has 4-6 independent 16-byte loads in flight instead of one.
+  auto fetch = [&](const float* __restrict__ src, int ld, int c0, int cols, bool vec, int q4, int e, long long rb) -> float4 {
+    const int r = e / q4, c = (e % q4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rb + r < r1) {
+      const float* p = src + (rb + r) * ld + c0 + c;
+      if (vec && c0 + c + 3 < cols) v = *reinterpret_cast<const float4*>(p);
+      else {
+        if (c0 + c < cols) v.x = p[0];
+        if (c0 + c + 1 < cols) v.y = p[1];
+        if (c0 + c + 2 < cols) v.z = p[2];
+        if (c0 + c + 3 < cols) v.w = p[3];
       }
-      *reinterpret_cast<float4*>(dst + r * dld + c) = v;
     }
+    return v;
   };
+  auto put = [&](float4 v, float* dst, int dld, int q4, int e, long long rb, bool xf) {
+    const int r = e / q4, c = (e % q4) * 4;
+    if (xf && rb + r < r1) {       // columns beyond the matrix have sc = sh = 0 and stay 0 (SiLU(0) = 0)
+      v.x = fmaf(v.x, sSc[c], sSh[c]); v.y = fmaf(v.y, sSc[c + 1], sSh[c + 1]);
+      v.z = fmaf(v.z, sSc[c + 2], sSh[c + 2]); v.w = fmaf(v.w, sSc[c + 3], sSh[c + 3]);
+      if (tf.act) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w)); }
+    }
+    *reinterpret_cast<float4*>(dst + r * dld + c) = v;
+  };
+  constexpr int NLD = RS * (TJ / 4) / 256, NLX = RS * (TI / 4) / 256;
+  static_assert(NLD >= 1 && NLX >= 1 && RS * (TJ / 4) % 256 == 0 && RS * (TI / 4) % 256 == 0, "staging loop shape");
   for (long long rb = r0; rb < r1; rb += RS) {
     __syncthreads();
-    stage(D, ldd, j0, J, vecD, &sD[0][0], TJ + 4, TJ, rb, false);
-    stage(X, ldx, i0, I, vecX, &sX[0][0], TI + 4, TI, rb, tfon);
+    float4 vd[NLD], vx[NLX];
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) vd[u] = fetch(D, ldd, j0, J, vecD, TJ / 4, tid + u * 256, rb);
+#pragma unroll
+    for (int u = 0; u < NLX; ++u) vx[u] = fetch(X, ldx, i0, I, vecX, TI / 4, tid + u * 256, rb);
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) put(vd[u], &sD[0][0], TJ + 4, TJ / 4, tid + u * 256, rb, false);
+#pragma unroll
+    for (int u = 0; u < NLX; ++u) put(vx[u], &sX[0][0], TI + 4, TI / 4, tid + u * 256, rb, tfon);
     __syncthreads();
 #pragma unroll 4
     for (int r = g; r < RS; r += G) {
@@ -449,19 +470,33 @@ __global__ void __launch_bounds__(256) dw_tiled_kernel(const float* __restrict__
     const int ty0 = (t % tiles_y) * TY;
     const int n = t / tiles_y;
     __syncthreads();
-    for (int i = tid; i < IH * IW * 4; i += 256) {
-      const int qq = i & 3, pp = i >> 2;
-      const int iy = ty0 + pp / IW - PAD, ix = tx0 + pp % IW - PAD;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (qq < nq && iy >= 0 && iy < H && ix >= 0 && ix < Wd) {
-        v = *reinterpret_cast<const float4*>(X + ((size_t)(n * H + iy) * Wd + ix) * ldx + cg + qq * 4);
-        if (tfon) {        // the conv zero-pads the TRANSFORMED tensor: only in-image pixels are mapped
+    {
+      // the input tile: all of a thread's 16-byte loads are issued before its first shared-memory store
+      constexpr int TOT = IH * IW * 4, NL = (TOT + 255) / 256;
+      float4 vv[NL];
+      bool inimg[NL];
+#pragma unroll
+      for (int u = 0; u < NL; ++u) {
+        const int i = tid + u * 256;
+        const int qq = i & 3, pp = i >> 2;
+        const int iy = ty0 + pp / IW - PAD, ix = tx0 + pp % IW - PAD;
+        vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        inimg[u] = i < TOT && qq < nq && iy >= 0 && iy < H && ix >= 0 && ix < Wd;
+        if (inimg[u]) vv[u] = *reinterpret_cast<const float4*>(X + ((size_t)(n * H + iy) * Wd + ix) * ldx + cg + qq * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < NL; ++u) {
+        const int i = tid + u * 256;
+        if (i >= TOT) break;
+        const int qq = i & 3, pp = i >> 2;
+        float4 v = vv[u];
+        if (tfon && inimg[u]) {        // the conv zero-pads the TRANSFORMED tensor: only in-image pixels are mapped
           const float4 sc = *reinterpret_cast<const float4*>(sSc + qq * 4), sh = *reinterpret_cast<const float4*>(sSh + qq * 4);
           v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
           if (tf.act) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w)); }
         }
+        *reinterpret_cast<float4*>(sIn + pp * PS + qq * 4) = v;
       }
-      *reinterpret_cast<float4*>(sIn + pp * PS + qq * 4) = v;
     }
     __syncthreads();
     const int y = ty0 + ty;
