@@ -556,7 +556,19 @@ __global__ void __launch_bounds__(512) eca_gate_bf16_kernel(const bf16* __restri
   const bf16* xb = x + (size_t)blockIdx.x * HW * cs + g * 8;
   float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (lane < lanes) {
-    for (int i = lane; i < HW; i += lanes) {
+    int i = lane;
+    for (; i + 3 * lanes < HW; i += 4 * lanes) {           // four independent 16-byte loads in flight per thread
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(xb + (size_t)(i + u * lanes) * cs);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a[2 * j] += __low2float(h[j]); a[2 * j + 1] += __high2float(h[j]); }
+      }
+    }
+    for (; i < HW; i += lanes) {
       const uint4 v = *reinterpret_cast<const uint4*>(xb + (size_t)i * cs);
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll

@@ -136,14 +136,26 @@ __global__ void __launch_bounds__(128) attention64_kernel(const bf16* __restrict
   const bf16* base = qkv + tok0 * qkv_cs + h * 3 * HD;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, tig = lane & 3;
   // stage K (row-major) and V (transposed): 64 tokens x 32 dims each, 8-byte vector loads
-  for (int i = tid; i < NT * (HD / 4); i += 128) {
-    const int tok = i / (HD / 4), d4 = (i % (HD / 4)) * 4;
-    uint2 kv = *reinterpret_cast<const uint2*>(base + (size_t)tok * qkv_cs + HD + d4);
-    *reinterpret_cast<uint2*>(sK + tok * KS + d4) = kv;
-    uint2 vv = *reinterpret_cast<const uint2*>(base + (size_t)tok * qkv_cs + 2 * HD + d4);
-    const bf16* ve = reinterpret_cast<const bf16*>(&vv);
+  {
+    // all eight 8-byte loads of a thread are issued before its first shared-memory store
+    constexpr int NL = NT * (HD / 4) / 128;
+    uint2 kk[NL], vv[NL];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sV[(d4 + j) * VS + tok] = ve[j];
+    for (int u = 0; u < NL; ++u) {
+      const int i = tid + u * 128;
+      const int tok = i / (HD / 4), d4 = (i % (HD / 4)) * 4;
+      kk[u] = *reinterpret_cast<const uint2*>(base + (size_t)tok * qkv_cs + HD + d4);
+      vv[u] = *reinterpret_cast<const uint2*>(base + (size_t)tok * qkv_cs + 2 * HD + d4);
+    }
+#pragma unroll
+    for (int u = 0; u < NL; ++u) {
+      const int i = tid + u * 128;
+      const int tok = i / (HD / 4), d4 = (i % (HD / 4)) * 4;
+      *reinterpret_cast<uint2*>(sK + tok * KS + d4) = kk[u];
+      const bf16* ve = reinterpret_cast<const bf16*>(&vv[u]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sV[(d4 + j) * VS + tok] = ve[j];
+    }
   }
   // Q fragments straight from global: rows g / g+8 of this warp's 16 queries, 2 k-steps of 16 dims
   uint32_t qa[2][4];
