@@ -174,6 +174,10 @@ int ysp_train_step(ysp_trainer* t, const float* d_skipA, const float* d_skipB, c
                    const float* d_target, const float* d_params, float* d_grads, float* d_stats, float momentum,
                    int loss_kind, float grad_scale, float* d_loss3, float* d_mask_logits, void* d_ws, size_t ws_bytes,
                    void* stream);
+/* The loss alone, over n = B*H*W mask logits (validation half of the epoch, train.py:356-357): d_loss3 = {total, dice, bce}
+ * with the same reductions as ysp_train_step.  d_ws32 = 32 bytes of device scratch. */
+int ysp_seg_loss(const float* d_logits, const float* d_target, int64_t n, int loss_kind, float* d_loss3, void* d_ws32,
+                 void* stream);
 /* torch.optim.AdamW step over a flat buffer (train.py:262, :325): grads are multiplied by grad_scale first; max_norm > 0
  * applies clip_grad_norm_ semantics (train.py:324 -- a no-op in the reference, its parameter generator is already
  * exhausted; so callers pass 0).  d_ws8 = 8 bytes of device scratch (only read when clipping). */

@@ -167,3 +167,23 @@ def test_shape_errors():
         tr.forward_backward(x.cuda(), tg.cuda(), lg[:, :, :4].cuda())
     with pytest.raises(Exception):
         tr.forward_backward(x, tg, lg)            # CPU tensors: no fallback
+
+
+def test_validate_batch_matches_eval_mode_oracle():
+    """train.py:346-366: eval-mode forward + loss value + Dice counters after a few training steps."""
+    import copy
+    from oracle.model import dice_loss, mask_counts
+    B, S = 2, 64
+    seg, tr, x, lg, tg = _setup(B, S)
+    for _ in range(2):
+        tr.step(x.cuda(), tg.cuda(), lg.cuda())
+    loss3, counts, pred = tr.validate_batch(x.cuda(), tg.cuda(), lg.cuda())
+    seg2 = copy.deepcopy(seg)
+    seg2.load_state_dict({k: v.cpu() for k, v in tr.state_dict().items()}, strict=True)
+    seg2.eval()
+    with torch.no_grad():
+        ref = seg2(x, lg)
+        want = dice_loss(ref, tg).item()
+    assert (pred.cpu() - ref).abs().max().item() <= 1e-3
+    assert abs(loss3[0].item() - want) <= 1e-5
+    assert torch.equal(counts.cpu().long(), mask_counts(pred.cpu(), tg))

@@ -1020,6 +1020,19 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict_
   }
 }
 
+__global__ void loss_value_kernel(const double* __restrict__ acc, long long n, int kind, float* loss_out) {
+  const double P = acc[0], Tt = acc[1], A = acc[2], eps = 1e-5;
+  const double dice = 1.0 - ((P + Tt - A) + eps) / (P + Tt + eps), bce = kind == 1 ? acc[3] / (double)n : 0.0;
+  loss_out[0] = (float)(dice + bce); loss_out[1] = (float)dice; loss_out[2] = (float)bce;
+}
+// loss only (validation, train.py:356-357): same reductions as launch_loss, no gradient
+void launch_loss_value(const float* X, const float* T, long long n, double* acc, int kind, float* loss_out, cudaStream_t s) {
+  int grid = (int)std::min<long long>(cdivl(n, 256), 148 * 8);
+  cudaMemsetAsync(acc, 0, 4 * sizeof(double), s);
+  loss_reduce_kernel<<<grid, 256, 0, s>>>(X, T, n, acc);
+  loss_value_kernel<<<1, 1, 0, s>>>(acc, n, kind, loss_out);
+}
+
 void launch_loss(const float* X, const float* T, long long n, double* acc, int kind, float grad_scale, float* DX,
                  float* loss_out, cudaStream_t s) {
   int grid = (int)std::min<long long>(cdivl(n, 256), 148 * 8);

@@ -464,6 +464,16 @@ int ysp_train_step(ysp_trainer* t, const float* d_skipA, const float* d_skipB, c
   return 0;
 }
 
+int ysp_seg_loss(const float* d_logits, const float* d_target, int64_t n, int loss_kind, float* d_loss3, void* d_ws32,
+                 void* stream) {
+  if (!d_logits || !d_target || !d_loss3 || !d_ws32 || n <= 0) return tfail(YSP_EINVAL, "ysp_seg_loss: bad arguments");
+  if (loss_kind < 0 || loss_kind > 1) return tfail(YSP_EINVAL, "ysp_seg_loss: loss_kind must be 0 (Dice) or 1 (Dice+BCE)");
+  launch_loss_value(d_logits, d_target, (long long)n, (double*)d_ws32, loss_kind, d_loss3, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return tfail(YSP_ECUDA, "ysp_seg_loss: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int ysp_adamw(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n, float lr, float beta1, float beta2,
               float eps, float weight_decay, int step, float grad_scale, float max_norm, void* d_ws8, void* stream) {
   if (!d_params || !d_grads || !d_m || !d_v || n < 0 || step < 1) return tfail(YSP_EINVAL, "ysp_adamw: bad arguments");

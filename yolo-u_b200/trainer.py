@@ -183,6 +183,28 @@ class SegHeadTrainer:
         self.optimizer_step()
         return loss, pred
 
+    @torch.no_grad()
+    def validate_batch(self, img: torch.Tensor, mask: torch.Tensor, heatmaps: torch.Tensor, mode: str = "fp32"):
+        """One iteration of the validation loop (train.py:346-366): model.eval() forward (BN running statistics) through
+        the inference engine, the loss value, and the integer counters (|P&T|, |P|, |T| per slice) that Dice, precision
+        and recall are made of.  Returns (loss3 device tensor {total, dice, bce}, counts int32 [B,3], pred logits)."""
+        if getattr(self, "_eval_step", None) != (self.step_count, mode):
+            self._eval = self.eval_engine(mode)               # weights changed since the last validation pass
+            self._eval_step = (self.step_count, mode)
+        require_cuda(img, "SegHeadTrainer")
+        pred = self._eval.segpp_forward(_f32c(img), _f32c(heatmaps))
+        mask = _f32c(mask)
+        B, _, H, W = pred.shape
+        loss3 = torch.empty(3, dtype=torch.float32, device=self.device)
+        counts = torch.empty(B, 3, dtype=torch.int32, device=self.device)
+        ws = torch.empty(4, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            st = _stream_ptr(self.device)
+            check(lib().ysp_seg_loss(pred.data_ptr(), mask.data_ptr(), pred.numel(), self.loss_kind, loss3.data_ptr(),
+                                     ws.data_ptr(), st))
+            check(lib().ysp_mask_dice(pred.data_ptr(), mask.data_ptr(), B, H * W, counts.data_ptr(), None, st))
+        return loss3, counts, pred
+
     def scheduler_step(self):
         """CosineAnnealingLR(T_max=epochs, eta_min=0).step() (train.py:264, :398), closed form."""
         self.epoch += 1
