@@ -15,6 +15,13 @@
  *   evaluate_model.py:157-158,166-174  sigmoid>0.5, TP/FP/FN, Dice counts        ysp_mask_dice
  *   evaluate_model.py:134-174  (the loop body = the de-facto predict())          ysp_pipeline
  *   evaluate_model.py:234-243 / YOLOSegPlusPlus.py:150 (state_dict tensors)      ysp_load_weight / ysp_finalize
+ *   train.py:302-331  zero_grad / forward (train mode) / DiceLoss / backward      ysp_encoder_forward + ysp_train_step
+ *   train.py:262,329  optim.AdamW(...).step()  (+ :328 clip_grad_norm_)           ysp_adamw
+ *   train.py:346-366  validation loss                                             ysp_seg_loss (+ ysp_mask_dice)
+ *   dataset.py:59-70  cv2.resize (INTER_LINEAR / INTER_NEAREST) + ToTensor         ysp_resize_u8
+ *   dataset.py:86-97  objectmap z-score + sigmoid                                  ysp_objectmap_transform
+ *   custom_detseg_predictor.py:177  ops.scale_boxes                               ysp_scale_boxes
+ *   evaluate_model.py:149-155  (commented-out) detection-confidence gate          ysp_conf_gate
  *
  * Conventions: every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a HOST pointer.  Nothing
  * is allocated per call: scratch comes from the caller-provided workspace (`d_ws`, at least
