@@ -4,8 +4,7 @@
 Inputs are regenerated from the seed by the tests; only sizes + cv2 outputs are stored."""
 import os
 
-import cv2
-import numpy as np
+import numpy as np      # cv2 is imported in main() only: the tests import `inputs` from here and must not need OpenCV
 
 CASES = [(155, 200, 96, 96), (96, 96, 96, 96), (75, 65, 60, 60), (60, 60, 120, 120),
          (128, 128, 64, 64), (128, 80, 64, 64), (97, 131, 64, 48), (64, 48, 97, 131), (33, 17, 128, 96), (1, 1, 8, 8),
@@ -20,6 +19,7 @@ def inputs(i, sh, sw):
 
 
 def main():
+    import cv2
     out = {"cases": np.array(CASES, dtype=np.int32), "cv2_version": np.array(cv2.__version__)}
     for i, (sh, sw, dh, dw) in enumerate(CASES):
         img, mask = inputs(i, sh, sw)
