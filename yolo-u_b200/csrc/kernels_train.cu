@@ -30,9 +30,10 @@ static void dw_tiled_launch(const float* X, int ldx, const float* W, float* Y, i
 // Thread micro-tile 4x4; BN in {16,32,64} columns per CTA and 4*(256/(BN/4)) rows, so narrow outputs waste nothing.
 // =====================================================================================================================
 template <int BN>
-__global__ void __launch_bounds__(256, 4) pw_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
-                                                      int ldw, int trans, const float* __restrict__ bias, float* C,
-                                                      int ldc, long long M, int I, int J, int beta, double* sums, InTf tf) {
+__global__ void __launch_bounds__(256, 4) pw_gemm_kernel(const float* __restrict__ A0, int lda0, const float* __restrict__ W0,
+                                                      int ldw0, int trans, const float* __restrict__ bias, float* C,
+                                                      int ldc, long long M, int I0, int J, int beta, double* sums, InTf tf,
+                                                      PwDual du) {
   constexpr int BK = 16, TX = BN / 4, TY = 256 / TX, BM = TY * 4;
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -41,90 +42,107 @@ __global__ void __launch_bounds__(256, 4) pw_gemm_kernel(const float* __restrict
   const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
   const bool tfon = tf.gamma != nullptr;
   if (tfon) {
-    for (int i = tid; i < I; i += 256) {
+    for (int i = tid; i < I0; i += 256) {
       const float sc = tf.gamma[i] * tf.invstd[i];
       sSc[i] = sc; sSh[i] = tf.beta[i] - tf.mean[i] * sc;
     }
     __syncthreads();
   }
   const int j0 = blockIdx.y * BN;
-  const bool vecA = ((lda | I) & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
-  const bool vecC = ((ldc | J) & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+  const int Jstat = du.Jsplit ? du.Jsplit : J;         // columns that carry BN statistics
+  const bool vecC = ((ldc | J | du.Jsplit | du.ldcb) & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(du.Cb) & 15) == 0;
   const long long mtiles = (M + BM - 1) / BM;
+  const int nparts = du.A2 ? 2 : 1;
   float cs1[4] = {0.f, 0.f, 0.f, 0.f}, cs2[4] = {0.f, 0.f, 0.f, 0.f};   // column sums of this thread's outputs (BN statistics)
   for (long long mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
     const long long m0 = mt * BM;
     float acc[4][4] = {};
-    for (int i0 = 0; i0 < I; i0 += BK) {
-      if (vecA) {
-        // all of this thread's 16-byte loads of the chunk are issued before the first shared-memory store
-        constexpr int NL = BM * (BK / 4) / 256;
-        float4 va[NL];
+    for (int part = 0; part < nparts; ++part) {
+      const float* __restrict__ A = part ? du.A2 : A0;
+      const float* __restrict__ W = part ? du.W2 : W0;
+      const int lda = part ? du.lda2 : lda0, ldw = part ? du.ldw2 : ldw0, I = part ? du.I2 : I0;
+      const bool vecA = ((lda | I) & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+      const bool xf = tfon && part == 0;
+      for (int i0 = 0; i0 < I; i0 += BK) {
+        if (vecA) {
+          // all of this thread's 16-byte loads of the chunk are issued before the first shared-memory store
+          constexpr int NL = BM * (BK / 4) / 256;
+          float4 va[NL];
 #pragma unroll
-        for (int u = 0; u < NL; ++u) {
-          const int e = tid + u * 256;
-          const int r = e / (BK / 4), i = (e % (BK / 4)) * 4;
-          const long long m = m0 + r;
-          va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < M && i0 + i < I) va[u] = *reinterpret_cast<const float4*>(A + m * lda + i0 + i);      // I % 4 == 0
-        }
-#pragma unroll
-        for (int u = 0; u < NL; ++u) {
-          const int e = tid + u * 256;
-          const int r = e / (BK / 4), i = (e % (BK / 4)) * 4;
-          float4 v = va[u];
-          if (tfon && m0 + r < M && i0 + i < I) {
-            const int ig = i0 + i;
-            v.x = fmaf(v.x, sSc[ig], sSh[ig]); v.y = fmaf(v.y, sSc[ig + 1], sSh[ig + 1]);
-            v.z = fmaf(v.z, sSc[ig + 2], sSh[ig + 2]); v.w = fmaf(v.w, sSc[ig + 3], sSh[ig + 3]);
-            if (tf.act) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w)); }
+          for (int u = 0; u < NL; ++u) {
+            const int e = tid + u * 256;
+            const int r = e / (BK / 4), i = (e % (BK / 4)) * 4;
+            const long long m = m0 + r;
+            va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && i0 + i < I) va[u] = *reinterpret_cast<const float4*>(A + m * lda + i0 + i);      // I % 4 == 0
           }
-          As[i][r] = v.x; As[i + 1][r] = v.y; As[i + 2][r] = v.z; As[i + 3][r] = v.w;
-        }
-      } else {
-        for (int e = tid; e < BM * BK; e += 256) {
-          int r = e / BK, i = e % BK;
-          long long m = m0 + r;
-          float v = 0.f;
-          if (m < M && i0 + i < I) {
-            v = A[m * lda + i0 + i];
-            if (tfon) { v = fmaf(v, sSc[i0 + i], sSh[i0 + i]); if (tf.act) v = v / (1.f + expf(-v)); }
+#pragma unroll
+          for (int u = 0; u < NL; ++u) {
+            const int e = tid + u * 256;
+            const int r = e / (BK / 4), i = (e % (BK / 4)) * 4;
+            float4 v = va[u];
+            if (xf && m0 + r < M && i0 + i < I) {
+              const int ig = i0 + i;
+              v.x = fmaf(v.x, sSc[ig], sSh[ig]); v.y = fmaf(v.y, sSc[ig + 1], sSh[ig + 1]);
+              v.z = fmaf(v.z, sSc[ig + 2], sSh[ig + 2]); v.w = fmaf(v.w, sSc[ig + 3], sSh[ig + 3]);
+              if (tf.act) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w)); }
+            }
+            As[i][r] = v.x; As[i + 1][r] = v.y; As[i + 2][r] = v.z; As[i + 3][r] = v.w;
           }
-          As[i][r] = v;
+        } else {
+          for (int e = tid; e < BM * BK; e += 256) {
+            int r = e / BK, i = e % BK;
+            long long m = m0 + r;
+            float v = 0.f;
+            if (m < M && i0 + i < I) {
+              v = A[m * lda + i0 + i];
+              if (xf) { v = fmaf(v, sSc[i0 + i], sSh[i0 + i]); if (tf.act) v = v / (1.f + expf(-v)); }
+            }
+            As[i][r] = v;
+          }
         }
-      }
-      for (int e = tid; e < BK * BN; e += 256) {
-        int i = e / BN, jj = e % BN;
-        int ig = i0 + i, jg = j0 + jj;
-        Bs[i][jj] = (ig < I && jg < J) ? (trans ? W[(size_t)ig * ldw + jg] : W[(size_t)jg * ldw + ig]) : 0.f;
-      }
-      __syncthreads();
+        for (int e = tid; e < BK * BN; e += 256) {
+          int i = e / BN, jj = e % BN;
+          int ig = i0 + i, jg = j0 + jj;
+          float w = 0.f;
+          if (ig < I && jg < J) {
+            if (du.Jsplit && jg >= du.Jsplit) w = du.Wb[(size_t)(jg - du.Jsplit) * du.ldwb + ig];      // forward layout [Cout][Cin]
+            else w = trans ? W[(size_t)ig * ldw + jg] : W[(size_t)jg * ldw + ig];
+          }
+          Bs[i][jj] = w;
+        }
+        __syncthreads();
 #pragma unroll
-      for (int kk = 0; kk < BK; ++kk) {
-        float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-        float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+        for (int kk = 0; kk < BK; ++kk) {
+          float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+          float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+          const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+          for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+            for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+        }
+        __syncthreads();
       }
-      __syncthreads();
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       long long m = m0 + ty * 4 + r;
       if (m >= M) continue;
       const int jb = j0 + tx * 4;
-      if (sums) {
+      if (sums && jb < Jstat) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) { cs1[c] += acc[r][c]; cs2[c] = fmaf(acc[r][c], acc[r][c], cs2[c]); }
       }
+      const bool second = du.Jsplit && jb >= du.Jsplit;
+      float* crow = second ? du.Cb + m * du.ldcb + (jb - du.Jsplit) : C + m * ldc + jb;
+      const float* brow = second ? (du.biasb ? du.biasb + (jb - du.Jsplit) : nullptr) : (bias ? bias + jb : nullptr);
       if (vecC) {
         if (jb >= J) continue;
-        float4* o = reinterpret_cast<float4*>(C + m * ldc + jb);
+        float4* o = reinterpret_cast<float4*>(crow);
         float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-        if (bias) { v.x += bias[jb]; v.y += bias[jb + 1]; v.z += bias[jb + 2]; v.w += bias[jb + 3]; }
+        if (brow) { v.x += brow[0]; v.y += brow[1]; v.z += brow[2]; v.w += brow[3]; }
         if (beta) { float4 pv = *o; v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w; }
         *o = v;
         continue;
@@ -133,8 +151,8 @@ __global__ void __launch_bounds__(256, 4) pw_gemm_kernel(const float* __restrict
       for (int c = 0; c < 4; ++c) {
         int jx = jb + c;
         if (jx >= J) continue;
-        float v = acc[r][c] + (bias ? bias[jx] : 0.f);
-        float* o = C + m * ldc + jx;
+        float v = acc[r][c] + (brow ? brow[c] : 0.f);
+        float* o = crow + c;
         *o = beta ? *o + v : v;
       }
     }
@@ -151,7 +169,7 @@ __global__ void __launch_bounds__(256, 4) pw_gemm_kernel(const float* __restrict
     }
     __syncthreads();
     for (int e = tid; e < 2 * BN; e += 256)
-      if (j0 + e % BN < J) atomicAdd(&sums[(e / BN) * J + j0 + e % BN], sRed[e / BN][e % BN]);
+      if (j0 + e % BN < Jstat) atomicAdd(&sums[(e / BN) * Jstat + j0 + e % BN], sRed[e / BN][e % BN]);
   }
 }
 
@@ -165,19 +183,19 @@ static int resident_ctas(Kern kern, int threads, size_t smem) {
 
 template <int BN>
 static void pw_gemm_launch(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc,
-                           long long M, int I, int J, int beta, cudaStream_t s, double* sums, InTf tf) {
+                           long long M, int I, int J, int beta, cudaStream_t s, double* sums, InTf tf, PwDual du) {
   constexpr int BM = (256 / (BN / 4)) * 4;
   static const int occ = resident_ctas(pw_gemm_kernel<BN>, 256, 0);
   const int jt = cdivl(J, BN);
   const int cap = std::max(1, 148 * occ / jt);
-  pw_gemm_kernel<BN><<<dim3(std::min(cdivl(M, BM), cap), jt), 256, 0, s>>>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, sums, tf);
+  pw_gemm_kernel<BN><<<dim3(std::min(cdivl(M, BM), cap), jt), 256, 0, s>>>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, sums, tf, du);
 }
 
 void launch_pw_gemm(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc,
-                    long long M, int I, int J, int beta, cudaStream_t s, double* sums, InTf tf) {
-  if (J <= 16) pw_gemm_launch<16>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums, tf);
-  else if (J <= 32) pw_gemm_launch<32>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums, tf);
-  else pw_gemm_launch<64>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums, tf);
+                    long long M, int I, int J, int beta, cudaStream_t s, double* sums, InTf tf, PwDual du) {
+  if (J <= 16) pw_gemm_launch<16>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums, tf, du);
+  else if (J <= 32) pw_gemm_launch<32>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums, tf, du);
+  else pw_gemm_launch<64>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums, tf, du);
 }
 
 // =====================================================================================================================

@@ -10,9 +10,18 @@ struct BnRef { const float *gamma, *beta, *mean, *invstd; };
 // consumer read its producer's raw conv output z, so the producer's normalised tensor is never written (gamma == NULL: off).
 struct InTf { const float *gamma = nullptr, *beta = nullptr, *mean = nullptr, *invstd = nullptr; int act = 0; };
 
+// Optional second operand set of launch_pw_gemm:
+//   A2/W2/I2 : a second reduction range, C += A2 * W2op  (the two input-gradient GEMMs that feed one tensor as ONE kernel);
+//   Jsplit   : output columns >= Jsplit use weights Wb (row j - Jsplit), bias biasb and go to Cb (two 1x1 convs that read
+//              the same input as ONE kernel); BN statistics are then taken over the first Jsplit columns only.
+struct PwDual {
+  const float* A2 = nullptr; int lda2 = 0; const float* W2 = nullptr; int ldw2 = 0; int I2 = 0;
+  int Jsplit = 0; const float* Wb = nullptr; int ldwb = 0; const float* biasb = nullptr; float* Cb = nullptr; int ldcb = 0;
+};
 // `sums` (optional, [2][J] doubles, pre-zeroed): per-column sum and sum of squares of the product (BN statistics)
 void launch_pw_gemm(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc,
-                    long long M, int I, int J, int beta, cudaStream_t s, double* sums = nullptr, InTf tf = InTf());
+                    long long M, int I, int J, int beta, cudaStream_t s, double* sums = nullptr, InTf tf = InTf(),
+                    PwDual du = PwDual());
 void launch_pw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I, int J,
                      cudaStream_t s, InTf tf = InTf());
 void launch_dw_conv(const float* X, int ldx, const float* W, float* Y, int ldy, int N, int H, int Wd, int C, int k,

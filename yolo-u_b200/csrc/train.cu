@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -163,7 +164,7 @@ InTf tf_of(const Ctx& c, const ConvBN* src) {
 // y == nullptr: "lazy" unit -- only z and the batch statistics are produced; the consumer passes this unit as `src` and
 // applies BN + activation while loading (saves writing and re-reading the normalised tensor).
 void convbn_fwd(Ctx& c, ConvBN& u, const float* x, int ldx, int N, int H, int W, float* y, int ldy, const float* res,
-                int ldr, const ConvBN* src = nullptr) {
+                int ldr, const ConvBN* src = nullptr, const Lin* rider = nullptr, float* rider_out = nullptr) {
   const long long M = (long long)N * H * W;
   u.x = src ? src->z : x; u.ldx = src ? src->Cout : ldx; u.N = N; u.H = H; u.W = W; u.src = src;
   u.z = c.alloc((size_t)M * u.Cout);
@@ -179,8 +180,14 @@ void convbn_fwd(Ctx& c, ConvBN& u, const float* x, int ldx, int N, int H, int W,
     stats_done = launch_dw_fwd_stats(u.x, u.ldx, c.P + u.w, u.z, u.Cout, sums, N, H, W, u.Cout, u.k, c.s, tf);   // conv + BN statistics
     if (!stats_done) launch_dw_conv(u.x, u.ldx, c.P + u.w, u.z, u.Cout, N, H, W, u.Cout, u.k, 0, 0, c.s);
   } else {
-    launch_pw_gemm(u.x, u.ldx, c.P + u.w, u.Cin, 0, nullptr, u.z, u.Cout, M, u.Cin, u.Cout, 0, c.s, sums, tf);     // conv + BN statistics
+    PwDual du;
+    if (rider) {     // a biased 1x1 conv on the same input (DoubleLightConv.residual_conv) rides in the same GEMM
+      du.Jsplit = u.Cout; du.Wb = c.P + rider->w; du.ldwb = rider->Cin; du.biasb = c.P + rider->b; du.Cb = rider_out; du.ldcb = rider->Cout;
+    }
+    launch_pw_gemm(u.x, u.ldx, c.P + u.w, u.Cin, 0, nullptr, u.z, u.Cout, M, u.Cin, u.Cout + (rider ? rider->Cout : 0), 0, c.s, sums,
+                   tf, du);                                                                                         // conv + BN statistics
     stats_done = true;
+    if (rider) c.acct((double)M * rider->Cout);
   }
   if (!stats_done) { launch_col_reduce(0, u.z, u.Cout, nullptr, 0, bn, 0, sums, u.Cout, 1, M, c.s); c.launches += 1; }
   launch_bn_finalize(sums, u.Cout, M, kBnEps, c.momentum, u.mean, u.invstd, c.S ? c.S + u.rm : nullptr,
@@ -195,7 +202,8 @@ void convbn_fwd(Ctx& c, ConvBN& u, const float* x, int ldx, int N, int H, int W,
 }
 
 // dy -> parameter gradients (+ input gradient into dx[:, :dx_ch], accumulated when beta)
-void convbn_bwd(Ctx& c, ConvBN& u, const float* dy, int ldd, float* dx, int lddx, int beta, int dx_ch) {
+void convbn_bwd(Ctx& c, ConvBN& u, const float* dy, int ldd, float* dx, int lddx, int beta, int dx_ch,
+                const Lin* rider = nullptr, const float* rider_dy = nullptr, int rider_ldd = 0) {
   const long long M = (long long)u.N * u.H * u.W;
   double* sums = c.sums(2 * (size_t)u.Cout);
   if (c.dry) return;
@@ -207,7 +215,12 @@ void convbn_bwd(Ctx& c, ConvBN& u, const float* dy, int ldd, float* dx, int lddx
     if (dx) launch_dw_conv(c.dz, u.Cout, c.P + u.w, dx, lddx, u.N, u.H, u.W, u.Cout, u.k, 1, beta, c.s);
   } else {
     launch_pw_wgrad(c.dz, u.Cout, u.x, u.ldx, c.G + u.w, u.Cin, M, u.Cin, u.Cout, c.s, tf_of(c, u.src));
-    if (dx) launch_pw_gemm(c.dz, u.Cout, c.P + u.w, u.Cin, 1, nullptr, dx, lddx, M, u.Cout, dx_ch, beta, c.s);
+    if (dx) {
+      PwDual du;
+      if (rider) { du.A2 = rider_dy; du.lda2 = rider_ldd; du.W2 = c.P + rider->w; du.ldw2 = rider->Cin; du.I2 = rider->Cout; }
+      launch_pw_gemm(c.dz, u.Cout, c.P + u.w, u.Cin, 1, nullptr, dx, lddx, M, u.Cout, dx_ch, beta, c.s, nullptr, InTf(), du);
+      if (rider) c.acct((double)M * rider->Cout);
+    }
   }
   c.launches += dx ? 4 : 3;
   // reduce (dy, z), apply (dy, z -> dz), wgrad (dz, x), dgrad (dz -> dx [+ dx])
@@ -277,16 +290,22 @@ void dlc_fwd(Ctx& c, Dlc& d, const float* xl, int ldx, int N, int h, int w, floa
   const long long M = (long long)N * H * W;
   d.u = c.alloc((size_t)M * d.Cin);
   float* r = c.alloc((size_t)M * d.C);
+  const bool lazy = dw_tiled_shape(H, W, 3);
+  static const bool no_dual = getenv("YSP_TRAIN_NO_DUAL") != nullptr;      // A/B switch: the two GEMM fusions off
+  const bool ride = lazy && d.C % 4 == 0 && !no_dual;      // the two-output GEMM splits its columns in groups of four
   if (!c.dry) {
     launch_up2(xl, ldx, d.u, d.Cin, N, h, w, d.Cin, c.s);
-    launch_pw_gemm(d.u, d.Cin, c.P + d.r.w, d.Cin, 0, c.P + d.r.b, r, d.C, M, d.Cin, d.C, 0, c.s);   // residual_conv
-    c.launches += 2;
-    c.acct((double)M * (d.Cin * 0.25 + d.Cin + d.Cin + d.C));
+    c.launches += 1;
+    c.acct((double)M * (d.Cin * 0.25 + d.Cin));
+    if (!ride) {
+      launch_pw_gemm(d.u, d.Cin, c.P + d.r.w, d.Cin, 0, c.P + d.r.b, r, d.C, M, d.Cin, d.C, 0, c.s);   // residual_conv
+      c.launches += 1;
+      c.acct((double)M * (d.Cin + d.C));
+    }
   }
   // the three inner normalised tensors are never written: each consumer applies its producer's BN (+SiLU) on load
-  const bool lazy = dw_tiled_shape(H, W, 3);
   if (lazy) {
-    convbn_fwd(c, d.p, d.u, d.Cin, N, H, W, nullptr, 0, nullptr, 0);
+    convbn_fwd(c, d.p, d.u, d.Cin, N, H, W, nullptr, 0, nullptr, 0, nullptr, ride ? &d.r : nullptr, r);      // conv.0.conv1 and residual_conv: one GEMM
     convbn_fwd(c, d.q, nullptr, 0, N, H, W, nullptr, 0, nullptr, 0, &d.p);
     convbn_fwd(c, d.p2, nullptr, 0, N, H, W, nullptr, 0, nullptr, 0, &d.q);
     convbn_fwd(c, d.q2, nullptr, 0, N, H, W, out, ldo, r, d.C, &d.p2);                               // out = conv(x) + residual
@@ -311,16 +330,22 @@ void dlc_bwd(Ctx& c, Dlc& d, const float* dout, int ldd, float* dxl, int lddx) {
   convbn_bwd(c, d.q2, dout, ldd, d1, d.C, 0, d.C);
   convbn_bwd(c, d.p2, d1, d.C, d2, d.C, 0, d.C);
   convbn_bwd(c, d.q, d2, d.C, d1, d.C, 0, d.C);
-  convbn_bwd(c, d.p, d1, d.C, dU, d.Cin, 0, d.Cin);
+  // dU = dz_p * W_p + dout * W_r: both input-gradient GEMMs of the upsampled tensor as one two-operand GEMM
+  static const bool no_dual = getenv("YSP_TRAIN_NO_DUAL") != nullptr;
+  convbn_bwd(c, d.p, d1, d.C, dU, d.Cin, 0, d.Cin, no_dual ? nullptr : &d.r, dout, ldd);
   if (c.dry) return;
   BnRef none = {};
   launch_col_reduce(2, dout, ldd, nullptr, 0, none, 0, bs, d.C, 1, M, c.s);
   launch_add_sums(bs, c.G + d.r.b, d.C, 1, c.s);
   launch_pw_wgrad(dout, ldd, d.u, d.Cin, c.G + d.r.w, d.Cin, M, d.Cin, d.C, c.s);
-  launch_pw_gemm(dout, ldd, c.P + d.r.w, d.Cin, 1, nullptr, dU, d.Cin, M, d.C, d.Cin, 1, c.s);
+  if (no_dual) {
+    launch_pw_gemm(dout, ldd, c.P + d.r.w, d.Cin, 1, nullptr, dU, d.Cin, M, d.C, d.Cin, 1, c.s);
+    c.launches += 1;
+    c.acct((double)M * (d.C + 2 * d.Cin));
+  }
   launch_up2_bwd(dU, d.Cin, dxl, lddx, N, H / 2, W / 2, d.Cin, c.s);
-  c.launches += 5;
-  c.acct((double)M * (d.C + (d.C + d.Cin) + (d.C + 2 * d.Cin) + d.Cin * 1.25));
+  c.launches += 4;
+  c.acct((double)M * (d.C + (d.C + d.Cin) + d.Cin * 1.25));
 }
 
 // ---- whole step -----------------------------------------------------------------------------------------------------------
