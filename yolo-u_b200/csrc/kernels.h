@@ -92,6 +92,7 @@ struct DlcTcP {
   const uint8_t* wpack;     // dlc_tc_prepare_kernel output
   const float* bo;          // head bias (device) or NULL
   int N, h, w, Cin, C, x_cs, out_cs;
+  int probe = 0;            // YSP_DLC_PROBE timing experiments (0 in production)
 };
 struct DlcTcPrep {          // fp32 folded weights in the engine's layouts ([K][ld] dense, [9][C] depthwise)
   const float *w1, *c1, *dw1, *b1, *w2, *c2, *dw2, *b3, *wr, *cr, *wo;

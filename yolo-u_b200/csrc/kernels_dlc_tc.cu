@@ -18,6 +18,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       const int li = bi + 1, lj = bj + 1;
       const int gi = py0 + li, gj = px0 + lj;
       uint4 o00, o01, o10, o11;
-      if (gi >= 0 && gi < p.h && gj >= 0 && gj < p.w) {
+      if (gi >= 0 && gi < p.h && gj >= 0 && gj < p.w && !(p.probe & 4)) {
         const uint8_t* c = sX + ((li * XC + lj) * CIN + kc * 8) * 2;
         constexpr int RS = XC * CIN * 2, PS = CIN * 2;
         const uint4 m0 = *reinterpret_cast<const uint4*>(c - RS - PS), m1 = *reinterpret_cast<const uint4*>(c - RS), m2 = *reinterpret_cast<const uint4*>(c - RS + PS);
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       const uint32_t r_lo = ((s32(sWr) & 0x3FFFF) >> 4) + (((uint32_t)(C * 16) >> 4) << 16);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
+        if ((p.probe & 1) && tap % 3) continue;        // timing probe (wrong results): one MMA per chain only
 #pragma unroll
         for (int ks = 0; ks < CIN / 16; ++ks)
           umma2(tmem + (3 * h + tap / 3) * C, a_lo + (((2 * ks) * PLANE) >> 4) + (tap / 3) * AP + (tap % 3), a_hi,
@@ -250,8 +252,8 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       for (int j = 0; j < 8; ++j) {
         const float s0 = __uint_as_float(v[2 * j]) + __uint_as_float(v1[2 * j]) + __uint_as_float(v2[2 * j]);
         const float s1 = __uint_as_float(v[2 * j + 1]) + __uint_as_float(v1[2 * j + 1]) + __uint_as_float(v2[2 * j + 1]);
-        const float f0 = inside ? silu_th(s0 + be[c0 + 2 * j]) : 0.f;
-        const float f1 = inside ? silu_th(s1 + be[c0 + 2 * j + 1]) : 0.f;
+        const float f0 = inside ? ((p.probe & 8) ? s0 : silu_th(s0 + be[c0 + 2 * j])) : 0.f;
+        const float f1 = inside ? ((p.probe & 8) ? s1 : silu_th(s1 + be[c0 + 2 * j + 1])) : 0.f;
         __nv_bfloat162 hv = __floats2bfloat162_rn(f0, f1);
         w[j] = *reinterpret_cast<uint32_t*>(&hv);
       }
@@ -273,6 +275,7 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       const uint32_t w_lo = ((s32(sW2) & 0x3FFFF) >> 4) + (((uint32_t)(C * 16) >> 4) << 16);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
+        if ((p.probe & 2) && tap % 3) continue;
 #pragma unroll
         for (int ks = 0; ks < C / 16; ++ks)
           umma2(tmem + (3 * h + tap / 3) * C, a_lo + (((2 * ks) * PLANE) >> 4) + (tap / 3) * AP + (tap % 3), a_hi,
@@ -400,7 +403,12 @@ static void dlc_tc_launch(const DlcTcP& p, cudaStream_t s) {
   launch_pdl(dlc_tc_kernel<CIN, C, HEAD>, dim3(tiles < ctas ? tiles : ctas), dim3(kDlcThreads), smem, s, p);
 }
 
-void launch_dlc_tc(const DlcTcP& p, cudaStream_t s) {
+void launch_dlc_tc(const DlcTcP& p0, cudaStream_t s) {
+  // YSP_DLC_PROBE (timing experiments only, results are wrong): 1 = conv1 issues 3 of its 9 taps, 2 = same for conv2,
+  // 4 = no up2 arithmetic in phase 1, 8 = no SiLU in epilogue 1
+  static const int probe = getenv("YSP_DLC_PROBE") ? atoi(getenv("YSP_DLC_PROBE")) : 0;
+  DlcTcP p = p0;
+  p.probe = probe;
   if (p.Cin == 32 && p.C == 16) dlc_tc_launch<32, 16, true>(p, s);
   else dlc_tc_launch<64, 32, false>(p, s);
 }
