@@ -29,7 +29,10 @@ namespace {
 constexpr int TH = 14, TW = 30;            // output tile (hi-res pixels)
 constexpr int AR = 18, AP = 34;            // u tile: rows, pitch (pixels); b tile uses the same pitch and 18 rows
 constexpr int XR = 11, XC = 19;            // low-res x tile incl. halo
-constexpr int PLANE = AR * AP * 16;        // bytes of one 8-channel plane of the u / b tile
+// Bytes of one 8-channel plane of the u / b tile (= the descriptors' LBO).  With 8 planes (CIN = 64) the pitch is padded by
+// 16 B so that the 8 lanes of a quarter-warp, which write the 8 planes of one pixel in phase 1, hit 8 different 16-byte
+// bank groups (unpadded: 9792 = 64 mod 128 -> 4-way conflicts; ncu r6: 22.6 M store wavefronts for 5.6 M ideal).
+__host__ __device__ constexpr int plane_bytes(int cin) { return AR * AP * 16 + (cin == 64 ? 16 : 0); }
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -87,6 +90,7 @@ constexpr int kDlcThreads = 320;            // warps 0-7: CUDA-core phases + epi
 template <int CIN, int C, bool HEAD>
 __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(DlcTcP p) {
   constexpr int KP1 = CIN / 8, KP2 = C / 8;          // 8-channel planes of u and of b
+  constexpr int PLANE = plane_bytes(CIN);
   constexpr int W1B = 9 * KP1 * C * 16, W2B = 9 * KP2 * C * 16, WRB = KP1 * C * 16;
   extern __shared__ __align__(128) uint8_t dsm[];
   uint8_t* sU = dsm;                                 // [KP1][AR][AP] x 16 B
@@ -153,24 +157,12 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  prefetch_x(blockIdx.x);
-  // persistent CTA: weights, TMEM and the barrier are set up once; tiles are strided over the grid
-  uint32_t tpar = 0;                                                   // mbarrier phase parity: every barrier completes once per tile
-#pragma unroll 1
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-  int t = tile;
-  const int tx = t % tiles_x; t /= tiles_x;
-  const int ty = t % tiles_y;
-  const int n = t / tiles_y;
-  const int X0 = tx * TW, Y0 = ty * TH;
-  const int px0 = X0 / 2 - 2, py0 = Y0 / 2 - 2;
-  // ---- low-res x tile (edge clamped = torch's index clamping for align_corners=False): prefetched with cp.async
-  //      during the previous tile's MMA / epilogue phases (sX is only read in phase 1) ----
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-
-  // ---- phase 1: u = up2(x) on the 18 x 34 tile, one thread per (2x2 hi-res block, 8 channels); zero outside the image ----
-  {
+  // phase 1 of a tile: u = up2(x) on the 18 x 34 tile, one thread per (2x2 hi-res block, 8 channels); zero outside the image
+  auto build_u = [&](int tl) {
+    int t = tl;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int px0 = tx * TW / 2 - 2, py0 = ty * TH / 2 - 2;
     const __nv_bfloat162 q25 = __floats2bfloat162_rn(0.25f, 0.25f), q75 = __floats2bfloat162_rn(0.75f, 0.75f);
 #pragma unroll 2
     for (int i = tid; i < (AR / 2) * (AP / 2) * KP1; i += kDlcThreads) {
@@ -193,13 +185,37 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
         o00 = o01 = o10 = o11 = make_uint4(0u, 0u, 0u, 0u);
       }
       uint8_t* d = sU + kc * PLANE + ((2 * bi) * AP + 2 * bj) * 16;
-      *reinterpret_cast<uint4*>(d) = o00; *reinterpret_cast<uint4*>(d + 16) = o01;
-      *reinterpret_cast<uint4*>(d + AP * 16) = o10; *reinterpret_cast<uint4*>(d + AP * 16 + 16) = o11;
+      if (KP1 == 4) {
+        // 4 planes: a quarter-warp is (4 planes) x (2 blocks) = bank groups {0,4} + {0,2}.  Planes 2,3 store the right
+        // pixel first, which adds the odd groups: 8 lanes -> 8 distinct groups (was a 2-way conflict).
+        const bool sw = (kc & 2) != 0;
+        const int o = sw ? 16 : 0;
+        *reinterpret_cast<uint4*>(d + o) = sw ? o01 : o00; *reinterpret_cast<uint4*>(d + 16 - o) = sw ? o00 : o01;
+        *reinterpret_cast<uint4*>(d + AP * 16 + o) = sw ? o11 : o10; *reinterpret_cast<uint4*>(d + AP * 16 + 16 - o) = sw ? o10 : o11;
+      } else {
+        *reinterpret_cast<uint4*>(d) = o00; *reinterpret_cast<uint4*>(d + 16) = o01;
+        *reinterpret_cast<uint4*>(d + AP * 16) = o10; *reinterpret_cast<uint4*>(d + AP * 16 + 16) = o11;
+      }
     }
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the tensor core
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the tensor core
+  };
+  // Software pipeline over the CTA's tiles: the u tile of tile i+1 is built while the conv2 MMAs of tile i run (sU is
+  // only read by conv1 + residual, all complete by then; sX holds x(i+1), prefetched during tile i's first half).
+  prefetch_x(blockIdx.x);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  prefetch_x(tile + gridDim.x);                                      // sX is free until the next tile's phase 1
+  if ((int)blockIdx.x < total_tiles) build_u(blockIdx.x);
+  __syncthreads();
+  prefetch_x(blockIdx.x + gridDim.x);
+  // persistent CTA: weights, TMEM and the barrier are set up once; tiles are strided over the grid
+  uint32_t tpar = 0;                                                   // mbarrier phase parity: every barrier completes once per tile
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  int t = tile;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int n = t / tiles_y;
+  const int X0 = tx * TW, Y0 = ty * TH;
 
   // ---- phase 2: conv1 (D1[h][r], h = 8-pixel column block of the 16 x 32 b region) and the residual 1x1 (Dr[h]),
   //      issued block by block by warp 8 with one commit per block, so the epilogue of block h (warps 0-7 below)
@@ -248,12 +264,15 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       ld16(tmem + ((uint32_t)(q * 32) << 16) + (3 * h + 2) * C + c0, v2);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       uint32_t w[8];
+      float bb[16];                                   // 16-byte shared loads (the scalar form was 16 LDS per thread)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(&bb[4 * j]) = *reinterpret_cast<const float4*>(be + c0 + 4 * j);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float s0 = __uint_as_float(v[2 * j]) + __uint_as_float(v1[2 * j]) + __uint_as_float(v2[2 * j]);
         const float s1 = __uint_as_float(v[2 * j + 1]) + __uint_as_float(v1[2 * j + 1]) + __uint_as_float(v2[2 * j + 1]);
-        const float f0 = inside ? ((p.probe & 8) ? s0 : silu_th(s0 + be[c0 + 2 * j])) : 0.f;
-        const float f1 = inside ? ((p.probe & 8) ? s1 : silu_th(s1 + be[c0 + 2 * j + 1])) : 0.f;
+        const float f0 = inside ? ((p.probe & 8) ? s0 : silu_th(s0 + bb[2 * j])) : 0.f;
+        const float f1 = inside ? ((p.probe & 8) ? s1 : silu_th(s1 + bb[2 * j + 1])) : 0.f;
         __nv_bfloat162 hv = __floats2bfloat162_rn(f0, f1);
         w[j] = *reinterpret_cast<uint32_t*>(&hv);
       }
@@ -262,6 +281,7 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       *reinterpret_cast<uint4*>(d + PLANE) = make_uint4(w[4], w[5], w[6], w[7]);
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");             // x(i+1) has landed (this thread's copies; the barrier publishes them)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -284,6 +304,9 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar2[h])) : "memory");
     }
   }
+
+  // ---- phase 1 of the NEXT tile, in the shadow of the conv2 MMAs ----
+  if (tile + (int)gridDim.x < total_tiles) build_u(tile + gridDim.x);
 
   // ---- phase 5: epilogue 2: out = SiLU(D2 + bias_eff2) + Dr + cr;  head: logit = wo . out + bo ----
   const int oy = by, oxl = bxl;
@@ -308,11 +331,22 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       float f[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        f[j] = silu_th(__uint_as_float(v[j]) + __uint_as_float(v1[j]) + __uint_as_float(v2[j]) + be[c0 + j]) + __uint_as_float(rsd[j]) + sCr[c0 + j];
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(be + c0 + 4 * j4), c4 = *reinterpret_cast<const float4*>(sCr + c0 + 4 * j4);
+        const float bq[4] = {b4.x, b4.y, b4.z, b4.w}, cq[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = 4 * j4 + jj;
+          f[j] = silu_th(__uint_as_float(v[j]) + __uint_as_float(v1[j]) + __uint_as_float(v2[j]) + bq[jj]) + __uint_as_float(rsd[j]) + cq[jj];
+        }
+      }
       if (HEAD) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) part = fmaf(f[j], sWo[c0 + j], part);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(sWo + c0 + 4 * j4);
+          part = fmaf(f[4 * j4], w4.x, part); part = fmaf(f[4 * j4 + 1], w4.y, part);
+          part = fmaf(f[4 * j4 + 2], w4.z, part); part = fmaf(f[4 * j4 + 3], w4.w, part);
+        }
       } else if (valid) {
         uint32_t w[8];
 #pragma unroll
@@ -331,6 +365,7 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  prefetch_x(tile + 2 * gridDim.x);                                  // sX is free: every thread is past build_u(i+1)
   tpar ^= 1;
   }  // tile loop
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -391,7 +426,7 @@ bool dlc_tc_supported(int Cin, int C, bool head) {
 
 template <int CIN, int C, bool HEAD>
 static void dlc_tc_launch(const DlcTcP& p, cudaStream_t s) {
-  constexpr size_t smem = (size_t)(CIN / 8 + C / 8) * PLANE + (size_t)XR * XC * CIN * 2 +
+  constexpr size_t smem = (size_t)(CIN / 8 + C / 8) * plane_bytes(CIN) + (size_t)XR * XC * CIN * 2 +
                           (size_t)(9 * (CIN / 8) * C * 8 + 9 * (C / 8) * C * 8 + (CIN / 8) * C * 8) * 2 + (size_t)20 * C * 4 + 128;
   static unsigned long long attr_done = 0;
   ensure_dyn_smem(dlc_tc_kernel<CIN, C, HEAD>, smem, attr_done, "dlc_tc_kernel");
