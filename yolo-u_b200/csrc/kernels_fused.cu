@@ -59,7 +59,7 @@ __device__ __forceinline__ void dw_strip(const float* src, int RW, int SC, const
 // FAST = bf16 "throughput mode": fast SiLU, pointwise conv on mma.sync bf16 tensor-core tiles (b and W2 rounded to
 // bf16, exactly what the unfused bf16 path stores); !FAST = fp32 parity mode: everything in fp32 FFMA.
 template <typename T, int C, int TH, int TW, int S2, int S4, bool FAST>
-__global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
+__global__ void __launch_bounds__(256, (FAST && C < 64) ? 3 : 2) dlc_fused_kernel(DlcP p) {   // C = 64: shared memory allows two CTAs per SM anyway
   constexpr int C4 = C / 4;
   constexpr int PH = TH / 2 + 4, PW = TW / 2 + 4;      // low-res tile incl. halo
   constexpr int AH = TH + 4, AW = TW + 4;              // a: tile + 2
@@ -67,6 +67,9 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
   constexpr int NB = BH * BW;
   constexpr int CS = C + 4;                            // fp32 b: padded pixel stride (conflict-free float4 per-pixel reads)
   constexpr int CSH = C + 8;                           // bf16 b: padded pixel stride (conflict-free mma A-fragment loads)
+  constexpr int CC = (FAST && C == 64) ? C + 8 : C;    // c: pixel stride (padded: the float2 accumulator stores of stage 3 hit
+                                                       // 16 distinct 8-byte slots per half-warp instead of 4; fits inside the a tile)
+  static_assert(BH * BW * CC <= AH * AW * C, "c tile must fit in the a tile");
   static_assert(BH % S2 == 0 && TH % S4 == 0 && S4 % 2 == 0, "strip heights");
   pdl_sync();
   extern __shared__ __align__(16) float sm[];
@@ -78,6 +81,7 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
   constexpr int SB_FLOATS = FAST ? (NB16 * CSH + 1) / 2 : NB * CS;
   float* sW2 = sB + SB_FLOATS;                         // fp32 [C][C] k-major (sW2[k*C+co])  (!FAST only)
   float* sB2 = sW2 + (FAST ? 0 : C * C);               // [C]
+  bf16* sW2h = reinterpret_cast<bf16*>(sB2 + C);       // bf16 [co][CSH]: W2^T for the mma B fragments (FAST only)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = 2 * p.h, W = 2 * p.w;
   const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
@@ -92,6 +96,17 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
   // ---- stage 0: pointwise weights + the low-res P tile (edge-clamped: out-of-range neighbours replicate the border,
   //      which is exactly torch's index clamping for align_corners=False) -> smem ----
   if (!FAST) for (int i = tid; i < C * C; i += 256) sW2[i] = p.w2[(i / C) * p.w2ld + (i % C)];
+  if (FAST) {
+    // W2^T as bf16 pairs (k, k+1): a quarter of a warp covers 8 output channels x 4 k-pairs, so the global loads use
+    // whole 32-byte sectors and the 4-byte shared stores fall into 32 different banks (word = co * (CSH/2) + k/2).
+    // (Before: every thread built its B fragments from 128 scalar global loads -- 18 % of the kernel's instructions.)
+    for (int i = tid; i < C * C / 2; i += 256) {
+      const int rest = i >> 5;
+      const int co = (rest % (C / 8)) * 8 + (i & 7), k = ((rest / (C / 8)) * 4 + ((i >> 3) & 3)) * 2;
+      const __nv_bfloat162 w = __floats2bfloat162_rn(p.w2[(size_t)k * p.w2ld + co], p.w2[(size_t)(k + 1) * p.w2ld + co]);
+      *reinterpret_cast<__nv_bfloat162*>(sW2h + co * CSH + k) = w;
+    }
+  }
   for (int i = tid; i < C; i += 256) sB2[i] = p.b2[i];
   {
     // batches of 4 global loads are issued before their shared-memory stores so the L2 round trips overlap
@@ -191,11 +206,8 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
         for (int nt = 0; nt < NTH; ++nt) {
           const int co = (nh * NTH + nt) * 8 + g;
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int k = ks * 16 + tig * 2 + hh * 8;
-            __nv_bfloat162 w = __floats2bfloat162_rn(p.w2[(size_t)k * p.w2ld + co], p.w2[(size_t)(k + 1) * p.w2ld + co]);
-            bf[ks][nt][hh] = *reinterpret_cast<uint32_t*>(&w);
-          }
+          for (int hh = 0; hh < 2; ++hh)
+            bf[ks][nt][hh] = *reinterpret_cast<const uint32_t*>(sW2h + co * CSH + ks * 16 + tig * 2 + hh * 8);
         }
       for (int mt = warp; mt < NB16 / 16; mt += 8) {
         float d[NTH][4];
@@ -224,7 +236,7 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
             for (int nt = 0; nt < NTH; ++nt) {
               const int co = (nh * NTH + nt) * 8 + tig * 2;
               float2 v = inside ? make_float2(d[nt][hh * 2], d[nt][hh * 2 + 1]) : make_float2(0.f, 0.f);
-              *reinterpret_cast<float2*>(sA + pp * C + co) = v;
+              *reinterpret_cast<float2*>(sA + pp * CC + co) = v;
             }
           }
         }
@@ -256,7 +268,7 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
         }
       }
       const bool inside = Y >= 0 && Y < H && X >= 0 && X < W;
-      float* crow = sA + pp * C + g * 16;
+      float* crow = sA + pp * CC + g * 16;
 #pragma unroll
       for (int j4 = 0; j4 < 4; ++j4)
         *reinterpret_cast<float4*>(crow + j4 * 4) = inside ? make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3])
@@ -281,7 +293,7 @@ __global__ void __launch_bounds__(256, FAST ? 3 : 2) dlc_fused_kernel(DlcP p) {
       const int it = i / C4;
       const int ox = it % TW, oy0 = (it / TW) * S4;
       float4 acc[S4];
-      dw_strip<S4>(sA + (oy0 * BW + ox) * C + c4 * 4, BW, C, wk, bias, acc);
+      dw_strip<S4>(sA + (oy0 * BW + ox) * CC + c4 * 4, BW, CC, wk, bias, acc);
       const int X = X0 + ox;
       // residual: bilinear x2 of P[:, C:].  Column pair + weights are fixed by the parity of X; the strip starts on an
       // even row, so its S4 rows need S4/2 + 2 low-res rows: lerp each once horizontally, then blend vertically.
@@ -320,7 +332,7 @@ static void dlc_launch(const DlcP& p, cudaStream_t s) {
   constexpr int PH = TH / 2 + 4, PW = TW / 2 + 4, AH = TH + 4, AW = TW + 4, BH = TH + 2, BW = TW + 2, CS = C + 4, CSH = C + 8;
   constexpr int NB = BH * BW, NB16 = (NB + 15) / 16 * 16;
   constexpr int SB_FLOATS = FAST ? (NB16 * CSH + 1) / 2 : NB * CS;
-  constexpr size_t smem = sizeof(float) * (PH * PW * 2 * C + AH * AW * C + SB_FLOATS + (FAST ? 0 : C * C) + C);
+  constexpr size_t smem = sizeof(float) * (PH * PW * 2 * C + AH * AW * C + SB_FLOATS + (FAST ? 0 : C * C) + C) + (FAST ? (size_t)C * CSH * 2 : 0);
   static_assert(((TH / S4) * TW * (C / 4)) % 256 == 0, "stage 4 must keep warps converged for the head shuffle");
   static unsigned long long attr_done = 0;
   ensure_dyn_smem(dlc_fused_kernel<T, C, TH, TW, S2, S4, FAST>, smem, attr_done, "dlc_fused_kernel");
