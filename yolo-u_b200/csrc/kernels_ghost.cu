@@ -33,8 +33,8 @@ template <int G>   // G = c/4: 8 (decoder.2) or 12 (decoder.0)
 __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
   constexpr int CA = 4 * G, HC = 2 * G;
   constexpr int PA = CA / 2 + 1;          // words per pixel of the a tile (bf16 pairs; odd pitch spreads the 4-pixel strips over banks)
-  constexpr int PG = G + 1;               // words per pixel of [g1|g2] (2G bf16 = G words)
-  constexpr int PH = G + 1;               // words per pixel of h1 (HC bf16 = G words)
+  constexpr int PG = G + 2;               // words per pixel of [g1|g2] (2G bf16 = G words); even: a thread's 4 channels are
+  constexpr int PH = G + 2;               // one aligned 8-byte access.  Same for h1 (HC bf16 = G words)
   extern __shared__ __align__(16) uint32_t gsm[];
   float* sW1 = reinterpret_cast<float*>(gsm);          // [CA][G]
   float* sW3 = sW1 + CA * G;                           // [2G][HC]
@@ -116,8 +116,8 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
         const int x = X0 - 4 + rx + j;
         const bool in = y >= 0 && y < p.H && x >= 0 && x < p.W;
         uint32_t* o = sG + (pp0 + j) * PG + q * 2;
-        o[0] = in ? pack2(silu_approx(acc[j][0]), silu_approx(acc[j][1])) : 0u;
-        o[1] = in ? pack2(silu_approx(acc[j][2]), silu_approx(acc[j][3])) : 0u;
+        *reinterpret_cast<uint2*>(o) = in ? make_uint2(pack2(silu_approx(acc[j][0]), silu_approx(acc[j][1])), pack2(silu_approx(acc[j][2]), silu_approx(acc[j][3])))
+                                          : make_uint2(0u, 0u);
       }
     }
   }
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
         const uint32_t* gp = sG + ((by + r) * GRA + bx) * PG + q * 2;
         float2 v0[8], v1[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { v0[j] = bf2(gp[j * PG]); v1[j] = bf2(gp[j * PG + 1]); }
+        for (int j = 0; j < 8; ++j) { const uint2 u = *reinterpret_cast<const uint2*>(gp + j * PG); v0[j] = bf2(u.x); v1[j] = bf2(u.y); }
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
           const float4 w = *reinterpret_cast<const float4*>(sD1 + (r * 5 + s) * G + q * 4);
@@ -150,8 +150,7 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint32_t* o = sG + ((by + 2) * GRA + bx + 2 + j) * PG + Q * 2 + q * 2;   // g2 sits behind g1 in the same pixel record
-        o[0] = pack2(silu_approx(acc[j][0]), silu_approx(acc[j][1]));
-        o[1] = pack2(silu_approx(acc[j][2]), silu_approx(acc[j][3]));
+        *reinterpret_cast<uint2*>(o) = make_uint2(pack2(silu_approx(acc[j][0]), silu_approx(acc[j][1])), pack2(silu_approx(acc[j][2]), silu_approx(acc[j][3])));
       }
     }
   }
@@ -185,8 +184,7 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
         const int x = X0 - 2 + bx + j;
         const bool in = y >= 0 && y < p.H && x >= 0 && x < p.W;
         uint32_t* o = sH + (by * GRB + bx + j) * PH + q * 2;
-        o[0] = in ? pack2(acc[j][0], acc[j][1]) : 0u;
-        o[1] = in ? pack2(acc[j][2], acc[j][3]) : 0u;
+        *reinterpret_cast<uint2*>(o) = in ? make_uint2(pack2(acc[j][0], acc[j][1]), pack2(acc[j][2], acc[j][3])) : make_uint2(0u, 0u);
       }
     }
   }
@@ -209,7 +207,7 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
         const uint32_t* hp = sH + ((ty + r) * GRB + tx) * PH + q * 2;
         float2 v0[8], v1[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { v0[j] = bf2(hp[j * PH]); v1[j] = bf2(hp[j * PH + 1]); }
+        for (int j = 0; j < 8; ++j) { const uint2 u = *reinterpret_cast<const uint2*>(hp + j * PH); v0[j] = bf2(u.x); v1[j] = bf2(u.y); }
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
           const float4 w = *reinterpret_cast<const float4*>(sD2 + (r * 5 + s) * HC + q * 4);
@@ -229,7 +227,8 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
         const uint32_t* hc = sH + ((ty + 2) * GRB + tx + j + 2) * PH + q * 2;           // h1 at the output pixel
         const bf16* ag = p.a + ((size_t)(n * p.H + y) * p.W + x) * p.a_cs;              // a at the output pixel (L2-resident)
         const uint2 alo = *reinterpret_cast<const uint2*>(ag + q * 4), ahi = *reinterpret_cast<const uint2*>(ag + HC + q * 4);
-        const float2 h0 = bf2(hc[0]), h1v = bf2(hc[1]);
+        const uint2 hu = *reinterpret_cast<const uint2*>(hc);
+        const float2 h0 = bf2(hu.x), h1v = bf2(hu.y);
         const float2 a0 = bf2(alo.x), a1 = bf2(alo.y);                                  // a[4q .. 4q+3]
         const float2 a2 = bf2(ahi.x), a3 = bf2(ahi.y);                                  // a[HC + 4q ..]
         bf16* op = obase + ((size_t)y * p.W + x) * p.out_cs;
@@ -242,7 +241,7 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
 }
 
 static size_t ghost_smem(int G) {
-  const int CA = 4 * G, HC = 2 * G, PA = CA / 2 + 1, PG = G + 1, PH = G + 1;
+  const int CA = 4 * G, HC = 2 * G, PA = CA / 2 + 1, PG = G + 2, PH = G + 2;
   (void)PH;                                            // the h1 tile aliases the (larger) a tile
   return 4 * ((size_t)GRA * GRA * PA + (size_t)GRA * GRA * PG) +
          4 * ((size_t)CA * G + 2 * G * HC + 25 * G + 25 * HC + 2 * G + 2 * HC);
