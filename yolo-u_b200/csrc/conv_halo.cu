@@ -183,9 +183,14 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(HaloP p) {
           if (!valid) continue;
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(v[j]) + sBias[c0 + j];
-            f[j] = p.act ? h_silu(a) : a;
+          for (int j4 = 0; j4 < 4; ++j4) {           // 16-byte shared loads (sBias sits at a multiple of 16 B, c0 % 16 == 0)
+            const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + 4 * j4);
+            const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const float a = __uint_as_float(v[4 * j4 + jj]) + bq[jj];
+              f[4 * j4 + jj] = p.act ? h_silu(a) : a;
+            }
           }
           if (p.res) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_cs + c0);
