@@ -39,9 +39,11 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const void* __restrict__
   long long t = e / OW2;
   const int oy = (int)(t % OH), n = (int)(t / OH);
   const int ox0 = oxp * 2;
-  float acc[2][16];
+  // accumulators as fp32 pairs: one FFMA2 (sm_100 packed fp32 FMA, scalar x broadcast) does two of the 16 channels --
+  // half the FMA issue slots of this issue-bound kernel, bit-identical to scalar fmaf
+  float2 acc[2][8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) { acc[0][j] = sb[j]; acc[1][j] = sb[j]; }
+  for (int j = 0; j < 8; ++j) { acc[0][j] = make_float2(sb[2 * j], sb[2 * j + 1]); acc[1][j] = acc[0][j]; }
   const size_t HW = (size_t)H * W;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -73,10 +75,9 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const void* __restrict__
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 wv = *reinterpret_cast<const float4*>(wr + j4 * 4);
-          acc[0][j4 * 4 + 0] = fmaf(x0, wv.x, acc[0][j4 * 4 + 0]); acc[0][j4 * 4 + 1] = fmaf(x0, wv.y, acc[0][j4 * 4 + 1]);
-          acc[0][j4 * 4 + 2] = fmaf(x0, wv.z, acc[0][j4 * 4 + 2]); acc[0][j4 * 4 + 3] = fmaf(x0, wv.w, acc[0][j4 * 4 + 3]);
-          acc[1][j4 * 4 + 0] = fmaf(x1, wv.x, acc[1][j4 * 4 + 0]); acc[1][j4 * 4 + 1] = fmaf(x1, wv.y, acc[1][j4 * 4 + 1]);
-          acc[1][j4 * 4 + 2] = fmaf(x1, wv.z, acc[1][j4 * 4 + 2]); acc[1][j4 * 4 + 3] = fmaf(x1, wv.w, acc[1][j4 * 4 + 3]);
+          const float2 wlo = make_float2(wv.x, wv.y), whi = make_float2(wv.z, wv.w);
+          acc[0][j4 * 2] = __ffma2_rn(make_float2(x0, x0), wlo, acc[0][j4 * 2]); acc[0][j4 * 2 + 1] = __ffma2_rn(make_float2(x0, x0), whi, acc[0][j4 * 2 + 1]);
+          acc[1][j4 * 2] = __ffma2_rn(make_float2(x1, x1), wlo, acc[1][j4 * 2]); acc[1][j4 * 2 + 1] = __ffma2_rn(make_float2(x1, x1), whi, acc[1][j4 * 2 + 1]);
         }
       }
   }
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const void* __restrict__
     for (int j4 = 0; j4 < 4; ++j4) {
       F4 v;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v.v[j] = silu_for<T>(acc[q][j4 * 4 + j]);
+      for (int j = 0; j < 2; ++j) { v.v[2 * j] = silu_for<T>(acc[q][j4 * 2 + j].x); v.v[2 * j + 1] = silu_for<T>(acc[q][j4 * 2 + j].y); }
       store4<T>(o + j4 * 4, v);
     }
   }
