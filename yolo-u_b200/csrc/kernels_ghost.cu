@@ -21,6 +21,18 @@ namespace {
 constexpr int GT = 16, GRA = GT + 8, GRB = GT + 4;          // output tile, a/g1 region, g2/h1 region
 
 __device__ __forceinline__ float2 bf2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+// Packed fp32 FMAs (FFMA2, sm_100): two of a thread's four channel accumulators per instruction -- half the FMA issue
+// slots, bit-identical to scalar fmaf.
+__device__ __forceinline__ void fma_s4(float (&a)[4], float x, const float4& w) {          // a += x * w
+  const float2 lo = __ffma2_rn(make_float2(x, x), make_float2(w.x, w.y), make_float2(a[0], a[1]));
+  const float2 hi = __ffma2_rn(make_float2(x, x), make_float2(w.z, w.w), make_float2(a[2], a[3]));
+  a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+}
+__device__ __forceinline__ void fma_v4(float (&a)[4], const float2& v0, const float2& v1, const float4& w) {   // a += [v0|v1] * w
+  const float2 lo = __ffma2_rn(v0, make_float2(w.x, w.y), make_float2(a[0], a[1]));
+  const float2 hi = __ffma2_rn(v1, make_float2(w.z, w.w), make_float2(a[2], a[3]));
+  a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -104,10 +116,8 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
 #pragma unroll
         for (int j = 0; j < SW; ++j) {
           const float2 av = bf2(ap[j * PA + k2]);
-          acc[j][0] = fmaf(av.x, w0.x, acc[j][0]); acc[j][1] = fmaf(av.x, w0.y, acc[j][1]);
-          acc[j][2] = fmaf(av.x, w0.z, acc[j][2]); acc[j][3] = fmaf(av.x, w0.w, acc[j][3]);
-          acc[j][0] = fmaf(av.y, w1.x, acc[j][0]); acc[j][1] = fmaf(av.y, w1.y, acc[j][1]);
-          acc[j][2] = fmaf(av.y, w1.z, acc[j][2]); acc[j][3] = fmaf(av.y, w1.w, acc[j][3]);
+          fma_s4(acc[j], av.x, w0);
+          fma_s4(acc[j], av.y, w1);
         }
       }
       const int y = Y0 - 4 + ry;
@@ -142,8 +152,7 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
           const float4 w = *reinterpret_cast<const float4*>(sD1 + (r * 5 + s) * G + q * 4);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            acc[j][0] = fmaf(v0[j + s].x, w.x, acc[j][0]); acc[j][1] = fmaf(v0[j + s].y, w.y, acc[j][1]);
-            acc[j][2] = fmaf(v1[j + s].x, w.z, acc[j][2]); acc[j][3] = fmaf(v1[j + s].y, w.w, acc[j][3]);
+            fma_v4(acc[j], v0[j + s], v1[j + s], w);
           }
         }
       }
@@ -172,10 +181,8 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 gv = bf2(gp[j * PG + k2]);
-          acc[j][0] = fmaf(gv.x, w0.x, acc[j][0]); acc[j][1] = fmaf(gv.x, w0.y, acc[j][1]);
-          acc[j][2] = fmaf(gv.x, w0.z, acc[j][2]); acc[j][3] = fmaf(gv.x, w0.w, acc[j][3]);
-          acc[j][0] = fmaf(gv.y, w1.x, acc[j][0]); acc[j][1] = fmaf(gv.y, w1.y, acc[j][1]);
-          acc[j][2] = fmaf(gv.y, w1.z, acc[j][2]); acc[j][3] = fmaf(gv.y, w1.w, acc[j][3]);
+          fma_s4(acc[j], gv.x, w0);
+          fma_s4(acc[j], gv.y, w1);
         }
       }
       const int y = Y0 - 2 + by;
@@ -213,8 +220,7 @@ __global__ void __launch_bounds__(256) ghost_fused_kernel(GhostP p) {
           const float4 w = *reinterpret_cast<const float4*>(sD2 + (r * 5 + s) * HC + q * 4);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            acc[j][0] = fmaf(v0[j + s].x, w.x, acc[j][0]); acc[j][1] = fmaf(v0[j + s].y, w.y, acc[j][1]);
-            acc[j][2] = fmaf(v1[j + s].x, w.z, acc[j][2]); acc[j][3] = fmaf(v1[j + s].y, w.w, acc[j][3]);
+            fma_v4(acc[j], v0[j + s], v1[j + s], w);
           }
         }
       }
