@@ -70,6 +70,16 @@ __device__ __forceinline__ float silu_th(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
 }
+// Packed fp32 (FADD2 / FMUL2 / FFMA2, sm_100): the epilogues handle two adjacent channels per instruction; the operation
+// order per channel is the scalar one, so results are bit-identical.
+__device__ __forceinline__ float2 f2(const uint32_t (&r)[16], int i) { return make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])); }
+__device__ __forceinline__ float2 silu_th2(float2 x) {
+  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+  return __ffma2_rn(h, t, h);
+}
 __device__ __forceinline__ __nv_bfloat162 lerp2(__nv_bfloat162 a, __nv_bfloat162 wa, __nv_bfloat162 b, __nv_bfloat162 wb) {
   return __hfma2(a, wa, __hmul2(b, wb));
 }
@@ -269,11 +279,9 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(&bb[4 * j]) = *reinterpret_cast<const float4*>(be + c0 + 4 * j);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float s0 = __uint_as_float(v[2 * j]) + __uint_as_float(v1[2 * j]) + __uint_as_float(v2[2 * j]);
-        const float s1 = __uint_as_float(v[2 * j + 1]) + __uint_as_float(v1[2 * j + 1]) + __uint_as_float(v2[2 * j + 1]);
-        const float f0 = inside ? ((p.probe & 8) ? s0 : silu_th(s0 + bb[2 * j])) : 0.f;
-        const float f1 = inside ? ((p.probe & 8) ? s1 : silu_th(s1 + bb[2 * j + 1])) : 0.f;
-        __nv_bfloat162 hv = __floats2bfloat162_rn(f0, f1);
+        const float2 sm = __fadd2_rn(__fadd2_rn(f2(v, 2 * j), f2(v1, 2 * j)), f2(v2, 2 * j));
+        const float2 ff = (p.probe & 8) ? sm : silu_th2(__fadd2_rn(sm, make_float2(bb[2 * j], bb[2 * j + 1])));
+        __nv_bfloat162 hv = __floats2bfloat162_rn(inside ? ff.x : 0.f, inside ? ff.y : 0.f);
         w[j] = *reinterpret_cast<uint32_t*>(&hv);
       }
       uint8_t* d = sB + (c0 / 8) * PLANE + (by * AP + bx) * 16;
@@ -335,9 +343,11 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
         const float4 b4 = *reinterpret_cast<const float4*>(be + c0 + 4 * j4), c4 = *reinterpret_cast<const float4*>(sCr + c0 + 4 * j4);
         const float bq[4] = {b4.x, b4.y, b4.z, b4.w}, cq[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
+        for (int jj = 0; jj < 4; jj += 2) {
           const int j = 4 * j4 + jj;
-          f[j] = silu_th(__uint_as_float(v[j]) + __uint_as_float(v1[j]) + __uint_as_float(v2[j]) + bq[jj]) + __uint_as_float(rsd[j]) + cq[jj];
+          const float2 sm = __fadd2_rn(__fadd2_rn(__fadd2_rn(f2(v, j), f2(v1, j)), f2(v2, j)), make_float2(bq[jj], bq[jj + 1]));
+          const float2 o2 = __fadd2_rn(__fadd2_rn(silu_th2(sm), f2(rsd, j)), make_float2(cq[jj], cq[jj + 1]));
+          f[j] = o2.x; f[j + 1] = o2.y;
         }
       }
       if (HEAD) {

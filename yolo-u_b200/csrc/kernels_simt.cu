@@ -265,8 +265,10 @@ __global__ void __launch_bounds__(TY * TX) conv_dw_tiled_kernel(DwP p) {
     for (int o = 0; o < 4; ++o)
 #pragma unroll
       for (int s2 = 0; s2 < K; ++s2) {
-        acc[o].x = fmaf(v[o + s2].x, w[s2].x, acc[o].x); acc[o].y = fmaf(v[o + s2].y, w[s2].y, acc[o].y);
-        acc[o].z = fmaf(v[o + s2].z, w[s2].z, acc[o].z); acc[o].w = fmaf(v[o + s2].w, w[s2].w, acc[o].w);
+        // packed fp32 FMAs (FFMA2, sm_100): two channels per instruction, bit-identical to scalar fmaf
+        const float2 lo = __ffma2_rn(make_float2(v[o + s2].x, v[o + s2].y), make_float2(w[s2].x, w[s2].y), make_float2(acc[o].x, acc[o].y));
+        const float2 hi = __ffma2_rn(make_float2(v[o + s2].z, v[o + s2].w), make_float2(w[s2].z, w[s2].w), make_float2(acc[o].z, acc[o].w));
+        acc[o] = make_float4(lo.x, lo.y, hi.x, hi.y);
       }
   }
   const int y = ty0 + ty;
@@ -362,8 +364,7 @@ __global__ void __launch_bounds__(256) conv_dw_row_kernel(DwP p) {
     for (int o = 0; o < 8; ++o)
 #pragma unroll
       for (int s2 = 0; s2 < K; ++s2) {
-        acc[o].x = fmaf(v[o + s2].x, w[s2].x, acc[o].x);
-        acc[o].y = fmaf(v[o + s2].y, w[s2].y, acc[o].y);
+        acc[o] = __ffma2_rn(v[o + s2], w[s2], acc[o]);          // FFMA2: the channel pair in one instruction
       }
   }
   const int y = ty0 + ty;
