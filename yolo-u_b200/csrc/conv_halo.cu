@@ -46,6 +46,11 @@ __device__ __forceinline__ void h_wait(uint64_t* bar, uint32_t parity) {
   asm volatile("{\n\t.reg .pred p;\n\tHW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra HD;\n\tbra HW;\n\tHD:\n\t}"
                ::"r"(hs32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ float h_tanh(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return t;
+}
 __device__ __forceinline__ float h_silu(float x) {
   const float h = 0.5f * x;
   float t;
@@ -187,9 +192,14 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(HaloP p) {
             const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + 4 * j4);
             const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const float a = __uint_as_float(v[4 * j4 + jj]) + bq[jj];
-              f[4 * j4 + jj] = p.act ? h_silu(a) : a;
+            for (int jj = 0; jj < 4; jj += 2) {         // packed fp32 (FADD2 / FMUL2 / FFMA2): two channels per instruction
+              const int j = 4 * j4 + jj;
+              float2 a = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(bq[jj], bq[jj + 1]));
+              if (p.act) {
+                const float2 h = __fmul2_rn(a, make_float2(0.5f, 0.5f));
+                a = __ffma2_rn(h, make_float2(h_tanh(h.x), h_tanh(h.y)), h);
+              }
+              f[j] = a.x; f[j + 1] = a.y;
             }
           }
           if (p.res) {

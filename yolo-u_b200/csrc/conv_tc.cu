@@ -109,6 +109,15 @@ __device__ __forceinline__ float silu_tanh(float x) {
   return fmaf(h, t, h);
 }
 
+// two adjacent channels at once on the packed fp32 pipe (FMUL2 / FFMA2, sm_100); per channel the same operations as silu_tanh
+__device__ __forceinline__ float2 silu_tanh2(float2 x) {
+  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+  return __ffma2_rn(h, t, h);
+}
+
 constexpr int kMaxStages = 8;
 
 constexpr int kTcThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue
@@ -259,9 +268,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cg + 4 * j4);
             const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const float x = __uint_as_float(v[4 * j4 + jj]) + bq[jj];
-              f[4 * j4 + jj] = p.act == ACT_SILU ? silu_tanh(x) : x;
+            for (int jj = 0; jj < 4; jj += 2) {
+              const int j = 4 * j4 + jj;
+              float2 x = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(bq[jj], bq[jj + 1]));
+              if (p.act == ACT_SILU) x = silu_tanh2(x);
+              f[j] = x.x; f[j + 1] = x.y;
             }
           }
           if (p.res) {

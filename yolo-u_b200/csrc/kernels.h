@@ -93,6 +93,7 @@ struct DlcTcP {
   const float* bo;          // head bias (device) or NULL
   int N, h, w, Cin, C, x_cs, out_cs;
   int probe = 0;            // YSP_DLC_PROBE timing experiments (0 in production)
+  unsigned magic_x = 0, magic_y = 0;   // ceil(2^32 / tiles_{x,y}) (0: divisor 1), filled by launch_dlc_tc: exact tile decode by __umulhi
 };
 struct DlcTcPrep {          // fp32 folded weights in the engine's layouts ([K][ld] dense, [9][C] depthwise)
   const float *w1, *c1, *dw1, *b1, *w2, *c2, *dw2, *b3, *wr, *cr, *wo;

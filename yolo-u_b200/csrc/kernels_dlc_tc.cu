@@ -122,6 +122,13 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
   const int H = 2 * p.h, W = 2 * p.w;
   const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
   const int total_tiles = tiles_x * tiles_y * p.N;
+  // tile -> (tx, ty, n) without runtime division (every thread decodes three tiles per iteration)
+  auto decode = [&](int t, int& tx, int& ty, int& n) {
+    const int r = p.magic_x ? (int)__umulhi((unsigned)t, p.magic_x) : t;        // t / tiles_x
+    tx = t - r * tiles_x;
+    n = p.magic_y ? (int)__umulhi((unsigned)r, p.magic_y) : r;                  // r / tiles_y
+    ty = r - n * tiles_y;
+  };
 
   // ---- prologue: constants only (overlaps the previous kernel under PDL) ----
   if (tid == 0) {
@@ -153,10 +160,8 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
   const uint32_t b_hi = (128u >> 4) | (1u << 14);                          // SBO = 8 rows x 16 B
   auto prefetch_x = [&](int tl) {
     if (tl >= total_tiles) return;
-    int t = tl;
-    const int tx = t % tiles_x; t /= tiles_x;
-    const int ty = t % tiles_y;
-    const int n = t / tiles_y;
+    int tx, ty, n;
+    decode(tl, tx, ty, n);
     const int px0 = tx * TW / 2 - 2, py0 = ty * TH / 2 - 2;
     const bf16* xg = reinterpret_cast<const bf16*>(p.x);
     for (int i = tid; i < XR * XC * KP1; i += kDlcThreads) {
@@ -169,9 +174,8 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
   };
   // phase 1 of a tile: u = up2(x) on the 18 x 34 tile, one thread per (2x2 hi-res block, 8 channels); zero outside the image
   auto build_u = [&](int tl) {
-    int t = tl;
-    const int tx = t % tiles_x; t /= tiles_x;
-    const int ty = t % tiles_y;
+    int tx, ty, n_unused;
+    decode(tl, tx, ty, n_unused);
     const int px0 = tx * TW / 2 - 2, py0 = ty * TH / 2 - 2;
     const __nv_bfloat162 q25 = __floats2bfloat162_rn(0.25f, 0.25f), q75 = __floats2bfloat162_rn(0.75f, 0.75f);
 #pragma unroll 2
@@ -221,10 +225,8 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
   uint32_t tpar = 0;                                                   // mbarrier phase parity: every barrier completes once per tile
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-  int t = tile;
-  const int tx = t % tiles_x; t /= tiles_x;
-  const int ty = t % tiles_y;
-  const int n = t / tiles_y;
+  int tx, ty, n;
+  decode(tile, tx, ty, n);
   const int X0 = tx * TW, Y0 = ty * TH;
 
   // ---- phase 2: conv1 (D1[h][r], h = 8-pixel column block of the 16 x 32 b region) and the residual 1x1 (Dr[h]),
@@ -454,6 +456,9 @@ void launch_dlc_tc(const DlcTcP& p0, cudaStream_t s) {
   static const int probe = getenv("YSP_DLC_PROBE") ? atoi(getenv("YSP_DLC_PROBE")) : 0;
   DlcTcP p = p0;
   p.probe = probe;
+  const unsigned txs = (2 * p.w + TW - 1) / TW, tys = (2 * p.h + TH - 1) / TH;
+  p.magic_x = txs > 1 ? (unsigned)((0x100000000ull + txs - 1) / txs) : 0u;
+  p.magic_y = tys > 1 ? (unsigned)((0x100000000ull + tys - 1) / tys) : 0u;
   if (p.Cin == 32 && p.C == 16) dlc_tc_launch<32, 16, true>(p, s);
   else dlc_tc_launch<64, 32, false>(p, s);
 }
