@@ -119,9 +119,16 @@ __global__ void __launch_bounds__(256, 4) pw_gemm_kernel(const float* __restrict
           float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
           const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-          for (int r = 0; r < 4; ++r)
+          for (int r = 0; r < 4; ++r) {      // FFMA2 (sm_100 packed fp32 FMA, scalar a broadcast): 8 instead of 16 issue slots per k
+            if (BN == 16) {                    // (the 64-register BN = 16 variant spills with register pairs: scalar FMAs there)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+              for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+              continue;
+            }
+            const float2 lo = __ffma2_rn(make_float2(av[r], av[r]), make_float2(bv[0], bv[1]), make_float2(acc[r][0], acc[r][1]));
+            const float2 hi = __ffma2_rn(make_float2(av[r], av[r]), make_float2(bv[2], bv[3]), make_float2(acc[r][2], acc[r][3]));
+            acc[r][0] = lo.x; acc[r][1] = lo.y; acc[r][2] = hi.x; acc[r][3] = hi.y;
+          }
         }
         __syncthreads();
       }
@@ -277,9 +284,11 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
       float4 x = *reinterpret_cast<const float4*>(&sX[r][ti * 4]);
       const float dv[4] = {d.x, d.y, d.z, d.w}, xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
+      for (int a = 0; a < 4; ++a) {
+        const float2 lo = __ffma2_rn(make_float2(dv[a], dv[a]), make_float2(xv[0], xv[1]), make_float2(acc[a][0], acc[a][1]));
+        const float2 hi = __ffma2_rn(make_float2(dv[a], dv[a]), make_float2(xv[2], xv[3]), make_float2(acc[a][2], acc[a][3]));
+        acc[a][0] = lo.x; acc[a][1] = lo.y; acc[a][2] = hi.x; acc[a][3] = hi.y;
+      }
     }
   }
   __syncthreads();
@@ -535,8 +544,9 @@ __global__ void __launch_bounds__(256) dw_tiled_kernel(const float* __restrict__
         for (int o = 0; o < 4; ++o)
 #pragma unroll
           for (int s2i = 0; s2i < K; ++s2i) {
-            acc[o].x = fmaf(v[o + s2i].x, w[s2i].x, acc[o].x); acc[o].y = fmaf(v[o + s2i].y, w[s2i].y, acc[o].y);
-            acc[o].z = fmaf(v[o + s2i].z, w[s2i].z, acc[o].z); acc[o].w = fmaf(v[o + s2i].w, w[s2i].w, acc[o].w);
+            const float2 lo = __ffma2_rn(make_float2(v[o + s2i].x, v[o + s2i].y), make_float2(w[s2i].x, w[s2i].y), make_float2(acc[o].x, acc[o].y));
+            const float2 hi = __ffma2_rn(make_float2(v[o + s2i].z, v[o + s2i].w), make_float2(w[s2i].z, w[s2i].w), make_float2(acc[o].z, acc[o].w));
+            acc[o] = make_float4(lo.x, lo.y, hi.x, hi.y);
           }
       }
       if (rowok) {
