@@ -3,6 +3,8 @@ compatibility, sharding, metric aggregation, error behaviour without a GPU).  No
 import ctypes
 import os
 import re
+import shutil
+import subprocess
 
 import pytest
 import torch
@@ -27,6 +29,20 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), f"libysp.so does not export {n}"
     assert set(names) == set(_lib.PROTOTYPES), "ctypes prototypes out of sync with include/ysp.h"
     assert L.ysp_version() >= 100
+
+
+def test_library_sass_is_blackwell_native():
+    """The built library carries the sm_100a instructions the design rests on (B200_PROFILING.md's SASS mnemonics):
+    tcgen05 MMAs (UTCHMMA) fed by TMA (UTMALDG) with TMEM loads (LDTM) in the epilogues, cp.async staging (LDGSTS) for the
+    halo / decoder tiles, and packed fp32 FMAs (FFMA2) in the CUDA-core kernels."""
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", os.path.join(ROOT, "yolo-u_b200", "libysp.so")], capture_output=True, text=True,
+                          check=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic, least in (("UTCHMMA", 100), ("UTMALDG", 4), ("LDTM", 8), ("UTCBAR", 4), ("LDGSTS", 8), ("FFMA2", 100)):
+        assert len(re.findall(r"\b" + mnemonic + r"\b", sass)) >= least, mnemonic
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
