@@ -46,8 +46,11 @@ extern "C" {
 #define YSP_ENOWEIGHT (-4)/* a state_dict tensor the topology needs was never loaded (message names it) */
 
 /* arithmetic / storage mode of the conv path */
-#define YSP_MODE_FP32 0   /* "parity mode": fp32 activations, fp32 FFMA, bit-for-bit deterministic            */
+#define YSP_MODE_FP32 0   /* "CUDA-core parity mode": fp32 activations, fp32 FFMA, bit-for-bit deterministic   */
 #define YSP_MODE_BF16 1   /* "throughput mode": bf16 activations, tcgen05 bf16 MMA with fp32 TMEM accumulators */
+#define YSP_MODE_TC32 2   /* "tensor-core parity mode": fp32 activations; every MMA operand split into fp16 hi + lo and
+                             each product issued as 3 tcgen05 MMAs (hi.hi + lo.hi + hi.lo) with fp32 TMEM accumulators:
+                             fp32-accurate results (1e-3 logit parity) on the tensor cores                             */
 
 typedef struct ysp_handle ysp_handle;
 

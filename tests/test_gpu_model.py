@@ -61,9 +61,13 @@ def test_mask_dice_counts(ysp):
     assert torch.equal(c2[:, 1].cpu(), counts[:, 1].cpu()) and int(c2[:, 0].sum()) == 0
 
 
-def test_segpp_fp32_parity(ysp, models, ref240):
+PARITY_MODES = ["fp32", "tc32"]      # CUDA-core FFMA / tcgen05 with fp16 hi-lo operand splits: both must meet 1e-3
+
+
+@pytest.mark.parametrize("mode", PARITY_MODES)
+def test_segpp_fp32_parity(ysp, models, ref240, mode):
     pred, seg = models
-    m = ysp.YOLOSegPlusPlus(pred, mode="fp32")
+    m = ysp.YOLOSegPlusPlus(pred, mode=mode)
     m.load_state_dict(seg.state_dict())
     out = m(ref240["x"].cuda(), ref240["lg"].cuda())
     assert out.shape == (4, 1, 240, 240) and out.dtype == torch.float32
@@ -83,9 +87,10 @@ def test_segpp_fp32_parity(ysp, models, ref240):
         m(torch.rand(1, 4, 100, 100).cuda(), torch.rand(1, 1, 12, 12).cuda())
 
 
-def test_detector_fp32_parity(ysp, models, ref240):
+@pytest.mark.parametrize("mode", PARITY_MODES)
+def test_detector_fp32_parity(ysp, models, ref240, mode):
     pred, _ = models
-    det = ysp.B200Detector.from_predictor(pred, mode="fp32")
+    det = ysp.B200Detector.from_predictor(pred, mode=mode)
     from oracle.model import pad_to_multiple
     with torch.no_grad():
         y_ref, raws_ref = pred.model(pad_to_multiple(ref240["x"]))
@@ -105,10 +110,11 @@ def test_detector_fp32_parity(ysp, models, ref240):
     assert (raws[0].cpu() - raws_ref[0]).abs().max().item() <= 1e-3
 
 
-def test_pipeline_fp32_parity(ysp, models, ref240):
+@pytest.mark.parametrize("mode", PARITY_MODES)
+def test_pipeline_fp32_parity(ysp, models, ref240, mode):
     from oracle.model import dice_from_counts
     pred, seg = models
-    P = ysp.Predictor.from_modules(pred, seg, mode="fp32")
+    P = ysp.Predictor.from_modules(pred, seg, mode=mode)
     ml, dets, keep, counts = P.predict(ref240["x"].cuda(), ref240["tg"].cuda())
     assert (ml.cpu() - ref240["pipe_out"]).abs().max().item() <= TOL_LOGITS_FP32
     d_ref = dice_from_counts(ref240["counts"])

@@ -8,9 +8,12 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libysp.so")
 
-MODE_FP32, MODE_BF16 = 0, 1
-_MODES = {"fp32": MODE_FP32, "float32": MODE_FP32, "parity": MODE_FP32, "bf16": MODE_BF16, "bfloat16": MODE_BF16,
-          "throughput": MODE_BF16}
+MODE_FP32, MODE_BF16, MODE_TC32 = 0, 1, 2
+# "fp32": fp32 storage, CUDA-core FFMA convs.  "tc32" / "parity": fp32 storage, convs on tcgen05 with fp16 hi/lo operand
+# splits (3 MMAs per product, fp32-accurate: the mode that meets the 1e-3 logit tolerance ON tensor cores).
+# "bf16" / "throughput": bf16 storage, single tcgen05 bf16 MMA.
+_MODES = {"fp32": MODE_FP32, "float32": MODE_FP32, "ffma": MODE_FP32, "tc32": MODE_TC32, "parity": MODE_TC32,
+          "fp16x3": MODE_TC32, "bf16": MODE_BF16, "bfloat16": MODE_BF16, "throughput": MODE_BF16}
 
 vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 

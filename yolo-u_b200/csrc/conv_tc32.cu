@@ -1,0 +1,501 @@
+// conv_tc32.cu -- the PARITY-mode convolution (YSP_MODE_TC32): fp32 activations in HBM, fp32-accurate products on tcgen05.
+//
+// north_star asks for mask logits within 1e-3 of the fp32 reference AND convolutions on the 5th-gen tensor cores.  bf16
+// storage cannot do that (measured 0.16 max-abs on the logits, tools/gpu_debug.py), so this kernel keeps every activation
+// in fp32 and splits each MMA operand x into two fp16 numbers  x = hi + lo  (hi = rn16(x), lo = rn16(x - hi): 22 mantissa
+// bits) and issues THREE kind::f16 MMAs per product with fp32 accumulation in TMEM:
+//     x.w  ~=  xh.wh + xl.wh + xh.wl          (the dropped xl.wl term is 2^-22 relative)
+// The path is memory-bound, so tripling the MMA count is affordable: tensor-pipe use was 13-19 % in bf16 mode.
+//
+//   warp 0      TMA producer: one 4-D tiled load of the fp32 box {Kc, TW, TH, TN} per (tap, Cin chunk), straight from the
+//               NHWC tensor (OOB zero fill = conv padding and decision-D1 padding, element strides = stride 2), into a
+//               swizzled STAGING ring; streams the weight block of the k-iteration with one cp.async.bulk when the layer's
+//               weights do not fit in shared memory
+//   warps 2-5   converters: thread r owns pixel row r of the 128 x Kc tile: reads its fp32 row from the staging slot
+//               (de-swizzling), writes fp16 hi and lo tiles in the canonical K-major NO-SWIZZLE UMMA layout
+//               [8-channel group][row][16 B] (a warp store is 512 contiguous bytes), releases the staging slot
+//   warp 1      MMA issuer: 3 x Kc/16 tcgen05.mma (M = 128, N = N_tile) per k-iteration into a double-buffered TMEM
+//               accumulator; tcgen05.commit frees the operand slot
+//   warps 6-9   epilogue: tcgen05.ld -> + bias (BN folded) -> exact SiLU (expf, as the fp32 CUDA-core path) -> + residual
+//               -> fp32 NHWC store into the consumer's channel slice
+// Weights: packed once per conv by the engine as the exact shared-memory image, per (n-tile, tap, Cin chunk) block
+// [hi|lo][8-channel group][N_tile][8] fp16 (tc32_tiling() is the single source of the block shape).
+// Replaces ultralytics Conv.forward_fuse / nn.Conv2d wherever Cin % 16 == 0 in parity mode.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "kernels.h"
+
+namespace ysp {
+
+namespace {
+
+struct T32Params {
+  int kw, ntaps, stride, pad, kchunks, Kc, cin_pad;
+  int TW, TH, TN, tiles_w, tiles_h, tiles_n, n_tiles_m, n_tiles_n, N_tile, flat;
+  int tw_shift, th_shift; unsigned magic_w, magic_h;
+  int OH, OW, NB, Cout, Cout_st;
+  long long M;
+  const float* bias; const float* res; float* out; const uint8_t* wpack;
+  int res_cs, out_cs, act;
+  float w_unscale;          // the packed weights are scaled by a power of two; acc * w_unscale is exact
+  uint32_t idesc, stg_bytes, op_bytes, b_bytes, slot_bytes;
+  int S1, S2, tmem_cols;
+  int w_resident; uint32_t w_bytes;
+};
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W32_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra W32_DONE;\n\t"
+      "bra W32_LOOP;\n\t"
+      "W32_DONE:\n\t}" ::"r"(s32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(s32(dst)), "l"(tm), "r"(s32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+// K-major NO-SWIZZLE operand descriptor: core matrix = 8 rows x 16 B contiguous; LBO = byte distance between core
+// matrices adjacent in K, SBO = between core matrices adjacent in M/N (same encoding as conv_halo.cu / kernels_dlc_tc.cu)
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
+
+// x = hi + lo with hi = rn16(x), lo = rn16(x - hi); |x| clamped to the fp16 range (never reached by this network)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+constexpr int kMaxS = 8;
+
+}  // namespace
+
+struct Tc32ConvPlan {
+  T32Params p;
+  mutable CUtensorMap tmA;
+  mutable const void* last_in = nullptr;
+  int in_cs, H, W, NB, swizzle, pw, ph;
+  size_t smem;
+  int grid;
+};
+
+constexpr int kT32Threads = 320;   // warp0 TMA, warp1 MMA, warps 2-5 converters, warps 6-9 epilogue
+
+__global__ void __launch_bounds__(kT32Threads, 2)
+conv_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const T32Params p) {
+  extern __shared__ uint8_t smem_raw32[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxS], sfree_bar[kMaxS], opfull_bar[kMaxS], opfree_bar[kMaxS], tfull_bar[2],
+      tempty_bar[2], wfull_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_bias[528];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw32) + 1023) & ~(uintptr_t)1023);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    for (int i = 0; i < p.S1; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&sfree_bar[i], 4); }
+    for (int i = 0; i < p.S2; ++i) { mbar_init(&opfull_bar[i], p.w_resident ? 4 : 5); mbar_init(&opfree_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    mbar_init(&wfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 528; i += kT32Threads) s_bias[i] = i < p.Cout ? p.bias[i] : 0.f;
+  // PDL: everything above and the resident-weight load below touch constants only
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int total_tiles = p.n_tiles_m * p.n_tiles_n;
+  const int kiters = p.ntaps * p.kchunks;
+  uint8_t* const wsm = smem;                                   // resident weights: [n_tile][k-iteration] blocks of b_bytes
+  uint8_t* const stg = smem + p.w_bytes;                       // S1 staging slots (fp32, TMA-swizzled)
+  uint8_t* const ops = stg + (size_t)p.S1 * p.stg_bytes;       // S2 operand slots: [A hi | A lo | (B block when streaming)]
+  if (warp == 0 && lane == 0 && p.w_resident) {
+    mbar_expect_tx(&wfull_bar, p.w_bytes);
+    for (uint32_t o = 0; o < p.w_bytes; o += 16384u)
+      bulk_load(wsm + o, p.wpack + o, (p.w_bytes - o) < 16384u ? (p.w_bytes - o) : 16384u, &wfull_bar);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0, t = 0; uint32_t ph_s = 0, ph_t = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tn_i = tile % p.n_tiles_n, tm = tile / p.n_tiles_n;
+        int cw, ch, cn;
+        if (p.flat) { cw = tm * 128; ch = 0; cn = 0; }
+        else {
+          int ti = tm % p.tiles_w, r = tm / p.tiles_w;
+          int tj = r % p.tiles_h, tk = r / p.tiles_h;
+          cw = ti * p.TW * p.stride - p.pad; ch = tj * p.TH * p.stride - p.pad; cn = tk * p.TN;
+        }
+        int it = 0;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int tr = tap / p.kw, ts = tap - tr * p.kw;
+          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+            mbar_wait(&sfree_bar[s], ph_s ^ 1);
+            mbar_expect_tx(&full_bar[s], 128u * p.Kc * 4u);
+            tma_load_4d(stg + (size_t)s * p.stg_bytes, &tmA, &full_bar[s], kc * p.Kc, cw + ts, ch + tr, cn);
+            if (!p.w_resident) {
+              mbar_wait(&opfree_bar[t], ph_t ^ 1);
+              mbar_expect_tx(&opfull_bar[t], p.b_bytes);
+              bulk_load(ops + (size_t)t * p.slot_bytes + p.op_bytes, p.wpack + (size_t)(tn_i * kiters + it) * p.b_bytes, p.b_bytes,
+                        &opfull_bar[t]);
+            }
+            if (++s == p.S1) { s = 0; ph_s ^= 1; }
+            if (++t == p.S2) { t = 0; ph_t ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int t = 0; uint32_t ph_t = 0; int acc = 0; uint32_t acc_phase = 0;
+      if (p.w_resident) mbar_wait(&wfull_bar, 0);
+      const uint32_t a_kstep = 2u * 2048u;                      // two 8-channel groups of [128 rows][16 B]
+      const uint32_t b_grp = (uint32_t)p.N_tile * 16u;          // one 8-channel group of the weight block
+      const uint32_t b_lo_off = (uint32_t)(p.Kc >> 3) * b_grp;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tn_i = tile % p.n_tiles_n;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.N_tile);
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&opfull_bar[t], ph_t);
+          tc_fence_after();
+          const uint32_t sa = s32(ops + (size_t)t * p.slot_bytes);
+          const uint32_t sal = sa + 128u * p.Kc * 2u;
+          const uint32_t sb = p.w_resident ? s32(wsm + (size_t)(tn_i * kiters + it) * p.b_bytes) : sa + p.op_bytes;
+          const int nk = p.Kc >> 4;
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t ah = desc_nosw(sa + k * a_kstep, 2048u, 128u), al = desc_nosw(sal + k * a_kstep, 2048u, 128u);
+            const uint64_t bh = desc_nosw(sb + 2u * k * b_grp, b_grp, 128u), bl = desc_nosw(sb + b_lo_off + 2u * k * b_grp, b_grp, 128u);
+            umma_f16(d_tmem, ah, bh, p.idesc, (it | k) ? 1u : 0u);
+            umma_f16(d_tmem, al, bh, p.idesc, 1u);
+            umma_f16(d_tmem, ah, bl, p.idesc, 1u);
+          }
+          umma_commit(&opfree_bar[t]);
+          if (++t == p.S2) { t = 0; ph_t ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== converters: fp32 staging row -> fp16 hi / lo operand tiles =====
+    const int r = (warp - 2) * 32 + lane;
+    const uint32_t row_bytes = (uint32_t)p.Kc * 4u;             // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+    const uint32_t xr = ((r * row_bytes) >> 7) & ((row_bytes >> 4) - 1u);
+    const int ngrp = p.Kc >> 3;
+    int s = 0, t = 0; uint32_t ph_s = 0, ph_t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(&full_bar[s], ph_s);
+        mbar_wait(&opfree_bar[t], ph_t ^ 1);
+        tc_fence_after();
+        const uint8_t* src = stg + (size_t)s * p.stg_bytes + (size_t)r * row_bytes;
+        uint8_t* dh = ops + (size_t)t * p.slot_bytes + (size_t)r * 16;
+        uint8_t* dl = dh + 128u * p.Kc * 2u;
+        for (int g = 0; g < ngrp; ++g) {
+          const float4 v0 = *reinterpret_cast<const float4*>(src + (((uint32_t)(2 * g) ^ xr) << 4));
+          const float4 v1 = *reinterpret_cast<const float4*>(src + (((uint32_t)(2 * g + 1) ^ xr) << 4));
+          uint4 h, l;
+          split2(v0.x, v0.y, h.x, l.x); split2(v0.z, v0.w, h.y, l.y);
+          split2(v1.x, v1.y, h.z, l.z); split2(v1.z, v1.w, h.w, l.w);
+          *reinterpret_cast<uint4*>(dh + (size_t)g * 2048) = h;
+          *reinterpret_cast<uint4*>(dl + (size_t)g * 2048) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&sfree_bar[s]); mbar_arrive(&opfull_bar[t]); }
+        if (++s == p.S1) { s = 0; ph_s ^= 1; }
+        if (++t == p.S2) { t = 0; ph_t ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes [32q, 32q+32), q = w & 3 =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tw = row & (p.TW - 1), r2 = row >> p.tw_shift;
+    const int th = r2 & (p.TH - 1), tn = r2 >> p.th_shift;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int tn_i = 0, tm = tile;
+      if (p.n_tiles_n > 1) { tn_i = tile % p.n_tiles_n; tm = tile / p.n_tiles_n; }
+      long long pix; bool valid;
+      if (p.flat) { pix = (long long)tm * 128 + row; valid = pix < p.M; }
+      else {
+        const int r = p.magic_w ? (int)__umulhi((unsigned)tm, p.magic_w) : tm;
+        const int ti = tm - r * p.tiles_w;
+        const int tk = p.magic_h ? (int)__umulhi((unsigned)r, p.magic_h) : r;
+        const int tj = r - tk * p.tiles_h;
+        const int ox = ti * p.TW + tw, oy = tj * p.TH + th, n = tk * p.TN + tn;
+        valid = ox < p.OW && oy < p.OH && n < p.NB;
+        pix = ((long long)n * p.OH + oy) * p.OW + ox;
+      }
+      const int n_base = tn_i * p.N_tile;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.N_tile);
+      for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int cg = n_base + c0;
+        if (valid && cg < p.Cout_st) {
+          const int nvalid = p.Cout_st - cg;
+          float f[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cg + 4 * j4);
+            const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              float x = fmaf(__uint_as_float(v[4 * j4 + jj]), p.w_unscale, bq[jj]);
+              if (p.act == ACT_SILU) x = silu_f(x);
+              f[4 * j4 + jj] = x;
+            }
+          }
+          if (p.res) {
+            const float* rp = p.res + (size_t)pix * p.res_cs + cg;
+            if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 r4 = reinterpret_cast<const float4*>(rp)[j];
+                f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (j < nvalid && cg + j < p.Cout) f[j] += rp[j];
+            }
+          }
+          float* op = p.out + (size_t)pix * p.out_cs + cg;
+          if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<float4*>(op)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (j < nvalid) op[j] = f[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn32)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn32 get_encode32() {
+  static EncodeTiledFn32 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && p) fn = (EncodeTiledFn32)p;
+  }
+  return fn;
+}
+static int num_sms32() {
+  static int n = 0;
+  if (!n) { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); if (n <= 0) n = 148; }
+  return n;
+}
+
+Tc32Tiling tc32_tiling(int Cin, int Cout, int taps) {
+  Tc32Tiling t;
+  t.cin_pad = (Cin + 15) / 16 * 16;
+  t.cout_pad = (Cout + 15) / 16 * 16;
+  t.Kc = t.cin_pad % 32 == 0 ? 32 : 16;
+  t.kchunks = t.cin_pad / t.Kc;
+  t.n_tiles_n = (t.cout_pad + 255) / 256;
+  t.N_tile = ((t.cout_pad + t.n_tiles_n - 1) / t.n_tiles_n + 15) / 16 * 16;
+  t.b_bytes = 2u * (uint32_t)t.Kc * (uint32_t)t.N_tile * 2u;
+  t.total_bytes = (size_t)t.n_tiles_n * taps * t.kchunks * t.b_bytes;
+  return t;
+}
+
+bool tc32_conv_supported(const ConvP& p) {
+  if (p.kh != p.kw || (p.kh != 1 && p.kh != 3) || (p.stride != 1 && p.stride != 2)) return false;
+  const int cin_pad = (p.Cin + 15) / 16 * 16;
+  if (p.Cin % 16 != 0 && !(p.in_zpad && p.in_cs >= cin_pad)) return false;   // padded K only over zero-filled channels
+  if (p.in_cs % 4 != 0 || p.out_cs % 4 != 0) return false;
+  if (p.M < 128) return false;
+  return get_encode32() != nullptr;
+}
+
+static bool encode_A32(const Tc32ConvPlan* pl, const void* in) {
+  const T32Params& p = pl->p;
+  cuuint64_t dims[4]; cuuint64_t strides[3]; cuuint32_t box[4]; cuuint32_t es[4];
+  const cuuint64_t px = (cuuint64_t)pl->in_cs * 4;
+  if (p.flat) {
+    dims[0] = p.cin_pad; dims[1] = (cuuint64_t)p.M; dims[2] = 1; dims[3] = 1;
+    strides[0] = px; strides[1] = px * (cuuint64_t)p.M; strides[2] = strides[1];
+    box[0] = p.Kc; box[1] = 128; box[2] = 1; box[3] = 1;
+    es[0] = es[1] = es[2] = es[3] = 1;
+  } else {
+    dims[0] = p.cin_pad; dims[1] = pl->W; dims[2] = pl->H; dims[3] = pl->NB;
+    strides[0] = px; strides[1] = px * pl->pw; strides[2] = px * pl->pw * pl->ph;
+    box[0] = p.Kc; box[1] = p.TW * p.stride; box[2] = p.TH * p.stride; box[3] = p.TN;
+    es[0] = 1; es[1] = p.stride; es[2] = p.stride; es[3] = 1;
+  }
+  CUresult r = get_encode32()(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(in), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              pl->swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { fprintf(stderr, "libysp: cuTensorMapEncodeTiled(A, fp32) failed: %d\n", (int)r); return false; }
+  pl->last_in = in;
+  return true;
+}
+
+Tc32ConvPlan* tc32_conv_plan_create(const ConvP& c, const void* wpack, float w_unscale) {
+  Tc32ConvPlan* pl = new Tc32ConvPlan();
+  T32Params& p = pl->p;
+  p = T32Params();
+  const Tc32Tiling tl = tc32_tiling(c.Cin, c.Cout, c.kh * c.kw);
+  p.kw = c.kw; p.ntaps = c.kh * c.kw; p.stride = c.stride; p.pad = c.pad; p.cin_pad = tl.cin_pad;
+  p.Kc = tl.Kc; p.kchunks = tl.kchunks; p.n_tiles_n = tl.n_tiles_n; p.N_tile = tl.N_tile; p.b_bytes = tl.b_bytes;
+  p.OH = c.OH; p.OW = c.OW; p.NB = c.N; p.Cout = c.Cout; p.Cout_st = c.cout_store > c.Cout ? c.cout_store : c.Cout; p.M = c.M;
+  const bool pitched = (c.in_pw && c.in_pw != c.W) || (c.in_ph && c.in_ph != c.H);
+  p.flat = (c.kh == 1 && c.stride == 1 && c.OH == c.H && c.OW == c.W && !pitched) ? 1 : 0;
+  if (p.flat) {
+    p.TW = 128; p.TH = 1; p.TN = 1; p.tiles_w = p.tiles_h = p.tiles_n = 1;
+    p.n_tiles_m = (int)((c.M + 127) / 128);
+  } else {
+    double best = 1e30; int bw = 8, bh = 16, bn = 1;       // the 128-pixel output tile (powers of two) wasting the fewest pixels
+    for (int tw = 128; tw >= 1; tw >>= 1) {
+      if (tw < 8 && c.OW >= 8) continue;
+      if (tw * c.stride > 256) continue;
+      for (int th = 128 / tw; th >= 1; th >>= 1) {
+        int tn = 128 / (tw * th);
+        if (th * c.stride > 256 || tn > 256) continue;
+        double cover = (double)((c.OW + tw - 1) / tw * tw) * ((c.OH + th - 1) / th * th) * ((c.N + tn - 1) / tn * tn);
+        double cost = cover * (1.0 + 0.01 * tn);
+        if (cost < best) { best = cost; bw = tw; bh = th; bn = tn; }
+      }
+    }
+    p.TW = bw; p.TH = bh; p.TN = bn;
+    p.tiles_w = (c.OW + bw - 1) / bw; p.tiles_h = (c.OH + bh - 1) / bh; p.tiles_n = (c.N + bn - 1) / bn;
+    p.n_tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  }
+  p.tw_shift = 0; while ((1 << p.tw_shift) < p.TW) ++p.tw_shift;
+  p.th_shift = 0; while ((1 << p.th_shift) < p.TH) ++p.th_shift;
+  p.magic_w = p.tiles_w > 1 ? (unsigned)((0x100000000ull + p.tiles_w - 1) / p.tiles_w) : 0u;
+  p.magic_h = p.tiles_h > 1 ? (unsigned)((0x100000000ull + p.tiles_h - 1) / p.tiles_h) : 0u;
+  pl->swizzle = p.Kc * 4;
+  p.stg_bytes = 128u * p.Kc * 4u;                    // 16 KB / 8 KB: multiples of the 1024-byte swizzle atom
+  p.op_bytes = 2u * 128u * p.Kc * 2u;                // hi + lo operand tiles
+  int cols = 32;
+  while (cols < 2 * p.N_tile) cols <<= 1;
+  p.tmem_cols = cols;
+  p.w_resident = tl.total_bytes <= 80u * 1024u ? 1 : 0;
+  p.w_bytes = p.w_resident ? (uint32_t)tl.total_bytes : 0u;
+  p.slot_bytes = p.op_bytes + (p.w_resident ? 0u : p.b_bytes);
+  // two CTAs per SM (TMEM <= 256 columns, <= ~104 KB each) when 3 staging + 2 operand slots fit next to the weights;
+  // otherwise one CTA with deeper rings
+  uint32_t budget = 104u * 1024u;
+  if (cols > 256 || p.w_bytes + 3u * p.stg_bytes + 2u * p.slot_bytes > budget) budget = 200u * 1024u;
+  uint32_t left = budget - p.w_bytes;
+  int s2 = (int)(left / (p.stg_bytes + p.slot_bytes));      // start balanced, then give the remainder to staging
+  if (s2 > 4) s2 = 4;
+  if (s2 < 1) s2 = 1;
+  int s1 = (int)((left - (uint32_t)s2 * p.slot_bytes) / p.stg_bytes);
+  if (s1 > kMaxS) s1 = kMaxS;
+  if (s1 < 1) s1 = 1;
+  p.S1 = s1; p.S2 = s2;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bit 4), A = B = F16 (format 0), K-major both, N>>3 @17, M>>4 @24
+  p.idesc = (1u << 4) | ((uint32_t)(p.N_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.bias = c.bias; p.res_cs = c.res_cs; p.out_cs = c.out_cs; p.act = c.act;
+  p.wpack = reinterpret_cast<const uint8_t*>(wpack);
+  p.w_unscale = w_unscale;
+  pl->in_cs = c.in_cs; pl->H = c.H; pl->W = c.W; pl->NB = c.N;
+  pl->pw = c.in_pw ? c.in_pw : c.W; pl->ph = c.in_ph ? c.in_ph : c.H;
+  pl->smem = (size_t)p.w_bytes + (size_t)p.S1 * p.stg_bytes + (size_t)p.S2 * p.slot_bytes + 1024;
+  const int total = p.n_tiles_m * p.n_tiles_n;
+  const int ctas_per_sm = (p.tmem_cols <= 256 && pl->smem <= 110 * 1024) ? 2 : 1;
+  pl->grid = total < ctas_per_sm * num_sms32() ? total : ctas_per_sm * num_sms32();
+  if (pl->smem > 224 * 1024) { delete pl; return nullptr; }
+  static unsigned long long attr_done = 0;
+  ensure_dyn_smem(conv_tc32_kernel, 224 * 1024, attr_done, "conv_tc32_kernel");
+  return pl;
+}
+
+void tc32_conv_plan_destroy(Tc32ConvPlan* p) { delete p; }
+
+void launch_conv_tc32(const Tc32ConvPlan* pl, const ConvP& c, cudaStream_t s) {
+  if (pl->last_in != c.in && !encode_A32(pl, c.in)) return;
+  T32Params p = pl->p;
+  p.res = reinterpret_cast<const float*>(c.res); p.out = reinterpret_cast<float*>(c.out);
+  static const bool no_pdl = getenv("YSP_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl->grid); cfg.blockDim = dim3(kT32Threads); cfg.dynamicSmemBytes = pl->smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaLaunchKernelEx(&cfg, conv_tc32_kernel, pl->tmA, p);
+}
+
+}  // namespace ysp

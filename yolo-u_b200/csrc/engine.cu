@@ -5,6 +5,7 @@
 // (batch, H, W).  Activations live in a caller-provided workspace as NHWC views; concatenations are formed by
 // construction (producers write into channel slices of the consumer's buffer), buffers are packed by lifetime so
 // the working set of consecutive layers stays L2-resident.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -42,6 +43,7 @@ struct DevConv {           // packed weights of one conv (BN folded)
   float* bias = nullptr;   // [Cout]
   void* w_tc = nullptr;    // bf16 [Cout_pad][K_pad] K-major (tensor-core path), or NULL
   int Cout = 0, Cin = 0, kh = 0, kw = 0, wld = 0, K = 0, Ktc = 0;
+  float w_unscale = 1.f;   // TC32 pack: weights are stored times a power of two (keeps the fp16 lo parts normal); epilogue undoes it
   bool dw = false;
 };
 
@@ -66,9 +68,10 @@ struct Plan {
   std::vector<BufInfo> bufs;
   std::map<std::string, TRef> named;
   std::vector<TcConvPlan*> tc_plans;
+  std::vector<Tc32ConvPlan*> tc32_plans;
   size_t ws_bytes = 0;
   int launches = 0;
-  ~Plan() { for (auto* t : tc_plans) tc_conv_plan_destroy(t); }
+  ~Plan() { for (auto* t : tc_plans) tc_conv_plan_destroy(t); for (auto* t : tc32_plans) tc32_conv_plan_destroy(t); }
   void* ptr(const RunCtx& c, const TRef& t) const {
     char* base = t.buf >= 0 ? c.ws + bufs[t.buf].off : reinterpret_cast<char*>(c.ext[-1 - t.buf]);
     return base ? base + (size_t)t.co * esize(t.dt) : nullptr;
@@ -96,6 +99,7 @@ struct ysp_handle {
   cudaStream_t aux = nullptr;                // pipeline: seg encoder / NMS run here, concurrently with the detector
   std::string build_err;
   int act_dt() const { return mode == YSP_MODE_BF16 ? DT_BF16 : DT_F32; }
+  bool tc32() const { return mode == YSP_MODE_TC32; }   // fp32 storage, convs on tcgen05 with fp16 hi/lo operand splits
 };
 
 namespace {
@@ -201,6 +205,41 @@ static int pack_conv_cat(ysp_handle* h, const std::string& key, const std::vecto
         }
     CUDA_OK(cudaMalloc(&dc.w_tc, hbf.size() * 2));
     CUDA_OK(cudaMemcpy(dc.w_tc, hbf.data(), hbf.size() * 2, cudaMemcpyHostToDevice));
+  }
+  if (!dc.dw && h->mode == YSP_MODE_TC32) {
+    // parity-mode tensor-core pack (conv_tc32.cu): per (n-tile, tap, Cin chunk) block [hi|lo][8-channel group][N_tile][8] fp16,
+    // w = hi + lo with hi = rn16(w), lo = rn16(w - hi)
+    const Tc32Tiling tl = tc32_tiling(dc.Cin, dc.Cout, taps);
+    dc.Ktc = taps * tl.cin_pad;
+    // Scale by 2^e so that max|w| lands in [2^13, 2^14): hi stays far from the fp16 overflow, and lo = rn16(w - hi) is a
+    // NORMAL fp16 number for every weight above 2^-17 of the largest one (unscaled, lo of a typical 0.05 weight would be
+    // subnormal and carry an absolute error of 2^-25, four times the 2^-22 relative error of the split itself).
+    double wmax = 0.0;
+    for (double v : f.w) wmax = std::max(wmax, std::fabs(v));
+    int e2 = 0;
+    if (wmax > 0.0) { int ex; std::frexp(wmax, &ex); e2 = 14 - ex; }      // wmax = m * 2^ex, m in [0.5, 1)
+    const float wsc = std::ldexp(1.0f, e2);
+    dc.w_unscale = std::ldexp(1.0f, -e2);
+    std::vector<__half> hp(tl.total_bytes / 2, __float2half_rn(0.f));
+    const int ngrp = tl.Kc / 8;
+    for (int tn = 0; tn < tl.n_tiles_n; ++tn)
+      for (int t = 0; t < taps; ++t)
+        for (int kc = 0; kc < tl.kchunks; ++kc) {
+          __half* blk = hp.data() + ((size_t)(tn * taps + t) * tl.kchunks + kc) * (tl.b_bytes / 2);
+          for (int g = 0; g < ngrp; ++g)
+            for (int n = 0; n < tl.N_tile; ++n)
+              for (int j = 0; j < 8; ++j) {
+                const int co = tn * tl.N_tile + n, ci = kc * tl.Kc + g * 8 + j;
+                if (co >= dc.Cout || ci >= dc.Cin) continue;
+                const float v = (float)f.w[((size_t)co * dc.Cin + ci) * taps + t] * wsc;
+                const __half hi = __float2half_rn(v);
+                const __half lo = __float2half_rn(v - __half2float(hi));
+                blk[((size_t)g * tl.N_tile + n) * 8 + j] = hi;
+                blk[((size_t)(ngrp + g) * tl.N_tile + n) * 8 + j] = lo;
+              }
+        }
+    CUDA_OK(cudaMalloc(&dc.w_tc, tl.total_bytes));
+    CUDA_OK(cudaMemcpy(dc.w_tc, hp.data(), tl.total_bytes, cudaMemcpyHostToDevice));
   }
   auto res = h->convs.emplace(key, dc);
   *out = &res.first->second;
@@ -335,15 +374,25 @@ struct Builder {
         if (tcp) pl->tc_plans.push_back(tcp);
       }
     }
-    if ((in.pw || in.ph) && !tcp && !halo) { rc = fail(YSP_EINVAL, "conv %s: pitched input needs the tensor-core path", prefix.c_str()); return; }
+    Tc32ConvPlan* tcp32 = nullptr;
+    if (h->tc32() && dc->w_tc && in_dt == DT_F32 && out_dt == DT_F32 && getenv("YSP_NO_TC") == nullptr) {
+      ConvP q = p; q.K = dc->Ktc;
+      const char* only = getenv("YSP_TC_ONLY");
+      if ((!only || prefix.find(only) != std::string::npos) && tc32_conv_supported(q)) {
+        tcp32 = tc32_conv_plan_create(q, dc->w_tc, dc->w_unscale);
+        if (tcp32) pl->tc32_plans.push_back(tcp32);
+      }
+    }
+    if ((in.pw || in.ph) && !tcp && !halo && !tcp32) { rc = fail(YSP_EINVAL, "conv %s: pitched input needs the tensor-core path", prefix.c_str()); return; }
     emit([=](RunCtx& c) {
       ConvP q = p;
       q.in = pl->ptr(c, in); q.out = pl->ptr(c, out); q.res = has_res ? pl->ptr(c, rres) : nullptr;
       if (halo) launch_conv_halo(q, w_tc, Ktc, c.s);
+      else if (tcp32) launch_conv_tc32(tcp32, q, c.s);
       else if (tcp) launch_conv_tc(tcp, q, c.s);
       else launch_conv_dense(q, in_dt, out_dt, c.s);
     }, {&in, &out, res}, 1,
-    StepInfo{prefix, std::string(halo ? "halo_conv" : tcp ? "tc_conv" : "conv") + std::to_string(k) + "x" + std::to_string(k) + (s == 2 ? "s2" : ""),
+    StepInfo{prefix, std::string(halo ? "halo_conv" : tcp32 ? "tc32_conv" : tcp ? "tc_conv" : "conv") + std::to_string(k) + "x" + std::to_string(k) + (s == 2 ? "s2" : ""),
              tbytes(in) + tbytes(out) + (res ? tbytes(*res) : 0.0) + (double)dc->K * dc->Cout * ((tcp || halo) ? 2 : 4),
              2.0 * p.M * (double)dc->K * dc->Cout, 1});
   }
@@ -420,7 +469,7 @@ struct Builder {
   void bottleneck(const std::string& p, TRef x, TRef out, bool shortcut, int k0, int k1, double e) {
     int c_ = (int)(out.C * e);
     TRef t = alloc(x.N, x.H, x.W, c_);
-    if (dt == DT_BF16 && c_ % 16 != 0) {       // zero-pad the hidden channels to 16 so cv2 is a tensor-core conv too
+    if ((dt == DT_BF16 || h->tc32()) && c_ % 16 != 0) {       // zero-pad the hidden channels to 16 so cv2 is a tensor-core conv too
       t = alloc(x.N, x.H, x.W, c_, -1, (c_ + 15) / 16 * 16);
       t.zpad = true;
     }
@@ -797,9 +846,9 @@ static int build_seg(ysp_handle* h, Plan* plan, int B, int H, int W, bool shared
     auto it = h->host.find("seg.decoder.0.0.cv1.conv.weight");
     if (it != h->host.end() && it->second.shape.size() >= 2 && it->second.shape[1] == 128) use_logits = false;
   }
-  const int c0 = use_logits ? 129 : 128, c0s = use_logits ? (g.dt == DT_F32 ? 132 : 144) : 128;
+  const int c0 = use_logits ? 129 : 128, c0s = use_logits ? ((g.dt == DT_F32 && !h->tc32()) ? 132 : 144) : 128;
   TRef cat0 = g.alloc(B, h8, w8, c0, -1, c0s);  // dec0 input: [skipB 128 | logits 1 | zero pad]
-  cat0.zpad = use_logits && g.dt == DT_BF16;
+  cat0.zpad = use_logits && (g.dt == DT_BF16 || h->tc32());
   TRef skipB = Builder::slice(cat0, 0, 128);    g.c3k2("encoder.4", e3, skipB, false, 0.25, true);   g.name("encoder.4", skipB);
   g.bn_eps = 1e-5;
   plan->split = (int)plan->steps.size();       // everything above is independent of the detector
@@ -947,7 +996,7 @@ int ysp_version(void) { return 100; }
 const char* ysp_last_error(void) { return g_err; }
 
 int ysp_create(ysp_handle** out, int device, int mode) {
-  if (!out || (mode != YSP_MODE_FP32 && mode != YSP_MODE_BF16)) return fail(YSP_EINVAL, "ysp_create: bad arguments");
+  if (!out || (mode != YSP_MODE_FP32 && mode != YSP_MODE_BF16 && mode != YSP_MODE_TC32)) return fail(YSP_EINVAL, "ysp_create: bad arguments");
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) return fail(YSP_ECUDA, "no CUDA device (%s); libysp has no CPU fallback", cudaGetErrorString(e));

@@ -64,6 +64,15 @@ void tc_conv_plan_destroy(TcConvPlan*);
 void launch_conv_tc(const TcConvPlan* plan, const ConvP& p, cudaStream_t s);
 bool tc_conv_supported(const ConvP& p);
 
+// conv_tc32.cu (parity mode: fp32 activations, fp16 hi/lo operand split, 3 tcgen05 MMAs per product)
+struct Tc32Tiling { int cin_pad, cout_pad, Kc, kchunks, n_tiles_n, N_tile; uint32_t b_bytes; size_t total_bytes; };
+Tc32Tiling tc32_tiling(int Cin, int Cout, int taps);   // block shape of the packed weights (engine.cu packs, the kernel reads)
+struct Tc32ConvPlan;
+Tc32ConvPlan* tc32_conv_plan_create(const ConvP& p, const void* wpack, float w_unscale);
+void tc32_conv_plan_destroy(Tc32ConvPlan*);
+void launch_conv_tc32(const Tc32ConvPlan* plan, const ConvP& p, cudaStream_t s);
+bool tc32_conv_supported(const ConvP& p);
+
 // conv_halo.cu (tcgen05, halo tile + shifted descriptor views: small-channel 3x3 stride-1 convs on maps <= 64 wide)
 bool conv_halo_supported(const ConvP& p, int in_dt, int out_dt);
 void launch_conv_halo(const ConvP& p, const void* w_bf16_kmajor, int Ktc, cudaStream_t s);
