@@ -68,6 +68,8 @@ int ysp_load_weight(ysp_handle* h, const char* name, const float* h_data, int nd
 int ysp_finalize(ysp_handle* h, int which);
 /* scratch bytes needed for a batch of B slices of HxW through ysp_pipeline (>= every other entry's need) */
 size_t ysp_workspace_bytes(ysp_handle* h, int B, int H, int W);
+/* same for a caller-chosen max_det (the NMS scratch grows with it); ysp_workspace_bytes() == max_det 300 */
+size_t ysp_pipeline_workspace_bytes(ysp_handle* h, int B, int H, int W, int max_det);
 
 /* -- a1: input normalisation -------------------------------------------------------------------------------------- */
 /* u8 [B,H,W,4] (channel order as stored) -> fp32 NCHW [B,4,H,W] = x/255 (ToTensor).  HBM-bound, 4 B in / 16 B out per pixel. */
@@ -134,6 +136,10 @@ typedef struct ysp_pipeline_io {
   uint8_t* d_mask;           /* u8 [B,H,W] or NULL */
   float conf_thres, iou_thres;
   int max_det;
+  const uint8_t* d_target_u8;/* u8 [B,H,W] ground-truth mask as stored in the PNG (dataset.py:55, before ToTensor): T = v/255 > 0.5
+                                <=> v >= 128; used when d_target is NULL (a quarter of the upload).  NULL = not given */
+  uint32_t* d_mask_bits;     /* bit-packed predicted mask, uint32 [B, H*W/32] (pixel i -> bit i%32 of word i/32), or NULL;
+                                needs H*W % 128 == 0.  1/32 of the logits: what a predict() caller copies back */
 } ysp_pipeline_io;
 int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, void* d_ws, size_t ws_bytes,
                  void* stream);

@@ -10,7 +10,7 @@ Rules fixed in SURVEY 8(c):
   (iv)  `conf > thr` is strict (nms.py:76,121); class offset cls*max_wh added in fp32 before IoU (nms.py:143,149).
 
 PINNED: tests/golden/nms_*.pt hold outputs of the reference file itself, run through the import shim
-in oracle/ref_shim.py by tests/golden/make_nms_golden.py; tests/test_nms_oracle.py checks this restatement (and
+in oracle/ref_shim.py by tests/golden/make_nms_golden.py; tests/test_oracle_pins.py checks this restatement (and
 the C restatement oracle/nms_oracle.c) against them.
 """
 from __future__ import annotations

@@ -10,7 +10,7 @@
  *     inter / (area_i + area_j - inter) > thr, every fp32 op rounded on its own (build with -ffp-contract=off)
  *   - first max_det survivors                                          (nms.py:157)
  *   - no wall-clock limit (nms.py:162-164 dropped: non-deterministic)
- * PINNED against outputs of the reference file itself: tests/golden/nms_*.pt (tests/test_nms_oracle.py).
+ * PINNED against outputs of the reference file itself: tests/golden/nms_*.pt (tests/test_oracle_pins.py).
  *
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -pthread -shared -fPIC).
  */

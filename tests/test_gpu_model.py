@@ -96,18 +96,21 @@ def test_detector_fp32_parity(ysp, models, ref240, mode):
         y_ref, raws_ref = pred.model(pad_to_multiple(ref240["x"]))
     y, raws = det(ref240["x"].cuda())
     assert y.shape == (4, 5, 1344)
+    # north_star bounds the MASK logits (1e-3) and Dice; the detector's raw head maps (logits of std 2, range +-15, computed
+    # from features up to +-40) are bounded here at 1e-3 for the FFMA mode and 2.5e-3 for the fp16-split tensor-core mode
+    tol_raw, tol_box = (1e-3, 2e-2) if mode == "fp32" else (2.5e-3, 6e-2)
     for r, rr in zip(raws, raws_ref):
         assert r.shape == rr.shape
-        assert (r.cpu() - rr).abs().max().item() <= 1e-3
-    assert (y[:, 4:].cpu() - y_ref[:, 4:]).abs().max().item() <= 1e-4         # sigmoid cls
-    assert (y[:, :4].cpu() - y_ref[:, :4]).abs().max().item() <= 2e-2         # boxes in pixels (x stride 8..32)
+        assert (r.cpu() - rr).abs().max().item() <= tol_raw
+    assert (y[:, 4:].cpu() - y_ref[:, 4:]).abs().max().item() <= 2e-4         # sigmoid cls
+    assert (y[:, :4].cpu() - y_ref[:, :4]).abs().max().item() <= tol_box      # boxes in pixels (x stride 8..32)
     # native %32 input, reference resolution
     x160 = torch.rand(2, 4, 160, 160, generator=torch.Generator().manual_seed(9))
     with torch.no_grad():
         y_ref, raws_ref = pred.model(x160)
     y, raws = det(x160.cuda())
     assert y.shape == (2, 5, 525)
-    assert (raws[0].cpu() - raws_ref[0]).abs().max().item() <= 1e-3
+    assert (raws[0].cpu() - raws_ref[0]).abs().max().item() <= tol_raw
 
 
 @pytest.mark.parametrize("mode", PARITY_MODES)
@@ -135,6 +138,63 @@ def test_pipeline_fp32_parity(ysp, models, ref240, mode):
     a = P.predict_raw(u8.cuda())["mask_logits"].clone()
     b = P.predict_raw(xf.cuda())["mask_logits"].clone()
     assert torch.equal(a, b)
+
+
+def test_u8_target_bitmask_and_large_max_det(ysp, models, ref240):
+    """ysp_pipeline_io.d_target_u8 / d_mask_bits (the e2e path's formats) and max_det > 300 (workspace sized per call)."""
+    pred, seg = models
+    P = ysp.Predictor.from_modules(pred, seg, mode="tc32")
+    x, tg = ref240["x"].cuda(), ref240["tg"].cuda()
+    a = {k: v.clone() for k, v in P.predict_raw(x, tg).items()}
+    tg_u8 = (ref240["tg"][:, 0] * 255).to(torch.uint8).cuda()                   # PNG bytes: 0 / 255
+    b = P.predict_raw(x, tg_u8, want_bits=True)
+    assert torch.equal(a["counts"], b["counts"]) and torch.equal(a["mask_logits"], b["mask_logits"])
+    bits = b["mask_bits"].cpu().view(4, -1, 1)                                  # [B, HW/32, 1] int32
+    unpacked = ((bits >> torch.arange(32, dtype=torch.int32)) & 1).view(4, 240, 240).bool()
+    assert torch.equal(unpacked, torch.sigmoid(b["mask_logits"].cpu()[:, 0]) > 0.5)
+    tg_u8[0, 0, :5] = torch.tensor([127, 128, 1, 254, 129], dtype=torch.uint8)  # v/255 > 0.5 <=> v >= 128
+    c = P.predict_raw(x, tg_u8)["counts"].cpu()
+    want_t = (tg_u8.cpu().float() / 255 > 0.5).view(4, -1).sum(1)
+    assert torch.equal(c[:, 2].long(), want_t)
+    ml, dets, keep, counts = P.predict(x, tg, conf_thres=0.001, iou_thres=0.7, max_det=1000)
+    from oracle import cnms
+    want_d, want_k = cnms.nms_batched(P._out["y"].cpu(), 0.001, 0.7, 1000)
+    for i in range(4):
+        assert torch.equal(keep[i].cpu(), want_k[i])
+
+
+@pytest.mark.parametrize("mode,tol_l,tol_d", [("tc32", TOL_LOGITS_FP32, TOL_DICE), ("bf16", TOL_LOGITS_BF16, TOL_DICE_BF16)])
+def test_parity_at_bench_batch(ysp, models, mode, tol_l, tol_d):
+    """The configuration bench.py times: B = 256 slices per call (persistent-CTA tile scheduling differs from small
+    batches).  The first 24 slices of the batch are checked against the CPU oracle."""
+    from oracle.model import dice_from_counts, mask_counts, pipeline
+    from oracle import nms as onms
+    from oracle import cnms
+    pred, seg = models
+    g = torch.Generator().manual_seed(77)
+    x = torch.rand(256, 4, 240, 240, generator=g)
+    tg = (torch.rand(256, 1, 240, 240, generator=g) > 0.5).float()
+    n = 24
+    with torch.no_grad():
+        want, _, _, _, _ = pipeline(pred, seg, x[:n], onms.non_max_suppression)
+    P = ysp.Predictor.from_modules(pred, seg, mode=mode)
+    o = P.predict_raw(x.cuda(), tg.cuda())
+    torch.cuda.synchronize()
+    ml = o["mask_logits"][:n].cpu()
+    err = (ml - want).abs().max().item()
+    d = ysp.dice_from_counts(o["counts"][:n].cpu())
+    derr = (d - dice_from_counts(mask_counts(want, tg[:n]))).abs().max().item()
+    print(f"{mode} @B=256: logits max-abs {err:.3e}, dice err {derr:.2e}")
+    assert err <= tol_l and derr <= tol_d
+    _, want_k = cnms.nms_batched(o["y"].cpu(), 0.25, 0.45, 300)
+    cnt = o["det_count"].tolist()
+    for b in range(256):
+        assert torch.equal(o["det_idx"][b, :cnt[b]].cpu(), want_k[b])
+    # the last slices of the batch agree with a small-batch run of the same slices (no tile-scheduling dependence)
+    if mode == "tc32":
+        big = o["mask_logits"][248:].clone()
+        small = P.predict_raw(x[248:].cuda(), tg[248:].cuda())["mask_logits"]
+        assert (small - big).abs().max().item() <= 2e-4
 
 
 def test_bf16_mode_bounds(ysp, models, ref240):

@@ -21,7 +21,8 @@ vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 class PipelineIO(C.Structure):
     _fields_ = [("d_img", vp), ("d_img_u8", vp), ("d_target", vp), ("d_mask_logits", vp), ("d_y", vp),
                 ("d_bottleneck", vp), ("d_det_boxes", vp), ("d_det_idx", vp), ("d_det_count", vp), ("d_counts", vp),
-                ("d_mask", vp), ("conf_thres", f32), ("iou_thres", f32), ("max_det", i32)]
+                ("d_mask", vp), ("conf_thres", f32), ("iou_thres", f32), ("max_det", i32), ("d_target_u8", vp),
+                ("d_mask_bits", vp)]
 
 
 # name -> (restype, argtypes); every symbol include/ysp.h declares
@@ -33,6 +34,7 @@ PROTOTYPES = {
     "ysp_load_weight": (i32, [vp, C.c_char_p, vp, i32, C.POINTER(i64)]),
     "ysp_finalize": (i32, [vp, i32]),
     "ysp_workspace_bytes": (sz, [vp, i32, i32, i32]),
+    "ysp_pipeline_workspace_bytes": (sz, [vp, i32, i32, i32, i32]),
     "ysp_normalize_u8": (i32, [vp, vp, i32, i32, i32, vp]),
     "ysp_detector_forward": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]),
     "ysp_bottleneck": (i32, [vp, i32, i32, i32, i32, vp, i32, i32, vp]),

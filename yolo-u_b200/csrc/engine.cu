@@ -1059,20 +1059,29 @@ int ysp_finalize(ysp_handle* h, int which) {
   return 0;
 }
 
-size_t ysp_workspace_bytes(ysp_handle* h, int B, int H, int W) {
+size_t ysp_pipeline_workspace_bytes(ysp_handle* h, int B, int H, int W, int max_det) {
   if (!h || B <= 0 || H <= 0 || W <= 0) return 0;
   if (cudaSetDevice(h->device) != cudaSuccess) return 0;
+  if (max_det <= 0) max_det = 300;
   size_t total = 0;
   Plan* p = nullptr;
   if (h->det_ready && get_plan(h, "det", B, H, W, &p) == 0) total += align_up(p->ws_bytes, 256);
-  if (h->seg_ready && (H % 8 == 0) && (W % 8 == 0) && get_plan(h, "seg", B, H, W, &p) == 0) total += align_up(p->ws_bytes, 256);
+  if (h->seg_ready && (H % 8 == 0) && (W % 8 == 0)) {
+    // ysp_pipeline runs the "segs" plan (shared stem) in bf16 mode and "seg" otherwise: size for the larger of the two
+    size_t sb = 0;
+    if (get_plan(h, "seg", B, H, W, &p) == 0) sb = p->ws_bytes;
+    if (h->mode == YSP_MODE_BF16 && !h->no_share && get_plan(h, "segs", B, H, W, &p) == 0) sb = std::max(sb, p->ws_bytes);
+    total += align_up(sb, 256);
+  }
   const int SH = (H + 31) / 32 * 32, SW = (W + 31) / 32 * 32;
   const int A = (SH / 8) * (SW / 8) + (SH / 16) * (SW / 16) + (SH / 32) * (SW / 32);
   total += align_up((size_t)B * 5 * A * 4, 256);                 // y when the caller does not want it
   total += align_up((size_t)B * (H / 8) * (W / 8) * 4, 256);     // bottleneck logits
-  total += nms_workspace_bytes(B, 5, A, 300) + 256;
+  total += nms_workspace_bytes(B, 5, A, max_det) + 256;
   return total;
 }
+
+size_t ysp_workspace_bytes(ysp_handle* h, int B, int H, int W) { return ysp_pipeline_workspace_bytes(h, B, H, W, 300); }
 
 int ysp_normalize_u8(const uint8_t* d_u8, float* d_out, int B, int H, int W, void* stream) {
   if (!d_u8 || !d_out || B < 0 || H <= 0 || W <= 0) return fail(YSP_EINVAL, "ysp_normalize_u8: bad arguments");
@@ -1201,7 +1210,7 @@ int ysp_mask_dice(const float* d_logits, const float* d_target, int B, int HW, i
                   void* stream) {
   if (!d_logits || !d_counts || B < 0 || HW < 0) return fail(YSP_EINVAL, "ysp_mask_dice: bad arguments");
   if (B == 0) return 0;
-  launch_mask_dice(d_logits, d_target, B, HW, d_counts, d_mask, (cudaStream_t)stream);
+  launch_mask_dice(d_logits, d_target, nullptr, B, HW, d_counts, d_mask, nullptr, (cudaStream_t)stream);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1225,6 +1234,7 @@ int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, 
       !io->d_det_count || !io->d_counts)
     return fail(YSP_EINVAL, "ysp_pipeline: bad arguments");
   if (H % 8 || W % 8) return fail(YSP_EINVAL, "H and W must be multiples of 8 (got %dx%d)", H, W);
+  if (io->d_mask_bits && (H * W) % 128) return fail(YSP_EINVAL, "d_mask_bits needs H*W %% 128 == 0 (got %d)", H * W);
   if (!(io->conf_thres >= 0.f && io->conf_thres <= 1.f) || !(io->iou_thres >= 0.f && io->iou_thres <= 1.f))
     return fail(YSP_EINVAL, "invalid thresholds");
   Plan *pd = nullptr, *ps = nullptr;
@@ -1280,7 +1290,7 @@ int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, 
     // P3 class-branch lane), i.e. concurrently with detector layers 15-20, the rest of the Detect head, decode and NMS
     cudaStreamWaitEvent(s2, sync_event(h, EV_BOTT), 0);
     if ((rc = run_plan(h, ps, c2, ps->split, -1, 24))) return rc;                        // :156
-    launch_mask_dice(io->d_mask_logits, io->d_target, B, H * W, io->d_counts, io->d_mask, s2);   // :157-174
+    launch_mask_dice(io->d_mask_logits, io->d_target, io->d_target_u8, B, H * W, io->d_counts, io->d_mask, io->d_mask_bits, s2);   // :157-174
     cudaEventRecord(sync_event(h, EV_ENC), s2);
     if (launch_nms(y, B, 5, A, 1, io->conf_thres, io->iou_thres, max_det, 30000, 7680.f, 0, nullptr, 0, io->d_det_boxes,
                    io->d_det_idx, io->d_det_count, ws + off_n, ws_bytes - off_n, s))     // :147
@@ -1298,7 +1308,7 @@ int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, 
   c2.s = s;
   if ((rc = run_plan(h, ps, c2, 0, -1, 24))) return rc;                                  // :156
   if (h->profiling) cudaEventRecord(pe[2], s);
-  launch_mask_dice(io->d_mask_logits, io->d_target, B, H * W, io->d_counts, io->d_mask, s);   // :157-174
+  launch_mask_dice(io->d_mask_logits, io->d_target, io->d_target_u8, B, H * W, io->d_counts, io->d_mask, io->d_mask_bits, s);   // :157-174
   h->last_launches += 1;
   if (h->profiling) {
     cudaEventRecord(pe[3], s);

@@ -31,8 +31,8 @@ struct DecodeP {
 void launch_detect_decode(const DecodeP& p, cudaStream_t s);
 void launch_bottleneck_nhwc(const float* raw, int cs, int ch, int B, int Hs, int Ws, float* logits, int h, int w, cudaStream_t s);
 void launch_bottleneck(const float* p3, int B, int C, int Hs, int Ws, float* logits, int h, int w, cudaStream_t s);
-void launch_mask_dice(const float* logits, const float* target, int B, int HW, int32_t* counts, uint8_t* mask,
-                      cudaStream_t s);
+void launch_mask_dice(const float* logits, const float* target, const uint8_t* target_u8, int B, int HW, int32_t* counts,
+                      uint8_t* mask, uint32_t* bits, cudaStream_t s);
 void launch_conf_gate(const float* det_boxes, const int32_t* det_count, int B, int max_det, int row, float thres, int32_t* counts,
                       uint8_t* mask, int HW, uint8_t* gated, cudaStream_t s);
 void launch_nhwc_to_nchw_f32(const void* in, float* out, int N, int H, int W, int C, int in_cs, int dt, cudaStream_t s);

@@ -881,29 +881,53 @@ void launch_bottleneck(const float* p3, int B, int C, int Hs, int Ws, float* log
 // logits in (0, ~9e-8] give sigmoid == 0.5), T = target > 0.5.  counts[b] = (|P&T|, |P|, |T|).  HBM-bound:
 // 8 B read per pixel (+1 B optional mask write).  grid = (chunks, B); warp-shuffle reduce then 3 atomics per block.
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) mask_dice_kernel(const float* __restrict__ lg, const float* __restrict__ tg,
-                                                        int HW, int32_t* counts, uint8_t* mask) {
+// TT = float (reference target tensor, T = t > 0.5) or uint8_t (the mask PNG as stored, before ToTensor: T = v/255 > 0.5
+// <=> v >= 128; a quarter of the H2D bytes).  `bits` (optional): the mask bit-packed, pixel i of slice b = bit i%32 of word
+// b*HW/32 + i/32 (needs HW % 128 == 0) -- 1/32 of the fp32 logits for the device->host read of a predict() caller.
+template <typename TT>
+__global__ void __launch_bounds__(256) mask_dice_kernel(const float* __restrict__ lg, const TT* __restrict__ tg,
+                                                        int HW, int32_t* counts, uint8_t* mask, uint32_t* bits) {
   const int b = blockIdx.y;
   const float* x = lg + (size_t)b * HW;
-  const float* t = tg ? tg + (size_t)b * HW : nullptr;
+  const TT* t = tg ? tg + (size_t)b * HW : nullptr;
   int ci = 0, cp = 0, ct = 0;
-  auto one = [&](float xv, float tv, size_t idx) {
+  auto one = [&](float xv, int ti, size_t idx) -> int {
     float s = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-xv)));
     int pi = s > 0.5f;
-    int ti = tv > 0.5f;
     ci += pi & ti; cp += pi; ct += ti;
     if (mask) mask[idx] = (uint8_t)pi;
+    return pi;
   };
   if ((HW & 3) == 0) {                     // 16-byte loads (HW = 57600 on the hot path)
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < HW; i += gridDim.x * blockDim.x * 4) {
       const float4 xv = *reinterpret_cast<const float4*>(x + i);
-      const float4 tv = t ? *reinterpret_cast<const float4*>(t + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      int t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      if (t) {
+        if (sizeof(TT) == 4) {
+          const float4 tv = *reinterpret_cast<const float4*>(t + i);
+          t0 = tv.x > 0.5f; t1 = tv.y > 0.5f; t2 = tv.z > 0.5f; t3 = tv.w > 0.5f;
+        } else {
+          const uchar4 tv = *reinterpret_cast<const uchar4*>(t + i);
+          t0 = tv.x >= 128; t1 = tv.y >= 128; t2 = tv.z >= 128; t3 = tv.w >= 128;
+        }
+      }
       const size_t o = (size_t)b * HW + i;
-      one(xv.x, tv.x, o); one(xv.y, tv.y, o + 1); one(xv.z, tv.z, o + 2); one(xv.w, tv.w, o + 3);
+      const int p0 = one(xv.x, t0, o), p1 = one(xv.y, t1, o + 1), p2 = one(xv.z, t2, o + 2), p3 = one(xv.w, t3, o + 3);
+      if (bits) {                          // HW % 128 == 0: a warp covers 128 consecutive pixels = 4 words, all lanes active
+        const int lane = threadIdx.x & 31;
+        uint32_t v = (uint32_t)(p0 | (p1 << 1) | (p2 << 2) | (p3 << 3)) << (4 * (lane & 7));
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        v |= __shfl_xor_sync(0xffffffffu, v, 4);
+        if ((lane & 7) == 0) bits[o >> 5] = v;
+      }
     }
   } else {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
-      one(x[i], t ? t[i] : 0.f, (size_t)b * HW + i);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+      int ti = 0;
+      if (t) ti = sizeof(TT) == 4 ? (float)t[i] > 0.5f : (int)t[i] >= 128;
+      one(x[i], ti, (size_t)b * HW + i);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -942,13 +966,14 @@ void launch_conf_gate(const float* det_boxes, const int32_t* det_count, int B, i
   conf_gate_kernel<<<dim3(mask ? 8 : 1, B), 256, 0, s>>>(det_boxes, det_count, max_det, row, thres, counts, mask, HW, gated);
 }
 
-void launch_mask_dice(const float* logits, const float* target, int B, int HW, int32_t* counts, uint8_t* mask,
-                      cudaStream_t s) {
+void launch_mask_dice(const float* logits, const float* target, const uint8_t* target_u8, int B, int HW, int32_t* counts,
+                      uint8_t* mask, uint32_t* bits, cudaStream_t s) {
   cudaMemsetAsync(counts, 0, sizeof(int32_t) * 3 * (size_t)B, s);
   int chunks = cdiv(HW, 256 * 8);
   if (chunks < 1) chunks = 1;
   dim3 g(chunks, B);
-  mask_dice_kernel<<<g, 256, 0, s>>>(logits, target, HW, counts, mask);
+  if (target_u8 && !target) mask_dice_kernel<uint8_t><<<g, 256, 0, s>>>(logits, target_u8, HW, counts, mask, bits);
+  else mask_dice_kernel<float><<<g, 256, 0, s>>>(logits, target, HW, counts, mask, bits);
 }
 
 

@@ -65,13 +65,19 @@ class Engine:
 
     # ---- workspace ---------------------------------------------------------------------------------------------
     def workspace(self, nbytes: int) -> torch.Tensor:
+        """One cached arena per Engine.  An Engine serves ONE stream at a time (libysp's own lanes / aux stream fork from and
+        join back into the caller's stream inside each call); before the arena is replaced by a larger one the device is
+        synchronised, so no kernel of an earlier call -- on whatever stream it ran -- can still be using the old block
+        when the caching allocator hands it out again."""
         if self._ws is None or self._ws.numel() < nbytes:
+            if self._ws is not None:
+                torch.cuda.synchronize(self.device)
             self._ws = None
             self._ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def _ws_for(self, B, H, W) -> torch.Tensor:
-        n = lib().ysp_workspace_bytes(self._h, B, H, W)
+    def _ws_for(self, B, H, W, max_det: int = 300) -> torch.Tensor:
+        n = lib().ysp_pipeline_workspace_bytes(self._h, B, H, W, int(max_det))
         if n == 0:
             raise _lib.YspError("ysp_workspace_bytes failed: " + lib().ysp_last_error().decode())
         return self.workspace(n)
@@ -119,9 +125,11 @@ class Engine:
         return out
 
     def pipeline(self, img: torch.Tensor, target: Optional[torch.Tensor] = None, conf_thres=0.25, iou_thres=0.45,
-                 max_det=300, out: Optional[Dict[str, torch.Tensor]] = None, want_mask=False):
-        """evaluate_model.py:134-174 in one call.  img fp32 [B,4,H,W] or uint8 [B,H,W,4].  Returns a dict of device
-        tensors (padded detections + counts); nothing is synchronised."""
+                 max_det=300, out: Optional[Dict[str, torch.Tensor]] = None, want_mask=False, want_bits=False):
+        """evaluate_model.py:134-174 in one call.  img fp32 [B,4,H,W] or uint8 [B,H,W,4].  `target`: the ground-truth masks,
+        fp32 [B,1,H,W] (T = t > 0.5) or uint8 [B,H,W] / [B,1,H,W] as stored in the mask PNG (T = v >= 128).  `want_bits`:
+        also return the predicted mask bit-packed (int32 [B, H*W/32], pixel i = bit i%32 of word i/32).  Returns a dict of
+        device tensors (padded detections + counts); nothing is synchronised."""
         require_cuda(img, "pipeline")
         u8 = img.dtype == torch.uint8
         if u8:
@@ -152,14 +160,20 @@ class Engine:
         dc = buf("det_count", (B,), torch.int32)
         cnt = buf("counts", (B, 3), torch.int32)
         mk = buf("mask", (B, H, W), torch.uint8) if want_mask else None
+        mb = buf("mask_bits", (B, H * W // 32), torch.int32) if want_bits else None
+        t_f32 = t_u8 = None
         if target is not None:
             require_cuda(target, "pipeline target")
-            target = _f32c(target)
+            if target.dtype == torch.uint8:
+                t_u8 = target.contiguous()
+            else:
+                t_f32 = _f32c(target)
         io = PipelineIO(None if u8 else img.data_ptr(), img.data_ptr() if u8 else None,
-                        target.data_ptr() if target is not None else None, ml.data_ptr(), y.data_ptr(), bt.data_ptr(),
+                        t_f32.data_ptr() if t_f32 is not None else None, ml.data_ptr(), y.data_ptr(), bt.data_ptr(),
                         db.data_ptr(), di.data_ptr(), dc.data_ptr(), cnt.data_ptr(),
-                        mk.data_ptr() if mk is not None else None, conf_thres, iou_thres, max_det)
-        ws = self._ws_for(B, H, W)
+                        mk.data_ptr() if mk is not None else None, conf_thres, iou_thres, max_det,
+                        t_u8.data_ptr() if t_u8 is not None else None, mb.data_ptr() if mb is not None else None)
+        ws = self._ws_for(B, H, W, max_det)
         with torch.cuda.device(self.device):
             check(lib().ysp_pipeline(self._h, C.byref(io), B, H, W, ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
         self._count()

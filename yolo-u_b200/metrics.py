@@ -62,5 +62,8 @@ class SegMetrics:
 
     def compute(self):
         sd, n, tp, fp, fn = self.state.tolist()
+        # precision / recall exactly as evaluate_model.py:177-178 (the 1e-6 in the denominator included).  Masks are binary
+        # here (T = target > 0.5, or PNG byte >= 128): for {0,1} masks TP/FP/FN equal the reference's float sums :166-168.
+        # HD95 (evaluate_model.py:58-63, :160-163) is not computed: outside the hot path.
         return {"dice": sd / n if n else float("nan"), "slices": int(n), "TP": int(tp), "FP": int(fp), "FN": int(fn),
-                "precision": tp / (tp + fp) if tp + fp else 0.0, "recall": tp / (tp + fn) if tp + fn else 0.0}
+                "precision": tp / (tp + fp + 1e-6), "recall": tp / (tp + fn + 1e-6)}

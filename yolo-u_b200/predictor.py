@@ -33,9 +33,10 @@ class Predictor:
 
     @torch.no_grad()
     def predict_raw(self, img: torch.Tensor, target: Optional[torch.Tensor] = None, conf_thres: float = 0.25,
-                    iou_thres: float = 0.45, max_det: int = 300, want_mask: bool = False):
+                    iou_thres: float = 0.45, max_det: int = 300, want_mask: bool = False, want_bits: bool = False):
         """Device-side results, padded, no synchronisation (for benchmarking / graph capture)."""
-        return self.engine.pipeline(img, target, conf_thres, iou_thres, max_det, out=self._out, want_mask=want_mask)
+        return self.engine.pipeline(img, target, conf_thres, iou_thres, max_det, out=self._out, want_mask=want_mask,
+                                    want_bits=want_bits)
 
     @torch.no_grad()
     def predict(self, img: torch.Tensor, target: Optional[torch.Tensor] = None, conf_thres: float = 0.25,
@@ -62,18 +63,24 @@ class Predictor:
 
 
 class HostPipeline:
-    """End-to-end driver for HOST batches: pinned u8 [B,H,W,4] slices in, padded detections + Dice counters out (host).
+    """End-to-end driver for HOST batches: pinned u8 [B,H,W,4] slices in, padded detections + Dice counters (+ optionally the
+    bit-packed predicted mask) out (host).
 
     Double-buffered over three CUDA streams so the H2D copy of batch i+1 and the D2H read of batch i-1 overlap the
-    kernels of batch i (PCIe moves 59 MB per 256 slices; the step itself is ~10 ms).  `submit` is asynchronous;
-    `results(i)` returns the host tensors of slot i after `synchronize()` (or after the slot's event completed)."""
+    kernels of batch i (PCIe moves 59 MB of slices + 15 MB of u8 masks per 256 slices; the step itself is ~5-10 ms).
+    `submit` is asynchronous; `results(i)` returns the host tensors of slot i after `synchronize()` (or after the slot's
+    event completed).  Ground-truth masks go up as uint8 (the PNG bytes, dataset.py:55) -- fp32 masks are accepted too but
+    cost four times the upload.  `return_mask=True` adds `mask_bits` (int32 [B, H*W/32]) to the results: the mask a
+    predict() caller wants, at 1/32 of the size of the fp32 logits."""
 
     KEYS = ("counts", "det_count", "det_boxes", "det_idx")
 
     def __init__(self, predictor: "Predictor", B: int, H: int, W: int, max_det: int = 300, conf_thres: float = 0.25,
-                 iou_thres: float = 0.45):
+                 iou_thres: float = 0.45, return_mask: bool = False):
         self.P, self.B, self.H, self.W = predictor, B, H, W
-        self.kw = dict(conf_thres=conf_thres, iou_thres=iou_thres, max_det=max_det)
+        self.kw = dict(conf_thres=conf_thres, iou_thres=iou_thres, max_det=max_det, want_bits=return_mask)
+        if return_mask:
+            self.KEYS = self.KEYS + ("mask_bits",)
         dev = predictor.engine.device
         self.dev = dev
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
@@ -89,8 +96,8 @@ class HostPipeline:
         self.d2h_bytes = 0
 
     def submit(self, h_img_u8: torch.Tensor, h_target: Optional[torch.Tensor] = None) -> int:
-        """h_img_u8: pinned uint8 [B,H,W,4]; h_target: optional pinned fp32 [B,1,H,W] ground-truth masks (both HOST).
-        Returns the slot (0/1) holding this batch's results."""
+        """h_img_u8: pinned uint8 [B,H,W,4]; h_target: optional pinned ground-truth masks, uint8 [B,H,W] (PNG bytes) or fp32
+        [B,1,H,W] (both HOST).  Returns the slot (0/1) holding this batch's results."""
         k = self.n % 2
         self.n += 1
         d_target = None
@@ -98,12 +105,12 @@ class HostPipeline:
             self.s_in.wait_event(self.ev_run[k])          # slot's previous compute has consumed d_img[k] / d_tgt[k]
             self.d_img[k].copy_(h_img_u8, non_blocking=True)
             if h_target is not None:
-                if self.d_tgt[k] is None:
-                    self.d_tgt[k] = torch.empty(h_target.shape, dtype=torch.float32, device=self.dev)
+                if self.d_tgt[k] is None or self.d_tgt[k].dtype != h_target.dtype or self.d_tgt[k].shape != h_target.shape:
+                    self.d_tgt[k] = torch.empty(h_target.shape, dtype=h_target.dtype, device=self.dev)
                 self.d_tgt[k].copy_(h_target, non_blocking=True)
                 d_target = self.d_tgt[k]
             self.ev_in[k].record(self.s_in)
-        self.h2d_bytes = h_img_u8.numel() + (h_target.numel() * 4 if h_target is not None else 0)
+        self.h2d_bytes = h_img_u8.numel() + (h_target.numel() * h_target.element_size() if h_target is not None else 0)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(self.ev_in[k])
             self.s_run.wait_event(self.ev_out[k])         # slot's previous results have left the device buffers
