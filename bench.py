@@ -52,14 +52,32 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  Polls NVML in-process
+    every 10 ms (nvidia_ml_py; the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints) -- a
+    freshly spawned nvidia-smi needs longer to start than a 100-250 ms timed region lasts.  Falls back to nvidia-smi -lms."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, gpu_index: int):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.proc, self.nv, self.stop_flag = gpu_index, [], None, None, False
+        self.sm, self.mx, self.mask, self.power = [], None, 0, []
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].strip().isdigit() else self.idx
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.nv = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -68,11 +86,27 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self.mask |= int(self.reasons_fn(self.h))
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag = True
+            self.t.join(1.0)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(n for n, b in self.BITS if self.mask & b), "samples": len(self.sm),
+                    "power_w_max": max(self.power) if self.power else None, "source": "nvml, 10 ms poll inside the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -89,7 +123,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -485,6 +519,123 @@ def main_ours(args):
     return 0
 
 
+def main_eval(args):
+    """BASELINE configs[2] (not the headline metric): the reference's evaluation run (evaluate_model.py:134-187) over 64
+    synthetic volumes x 155 slices = 9,920 slices, contiguous-by-volume shards over the ranks (STRONG scaling: the job is
+    fixed), ragged last batch, and the metric all-reduce (NCCL) INSIDE the timed region.  One step = one whole evaluation."""
+    import torch
+    import torch.distributed as dist
+    import yolo_u_b200 as ysp
+    from yolo_u_b200.synth import calibrate, synth_state_dicts
+
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    NV, NS = args.volumes, 155
+    B, K, Wm = args.batch, args.steps, args.warmup
+    det_sd, seg_sd = calibrate(*synth_state_dicts(0), device=dev)
+    P = ysp.Predictor(det_sd, seg_sd, device=dev, mode=args.mode)
+    lo, hi = ysp.shard_slices(NV, NS, world, rank)
+    n_local = hi - lo
+    # this rank's shard: decoded PNG bytes (u8 HWC4 slices + u8 masks), generated per VOLUME from the volume index so the
+    # data -- and therefore every reduced counter -- is the same for every world size
+    h_img = torch.empty(n_local, H, W, 4, dtype=torch.uint8).pin_memory()
+    h_tgt = torch.empty(n_local, H, W, dtype=torch.uint8).pin_memory()
+    g = torch.Generator()
+    for v in range(lo // NS, hi // NS):
+        g.manual_seed(9000 + v)
+        o = (v - lo // NS) * NS
+        h_img[o:o + NS] = torch.randint(0, 256, (NS, H, W, 4), dtype=torch.uint8, generator=g)
+        h_tgt[o:o + NS] = (torch.rand(NS, H, W, generator=g) > 0.5).to(torch.uint8) * 255
+    d_img, d_tgt = h_img.to(dev), h_tgt.to(dev)               # 2.3 GB per 9,920 slices: far larger than L2
+    bl = ysp.batches(0, n_local, B)
+    all_counts = torch.zeros(max(n_local, 1), 3, dtype=torch.int32, device=dev)
+    outs = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def evaluate_device():
+        for a, b in bl:
+            o = P.engine.pipeline(d_img[a:b], d_tgt[a:b], out=outs.setdefault(b - a, {}))
+            all_counts[a:b].copy_(o["counts"], non_blocking=True)
+        met = ysp.SegMetrics()
+        if n_local:
+            met.update(all_counts[:n_local])              # ONE D2H of the integer counters per evaluation
+        return met.reduce(device=dev).compute()           # the path's only collective: 5 doubles, NCCL all-reduce
+
+    hp = ysp.HostPipeline(P, B, H, W)
+
+    def evaluate_host():
+        slots = []
+        met = ysp.SegMetrics()
+        for a, b in bl:
+            slots.append((hp.submit(h_img[a:b], h_tgt[a:b]), b - a))
+            if len(slots) == 2:                            # a slot's results are read before it is submitted to again
+                sl, _ = slots.pop(0)
+                met.update(hp.results(sl)["counts"])
+        for sl, _ in slots:
+            met.update(hp.results(sl)["counts"])
+        return met.reduce(device=dev).compute()
+
+    def timed(fn):
+        for _ in range(Wm):
+            res = fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(K):
+            res = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms, wall], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = (float(v) for v in t.tolist())
+        return res, ms, wall
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = P.engine.launches_total
+    res, ms, wall = timed(evaluate_device)
+    launches = (P.engine.launches_total - l0) * K // (K + Wm)
+    clocks = sampler.stop() if rank == 0 else None
+    res_h, ms_h, wall_h = timed(evaluate_host)
+    total = NV * NS
+    same = all(res[k] == res_h[k] for k in ("TP", "FP", "FN", "slices")) and abs(res["dice"] - res_h["dice"]) < 1e-12
+    if rank == 0:
+        line = {"metric": "evaluation slices/sec (BASELINE cfg 3: 64 volumes x 155 slices, sharded by volume, metric all-reduce in the timed region)",
+                "value": total * K / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
+                "wall_ms_per_step": wall / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": DTYPE_OF[args.mode], "data": "synthetic",
+                "config": {"workload": f"evaluate_model.py:134-187 over {NV} volumes x {NS} slices = {total} 4x{H}x{W} slices; u8 slices + u8 masks",
+                           "mode": args.mode, "batch": B, "batches_per_rank": [b - a for a, b in bl], "parallelism": f"shard{world} (contiguous by volume)",
+                           "collective": "one all-reduce(SUM) of [sum Dice, n, TP, FP, FN] per evaluation (NCCL), inside the timed region",
+                           "l2": f"inputs larger than L2: {n_local * H * W * 5 / 1e6:.0f} MB of device-resident slices + masks per rank"},
+                "e2e": {"value": total * K / (ms_h / 1e3), "unit": UNIT, "ms_per_step": ms_h / K, "wall_ms_per_step": wall_h / K,
+                        "h2d_bytes_per_step": n_local * H * W * 5, "d2h_bytes_per_step": sum(hp.d2h_bytes for _ in bl),
+                        "note": "the same evaluation from pinned HOST slices through HostPipeline.submit (H2D + D2H every batch)"},
+                "metrics": res, "metrics_e2e_equal": bool(same), "gpu_launches": int(launches), "clocks": clocks}
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main_train(args):
     """BASELINE cfg 4 (not the headline metric): seg-head training step, B=128/GPU, frozen detector encoder, Dice+BCE,
     data-parallel gradient all-reduce, AdamW.  Same timing rules as the inference arm; prints ONE JSON line."""
@@ -698,13 +849,17 @@ def main():
     ap.add_argument("--no-library", action="store_true", help="skip the stock-PyTorch (cuDNN) library baseline")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="infer", choices=["infer", "train", "nms"],
-                    help="infer = the headline metric (default); train = BASELINE cfg 4 (seg-head training step); "
+    ap.add_argument("--workload", default="infer", choices=["infer", "eval", "train", "nms"],
+                    help="infer = the headline metric (default); eval = BASELINE cfg 3 (9,920-slice evaluation, strong scaling, "
+                         "metric all-reduce inside the timed region); train = BASELINE cfg 4 (seg-head training step); "
                          "nms = BASELINE cfg 5 (NMS stress)")
+    ap.add_argument("--volumes", type=int, default=64, help="eval workload: number of 155-slice volumes")
     ap.add_argument("--loss", default="dice_bce", choices=["dice", "dice_bce"])
     args = ap.parse_args()
     if args.workload == "train" and args.batch == 256:
         args.batch = 128
+    if args.workload == "eval" and "--steps" not in " ".join(sys.argv):
+        args.steps = 5                                # one step = 9,920 slices
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return main_reference(args)
@@ -717,6 +872,8 @@ def main():
         return subprocess.call(cmd)
     if args.workload == "nms":
         return main_nms(args)
+    if args.workload == "eval":
+        return main_eval(args)
     return main_train(args) if args.workload == "train" else main_ours(args)
 
 

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+    config.addinivalue_line("markers", "slow: full-size sweeps (still part of -m gpu; tens of seconds each)")
 
 
 @pytest.fixture(scope="session")

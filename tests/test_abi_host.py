@@ -45,6 +45,14 @@ def test_library_sass_is_blackwell_native():
         assert len(re.findall(r"\b" + mnemonic + r"\b", sass)) >= least, mnemonic
 
 
+def test_library_has_no_work_skipping_switch():
+    """The dlc_tc timing probes (which drop MMAs / arithmetic) are compiled only with -DYSP_PROBES; the shipped library
+    must not even contain the name of the environment variable that used to enable them."""
+    blob = open(os.path.join(ROOT, "yolo-u_b200", "libysp.so"), "rb").read()
+    assert b"YSP_DLC_PROBE" not in blob
+    assert b"YSP_PROBES" not in open(os.path.join(ROOT, "yolo-u_b200", "build.py"), "rb").read()
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
 def test_no_cpu_fallback():
     h = ctypes.c_void_p()

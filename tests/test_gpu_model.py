@@ -131,7 +131,10 @@ def test_pipeline_fp32_parity(ysp, models, ref240, mode):
     for b in range(4):
         assert torch.equal(keep[b].cpu(), want_k[b])
         assert torch.equal(dets[b].cpu(), want_d[b])
-    assert (o["bottleneck"].cpu() - ref240["bott"]).abs().max().item() <= 1e-4
+    # a3: sigmoid of the P3 class logit.  FFMA mode 1e-4; the fp16-split tensor-core mode carries the detector's raw-map
+    # error (<= 2.5e-3, test_detector_fp32_parity) through sigmoid' <= 1/4 -- measured 1.2e-4; the bound north_star states
+    # (mask logits 1e-3, Dice 1e-4) is asserted above and includes this input.
+    assert (o["bottleneck"].cpu() - ref240["bott"]).abs().max().item() <= (1e-4 if mode == "fp32" else 3e-4)
     # u8 ingest path (a1) gives the same result as fp32 input of x/255
     u8 = (ref240["x"] * 255).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
     xf = u8.permute(0, 3, 1, 2).float() / 255

@@ -70,6 +70,26 @@ def test_nms_vs_c_oracle_sweep(ysp, kind, A, B, conf, iou):
         assert torch.equal(dets[b].cpu().reshape(-1, 6), want_d[b].reshape(-1, 6))
 
 
+@pytest.mark.slow
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("kind", ["uniform", "ties", "allequal", "below", "clustered"])
+def test_nms_cfg5_full_sweep(ysp, kind):
+    """BASELINE cfg 5 in full: ALL 1024 images x 8400 anchors per sweep (distinct scores / ties / all-equal / all below
+    threshold / clustered boxes), conf 0.001, IoU 0.7, max_det 300 -- every image's keep-index tensor and boxes bit-exact
+    against the plain-C oracle (all host cores)."""
+    from oracle import cnms
+    pred = make_case(seed=5000 + len(kind), B=1024, nc=1, A=8400, kind=kind)
+    want_d, want_k = cnms.nms_batched(pred, 0.001, 0.7, 300, nthreads=os.cpu_count() or 8)
+    dets, keep = ysp.non_max_suppression(pred.cuda(), 0.001, 0.7, return_idxs=True)
+    bad = [b for b in range(1024) if not torch.equal(keep[b].view(-1).long().cpu(), want_k[b])
+           or not torch.equal(dets[b].cpu().reshape(-1, 6), want_d[b].reshape(-1, 6))]
+    assert not bad, f"{kind}: {len(bad)} of 1024 images differ, first {bad[:5]}"
+    if kind == "below":
+        assert all(k.numel() == 0 for k in keep)
+    else:
+        assert sum(k.numel() for k in keep) > 1024
+
+
 def test_nms_options(ysp):
     from oracle import nms as onms
     pred = make_case(seed=77, B=3, nc=3, A=2100, kind="clustered")

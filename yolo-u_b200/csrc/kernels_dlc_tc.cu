@@ -95,6 +95,13 @@ __device__ __forceinline__ uint4 lerp8(const uint4& a, __nv_bfloat162 wa, const 
 
 }  // namespace
 
+// Timing probes (drop MMAs / arithmetic, results WRONG) exist only in -DYSP_PROBES builds: the shipped library cannot skip work.
+#ifdef YSP_PROBES
+#define PROBE(bit) ((p.probe & (bit)) != 0)
+#else
+#define PROBE(bit) false
+#endif
+
 constexpr int kDlcThreads = 320;            // warps 0-7: CUDA-core phases + epilogues; warps 8-9: MMA issue
 
 template <int CIN, int C, bool HEAD>
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       const int li = bi + 1, lj = bj + 1;
       const int gi = py0 + li, gj = px0 + lj;
       uint4 o00, o01, o10, o11;
-      if (gi >= 0 && gi < p.h && gj >= 0 && gj < p.w && !(p.probe & 4)) {
+      if (gi >= 0 && gi < p.h && gj >= 0 && gj < p.w && !PROBE(4)) {
         const uint8_t* c = sX + ((li * XC + lj) * CIN + kc * 8) * 2;
         constexpr int RS = XC * CIN * 2, PS = CIN * 2;
         const uint4 m0 = *reinterpret_cast<const uint4*>(c - RS - PS), m1 = *reinterpret_cast<const uint4*>(c - RS), m2 = *reinterpret_cast<const uint4*>(c - RS + PS);
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       const uint32_t r_lo = ((s32(sWr) & 0x3FFFF) >> 4) + (((uint32_t)(C * 16) >> 4) << 16);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        if ((p.probe & 1) && tap % 3) continue;        // timing probe (wrong results): one MMA per chain only
+        if (PROBE(1) && tap % 3) continue;             // timing probe (wrong results; -DYSP_PROBES builds only)
 #pragma unroll
         for (int ks = 0; ks < CIN / 16; ++ks)
           umma2(tmem + (3 * h + tap / 3) * C, a_lo + (((2 * ks) * PLANE) >> 4) + (tap / 3) * AP + (tap % 3), a_hi,
@@ -282,7 +289,7 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float2 sm = __fadd2_rn(__fadd2_rn(f2(v, 2 * j), f2(v1, 2 * j)), f2(v2, 2 * j));
-        const float2 ff = (p.probe & 8) ? sm : silu_th2(__fadd2_rn(sm, make_float2(bb[2 * j], bb[2 * j + 1])));
+        const float2 ff = PROBE(8) ? sm : silu_th2(__fadd2_rn(sm, make_float2(bb[2 * j], bb[2 * j + 1])));
         __nv_bfloat162 hv = __floats2bfloat162_rn(inside ? ff.x : 0.f, inside ? ff.y : 0.f);
         w[j] = *reinterpret_cast<uint32_t*>(&hv);
       }
@@ -305,7 +312,7 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       const uint32_t w_lo = ((s32(sW2) & 0x3FFFF) >> 4) + (((uint32_t)(C * 16) >> 4) << 16);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        if ((p.probe & 2) && tap % 3) continue;
+        if (PROBE(2) && tap % 3) continue;
 #pragma unroll
         for (int ks = 0; ks < C / 16; ++ks)
           umma2(tmem + (3 * h + tap / 3) * C, a_lo + (((2 * ks) * PLANE) >> 4) + (tap / 3) * AP + (tap % 3), a_hi,
@@ -451,11 +458,14 @@ static void dlc_tc_launch(const DlcTcP& p, cudaStream_t s) {
 }
 
 void launch_dlc_tc(const DlcTcP& p0, cudaStream_t s) {
-  // YSP_DLC_PROBE (timing experiments only, results are wrong): 1 = conv1 issues 3 of its 9 taps, 2 = same for conv2,
-  // 4 = no up2 arithmetic in phase 1, 8 = no SiLU in epilogue 1
-  static const int probe = getenv("YSP_DLC_PROBE") ? atoi(getenv("YSP_DLC_PROBE")) : 0;
   DlcTcP p = p0;
+  p.probe = 0;
+#ifdef YSP_PROBES
+  // YSP_DLC_PROBE (timing experiments only, results are wrong; compiled in with -DYSP_PROBES, never in build.py's flags):
+  // 1 = conv1 issues 3 of its 9 taps, 2 = same for conv2, 4 = no up2 arithmetic in phase 1, 8 = no SiLU in epilogue 1
+  static const int probe = getenv("YSP_DLC_PROBE") ? atoi(getenv("YSP_DLC_PROBE")) : 0;
   p.probe = probe;
+#endif
   const unsigned txs = (2 * p.w + TW - 1) / TW, tys = (2 * p.h + TH - 1) / TH;
   p.magic_x = txs > 1 ? (unsigned)((0x100000000ull + txs - 1) / txs) : 0u;
   p.magic_y = tys > 1 ? (unsigned)((0x100000000ull + tys - 1) / tys) : 0u;

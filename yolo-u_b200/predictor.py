@@ -92,43 +92,55 @@ class HostPipeline:
         self.ev_run = [torch.cuda.Event() for _ in range(2)]
         self.ev_out = [torch.cuda.Event() for _ in range(2)]
         self.n = 0
+        self.last_n = [B, B]
         self.h2d_bytes = B * H * W * 4
         self.d2h_bytes = 0
 
     def submit(self, h_img_u8: torch.Tensor, h_target: Optional[torch.Tensor] = None) -> int:
-        """h_img_u8: pinned uint8 [B,H,W,4]; h_target: optional pinned ground-truth masks, uint8 [B,H,W] (PNG bytes) or fp32
-        [B,1,H,W] (both HOST).  Returns the slot (0/1) holding this batch's results."""
+        """h_img_u8: pinned uint8 [n,H,W,4], n <= B (a ragged last batch keeps its own device / host result buffers);
+        h_target: optional pinned ground-truth masks, uint8 [n,H,W] (PNG bytes) or fp32 [n,1,H,W] (both HOST).  Returns the
+        slot (0/1) holding this batch's results."""
         k = self.n % 2
         self.n += 1
+        n = int(h_img_u8.shape[0])
+        if n > self.B:
+            raise ValueError(f"batch of {n} slices exceeds the pipeline's capacity {self.B}")
         d_target = None
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(self.ev_run[k])          # slot's previous compute has consumed d_img[k] / d_tgt[k]
-            self.d_img[k].copy_(h_img_u8, non_blocking=True)
+            d_img = self.d_img[k][:n]
+            d_img.copy_(h_img_u8, non_blocking=True)
             if h_target is not None:
-                if self.d_tgt[k] is None or self.d_tgt[k].dtype != h_target.dtype or self.d_tgt[k].shape != h_target.shape:
-                    self.d_tgt[k] = torch.empty(h_target.shape, dtype=h_target.dtype, device=self.dev)
-                self.d_tgt[k].copy_(h_target, non_blocking=True)
-                d_target = self.d_tgt[k]
+                shape = (self.B,) + tuple(h_target.shape[1:])
+                if self.d_tgt[k] is None or self.d_tgt[k].dtype != h_target.dtype or self.d_tgt[k].shape != shape:
+                    self.d_tgt[k] = torch.empty(shape, dtype=h_target.dtype, device=self.dev)
+                d_target = self.d_tgt[k][:n]
+                d_target.copy_(h_target, non_blocking=True)
             self.ev_in[k].record(self.s_in)
         self.h2d_bytes = h_img_u8.numel() + (h_target.numel() * h_target.element_size() if h_target is not None else 0)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(self.ev_in[k])
             self.s_run.wait_event(self.ev_out[k])         # slot's previous results have left the device buffers
-            o = self.P.engine.pipeline(self.d_img[k], d_target, out=self.d_out[k], **self.kw)
+            o = self.P.engine.pipeline(d_img, d_target, out=self.d_out[k].setdefault(n, {}), **self.kw)
             self.ev_run[k].record(self.s_run)
         if self.h_out[k] is None:
-            self.h_out[k] = {key: torch.empty(o[key].shape, dtype=o[key].dtype).pin_memory() for key in self.KEYS}
-            self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.h_out[k].values())
+            self.h_out[k] = {}
+        if n not in self.h_out[k]:
+            self.h_out[k][n] = {key: torch.empty(o[key].shape, dtype=o[key].dtype).pin_memory() for key in self.KEYS}
+        h = self.h_out[k][n]
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in h.values())
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_run[k])
             for key in self.KEYS:
-                self.h_out[k][key].copy_(o[key], non_blocking=True)
+                h[key].copy_(o[key], non_blocking=True)
             self.ev_out[k].record(self.s_out)
+        self.last_n[k] = n
         return k
 
     def results(self, slot: int):
+        """Host tensors of the batch last submitted to `slot` (valid until that slot is submitted to again)."""
         self.ev_out[slot].synchronize()
-        return self.h_out[slot]
+        return self.h_out[slot][self.last_n[slot]]
 
     def synchronize(self):
         for s in (self.s_in, self.s_run, self.s_out):
