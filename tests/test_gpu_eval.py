@@ -137,16 +137,17 @@ def test_scale_boxes(ysp):
         assert torch.allclose(out.cpu(), want, atol=1e-5) and torch.equal(d[:, 4:].cpu(), b[:, 4:])
 
 
-def test_shared_stem_is_exact(ysp, models, monkeypatch):
-    """bf16 pipeline: reading the detector's layer-1 output through a pitched view (shared stem) gives bit-identical
+@pytest.mark.parametrize("mode", ["bf16", "tc32"])
+def test_shared_stem_is_exact(ysp, models, monkeypatch, mode):
+    """Tensor-core pipelines: reading the detector's layer-1 output through a pitched view (shared stem) gives bit-identical
     results to recomputing encoder layers 0-1 (YSP_NO_SHARE=1 at handle creation)."""
     pred, seg = models
     g = torch.Generator().manual_seed(3)
     x = torch.rand(5, 4, 240, 240, generator=g).cuda()
     tg = (torch.rand(5, 1, 240, 240, generator=g) > 0.5).float().cuda()
-    a = {k: v.clone() for k, v in ysp.Predictor.from_modules(pred, seg, mode="bf16").predict_raw(x, tg).items()}
+    a = {k: v.clone() for k, v in ysp.Predictor.from_modules(pred, seg, mode=mode).predict_raw(x, tg).items()}
     monkeypatch.setenv("YSP_NO_SHARE", "1")
-    P2 = ysp.Predictor.from_modules(pred, seg, mode="bf16")
+    P2 = ysp.Predictor.from_modules(pred, seg, mode=mode)
     monkeypatch.delenv("YSP_NO_SHARE")
     b = P2.predict_raw(x, tg)
     assert P2.engine.launches_total > 0

@@ -41,7 +41,15 @@ template <> __device__ __forceinline__ void store4<bf16>(bf16* p, const F4& r) {
   *reinterpret_cast<uint2*>(p) = t;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+// SiLU(x) = x * rcp(1 + 2^(-x log2 e)) on the MUFU unit: ex2.approx (2 ulp) + rcp.approx (1 ulp) -> relative error ~3e-7, the
+// size of an fp32 rounding; 5 instructions instead of the ~25 of `x / (1 + expf(-x))` (IEEE divide + range-checked expf),
+// which ncu showed to be a quarter of all instructions of the parity-mode conv epilogues.  x << 0: 2^(..) = inf, rcp = 0.
+__device__ __forceinline__ float silu_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float apply_act(float x, int act) { return act == ACT_SILU ? silu_f(x) : x; }
 // SiLU(x) = h + h*tanh(h), h = x/2: one MUFU op (tanh.approx, rel. error ~2^-11 -- below bf16 resolution).  Used wherever
@@ -52,6 +60,20 @@ __device__ __forceinline__ float silu_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
 }
+// fp32 pair -> packed fp16 hi and lo with x = hi + lo (hi = rn16(x), lo = rn16(x - hi): 22 mantissa bits), the operand split of
+// the parity-mode tensor-core kernels.  The conversion saturates (F2FP.SATFINITE) instead of clamping with two FMNMX per value.
+__device__ __forceinline__ uint32_t f2h2_sat(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = f2h2_sat(a, b);
+  float fa, fb;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(fa), "=f"(fb) : "r"(hi));
+  lo = f2h2_sat(a - fa, b - fb);
+}
+
 template <typename T> __device__ __forceinline__ float silu_for(float x);
 template <> __device__ __forceinline__ float silu_for<float>(float x) { return silu_f(x); }
 template <> __device__ __forceinline__ float silu_for<bf16>(float x) { return silu_approx(x); }

@@ -99,16 +99,7 @@ __device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
 }
 
-// x = hi + lo with hi = rn16(x), lo = rn16(x - hi); |x| clamped to the fp16 range (never reached by this network)
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) { split2_f16(a, b, hi, lo); }
 
 constexpr int kMaxS = 8;
 

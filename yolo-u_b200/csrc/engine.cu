@@ -454,14 +454,20 @@ struct Builder {
   void attention(TRef qkv, TRef out, int heads, int area) {
     if (rc) return;
     Plan* pl = plan; int d = dt;
+    // tcgen05 kernel (attention_tc.cu) for 64-token areas in both tensor-core modes; the FFMA mode and other shapes use the
+    // SIMT kernel, YSP_NO_ATTN_TC=1 switches back to the mma.sync kernel (bf16) / the SIMT kernel for A/B timing
+    const bool tcmode = (h->mode == YSP_MODE_BF16 || h->tc32()) && getenv("YSP_NO_ATTN_TC") == nullptr && getenv("YSP_NO_TC") == nullptr;
+    const bool use_tc = tcmode && attention_tc_supported(qkv.H * qkv.W, heads, area > 0 ? area : 1, qkv.cs, out.cs, dt);
     emit([=](RunCtx& c) {
       const int ntok = qkv.H * qkv.W, ar = area > 0 ? area : 1;
-      if (d == DT_BF16 && ntok % ar == 0 && ntok / ar == 64)
+      if (use_tc)
+        launch_attention_tc(pl->ptr(c, qkv), pl->ptr(c, out), qkv.N, ntok, heads, ar, qkv.cs, out.cs, d, c.s);
+      else if (d == DT_BF16 && ntok % ar == 0 && ntok / ar == 64)
         launch_attention64_bf16(pl->ptr(c, qkv), pl->ptr(c, out), qkv.N, ntok, heads, ar, qkv.cs, out.cs, c.s);
       else
         launch_attention(pl->ptr(c, qkv), pl->ptr(c, out), qkv.N, ntok, out.C, heads, ar, qkv.cs, out.cs, d, c.s);
     }, {&qkv, &out}, 1,
-    StepInfo{"attention", "attention", tbytes(qkv) + tbytes(out),
+    StepInfo{"attention", use_tc ? "attention_tc" : "attention", tbytes(qkv) + tbytes(out),
              4.0 * qkv.N * (double)(qkv.H * qkv.W) * (qkv.H * qkv.W / (area > 0 ? area : 1)) * out.C, 1});
   }
 
@@ -601,12 +607,28 @@ struct Builder {
       rc = fail(YSP_EINVAL, "doublelight %s: unexpected weight shapes", p.c_str());
       return;
     }
+    const double hi = (double)xlow.N * xlow.H * xlow.W * 4;
+    if (h->tc32() && c2->w_tc && dlc32_supported(C, hd != nullptr) && P.cs % 4 == 0 && (hd || out.cs % 4 == 0) &&
+        getenv("YSP_NO_DLC32") == nullptr) {
+      // parity mode: composite up2 o depthwise on CUDA cores + the pointwise GEMM on tcgen05 (kernels_dlc32.cu)
+      Dlc32P q = {};
+      q.dw1 = d1->w; q.b1 = d1->bias; q.wpack = c2->w_tc; q.w_unscale = c2->w_unscale; q.b2 = c2->bias; q.dw2 = d2->w; q.b3 = d2->bias;
+      q.wo = hd ? hd->w : nullptr; q.bo = hd ? hd->bias : nullptr; q.wo_ld = hd ? hd->wld : 0;
+      q.N = xlow.N; q.h = xlow.H; q.w = xlow.W; q.C = C; q.p_cs = P.cs; q.out_cs = out.cs;
+      Plan* pl = plan;
+      emit([=](RunCtx& c) {
+        Dlc32P r = q;
+        r.P = pl->ptr(c, P); r.out = pl->ptr(c, out);
+        launch_dlc32(r, c.s);
+      }, {&P, &out}, 1,
+      StepInfo{p + ".fused", "dlc32", tbytes(P) + (hd ? hi * 4 : tbytes(out)), 2.0 * hi * C * (9 + C + 9 + (hd ? 1 : 0)) + 16.0 * hi * C, 1});
+      return;
+    }
     DlcP q = {};
     q.dw1 = d1->w; q.b1 = d1->bias; q.w2 = c2->w; q.b2 = c2->bias; q.w2ld = c2->wld; q.dw2 = d2->w; q.b3 = d2->bias;
     q.wo = hd ? hd->w : nullptr; q.bo = hd ? hd->bias : nullptr; q.wo_ld = hd ? hd->wld : 0;
     q.N = xlow.N; q.h = xlow.H; q.w = xlow.W; q.C = C; q.p_cs = P.cs; q.out_cs = out.cs;
     Plan* pl = plan; int d = dt;
-    const double hi = (double)xlow.N * xlow.H * xlow.W * 4;
     emit([=](RunCtx& c) {
       DlcP r = q;
       r.P = pl->ptr(c, P); r.out = pl->ptr(c, out);
@@ -815,7 +837,7 @@ static int build_detector(ysp_handle* h, Plan* plan, int B, int H, int W) {
 }
 
 // YOLO-Seg++ head (YOLOSegPlusPlus.py:150-178, :242-272)
-// `shared_stem` (pipeline, bf16 mode): encoder layers 0 and 1 are NOT recomputed.  They are stride-2 3x3 convs whose
+// `shared_stem` (pipeline, both tensor-core modes): encoder layers 0 and 1 are NOT recomputed.  They are stride-2 3x3 convs whose
 // outputs inside the H/4 x W/4 window depend only on input pixels inside the H x W image, and the detector computes the
 // very same layers (shared weights, YOLOSegPlusPlus.py:150) on the image zero-padded to %32 -- so the detector's layer-1
 // output, read through a pitched H/4 x W/4 view, IS encoder.1's output, exactly.  (From layer 2 on the 3x3 stride-1
@@ -1067,10 +1089,10 @@ size_t ysp_pipeline_workspace_bytes(ysp_handle* h, int B, int H, int W, int max_
   Plan* p = nullptr;
   if (h->det_ready && get_plan(h, "det", B, H, W, &p) == 0) total += align_up(p->ws_bytes, 256);
   if (h->seg_ready && (H % 8 == 0) && (W % 8 == 0)) {
-    // ysp_pipeline runs the "segs" plan (shared stem) in bf16 mode and "seg" otherwise: size for the larger of the two
+    // ysp_pipeline runs the "segs" plan (shared stem) in the tensor-core modes and "seg" otherwise: size for the larger of the two
     size_t sb = 0;
     if (get_plan(h, "seg", B, H, W, &p) == 0) sb = p->ws_bytes;
-    if (h->mode == YSP_MODE_BF16 && !h->no_share && get_plan(h, "segs", B, H, W, &p) == 0) sb = std::max(sb, p->ws_bytes);
+    if ((h->mode == YSP_MODE_BF16 || h->tc32()) && !h->no_share && get_plan(h, "segs", B, H, W, &p) == 0) sb = std::max(sb, p->ws_bytes);
     total += align_up(sb, 256);
   }
   const int SH = (H + 31) / 32 * 32, SW = (W + 31) / 32 * 32;
@@ -1239,7 +1261,7 @@ int ysp_pipeline(ysp_handle* h, const ysp_pipeline_io* io, int B, int H, int W, 
     return fail(YSP_EINVAL, "invalid thresholds");
   Plan *pd = nullptr, *ps = nullptr;
   if ((rc = get_plan(h, "det", B, H, W, &pd))) return rc;
-  const bool share = h->mode == YSP_MODE_BF16 && !h->no_share && (long long)B * (H / 4) * (W / 4) >= 128;
+  const bool share = (h->mode == YSP_MODE_BF16 || h->tc32()) && !h->no_share && (long long)B * (H / 4) * (W / 4) >= 128;
   if ((rc = get_plan(h, share ? "segs" : "seg", B, H, W, &ps))) return rc;
   const int SH = (H + 31) / 32 * 32, SW = (W + 31) / 32 * 32;
   const int A = (SH / 8) * (SW / 8) + (SH / 16) * (SW / 16) + (SH / 32) * (SW / 32);

@@ -48,6 +48,11 @@ void launch_stem_conv(const void* in, int in_u8, void* out, const float* w, cons
 void launch_attention64_bf16(const void* qkv, void* out, int B, int Ntok, int heads, int area, int qkv_cs, int out_cs,
                              cudaStream_t s);
 
+// attention_tc.cu (tcgen05: both tensor-core modes, 64-token areas, head_dim 32, even head count)
+bool attention_tc_supported(int Ntok, int heads, int area, int qkv_cs, int out_cs, int dt);
+void launch_attention_tc(const void* qkv, void* out, int B, int Ntok, int heads, int area, int qkv_cs, int out_cs, int dt,
+                         cudaStream_t s);
+
 // nms.cu
 size_t nms_workspace_bytes(int B, int C, int A, int max_det);
 int launch_nms(const float* pred, int B, int C, int A, int nc, float conf, float iou, int max_det, int max_nms,
@@ -91,6 +96,25 @@ struct DlcP {
   int N, h, w, C, p_cs, out_cs, w2ld, wo_ld;
 };
 void launch_dlc_fused(const DlcP& p, int dt, cudaStream_t s);
+}  // namespace ysp
+
+namespace ysp {
+// kernels_dlc32.cu -- fused DoubleLightConv tail of the PARITY mode (fp32 activations; pointwise GEMM on tcgen05 with fp16
+// hi/lo operand splits, composite up2 o depthwise on CUDA cores): see the file header
+struct Dlc32P {
+  const void* P;            // low-res NHWC fp32 [N, h, w, 2C] : [0,C) = conv.0.conv1 (BN folded, linear), [C,2C) = residual_conv
+  void* out;                // hi-res NHWC fp32 [N, 2h, 2w, C] or, with head, fp32 [N, 2h, 2w]
+  const float *dw1, *b1;    // conv.0.conv2 depthwise 3x3 [9][C] + bias (SiLU)
+  const void* wpack;        // conv.1.conv1 1x1 in the tc32 weight pack (engine.cu pack_conv_cat, tc32_tiling(C, C, 1))
+  float w_unscale;          // the pack is scaled by a power of two; acc * w_unscale is exact
+  const float* b2;          // conv.1.conv1 bias (linear)
+  const float *dw2, *b3;    // conv.1.conv2 depthwise 3x3 [9][C] + bias (SiLU)
+  const float *wo, *bo;     // optional head: 1x1 C -> 1 (+bias); NULL otherwise
+  int N, h, w, C, p_cs, out_cs, wo_ld;
+  unsigned magic_x = 0, magic_y = 0;   // filled by launch_dlc32
+};
+bool dlc32_supported(int C, bool head);
+void launch_dlc32(const Dlc32P& p, cudaStream_t s);
 }  // namespace ysp
 
 namespace ysp {
