@@ -79,8 +79,9 @@ def test_nms_cfg5_full_sweep(ysp, kind):
     against the plain-C oracle (all host cores)."""
     from oracle import cnms
     pred = make_case(seed=5000 + len(kind), B=1024, nc=1, A=8400, kind=kind)
-    want_d, want_k = cnms.nms_batched(pred, 0.001, 0.7, 300, nthreads=os.cpu_count() or 8)
-    dets, keep = ysp.non_max_suppression(pred.cuda(), 0.001, 0.7, return_idxs=True)
+    conf = 0.25 if kind == "below" else 0.001          # "below": every score is < 0.2, nothing may pass the confidence filter
+    want_d, want_k = cnms.nms_batched(pred, conf, 0.7, 300, nthreads=os.cpu_count() or 8)
+    dets, keep = ysp.non_max_suppression(pred.cuda(), conf, 0.7, return_idxs=True)
     bad = [b for b in range(1024) if not torch.equal(keep[b].view(-1).long().cpu(), want_k[b])
            or not torch.equal(dets[b].cpu().reshape(-1, 6), want_d[b].reshape(-1, 6))]
     assert not bad, f"{kind}: {len(bad)} of 1024 images differ, first {bad[:5]}"
