@@ -69,9 +69,21 @@ __device__ __forceinline__ uint32_t f2h2_sat(float lo_elem, float hi_elem) {
 }
 __device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
   hi = f2h2_sat(a, b);
-  float fa, fb;
-  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(fa), "=f"(fb) : "r"(hi));
-  lo = f2h2_sat(a - fa, b - fb);
+  float2 f;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(f.x), "=f"(f.y) : "r"(hi));
+  const float2 d = __ffma2_rn(f, make_float2(-1.f, -1.f), make_float2(a, b));      // (a - fa, b - fb), exact, one FFMA2
+  lo = f2h2_sat(d.x, d.y);
+}
+// Packed SiLU of two values (FMUL2 / FADD2 around the four MUFU ops): bit-identical to silu_f per lane, 8 instead of 10 issue slots
+__device__ __forceinline__ float2 silu2_f(float2 x) {
+  const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  float2 e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+  const float2 d = __fadd2_rn(e, make_float2(1.f, 1.f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+  return __fmul2_rn(x, r);
 }
 
 template <typename T> __device__ __forceinline__ float silu_for(float x);

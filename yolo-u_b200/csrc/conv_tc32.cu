@@ -287,16 +287,14 @@ conv_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const T32Params p) {
         if (valid && cg < p.Cout_st) {
           const int nvalid = p.Cout_st - cg;
           float f[16];
+          const float2 us2 = make_float2(p.w_unscale, p.w_unscale);
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
+          for (int j4 = 0; j4 < 4; ++j4) {           // packed fp32 (FFMA2 / FMUL2 / FADD2): two channels per issue slot
             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cg + 4 * j4);
-            const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              float x = fmaf(__uint_as_float(v[4 * j4 + jj]), p.w_unscale, bq[jj]);
-              if (p.act == ACT_SILU) x = silu_f(x);
-              f[4 * j4 + jj] = x;
-            }
+            float2 x0 = __ffma2_rn(make_float2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), us2, make_float2(b4.x, b4.y));
+            float2 x1 = __ffma2_rn(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), us2, make_float2(b4.z, b4.w));
+            if (p.act == ACT_SILU) { x0 = silu2_f(x0); x1 = silu2_f(x1); }
+            f[4 * j4] = x0.x; f[4 * j4 + 1] = x0.y; f[4 * j4 + 2] = x1.x; f[4 * j4 + 3] = x1.y;
           }
           if (p.res) {
             const float* rp = p.res + (size_t)pix * p.res_cs + cg;

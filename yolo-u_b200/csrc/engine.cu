@@ -375,10 +375,14 @@ struct Builder {
       }
     }
     Tc32ConvPlan* tcp32 = nullptr;
+    bool halo32 = false;
+    const float w_unscale = dc->w_unscale;
     if (h->tc32() && dc->w_tc && in_dt == DT_F32 && out_dt == DT_F32 && getenv("YSP_NO_TC") == nullptr) {
       ConvP q = p; q.K = dc->Ktc;
       const char* only = getenv("YSP_TC_ONLY");
-      if ((!only || prefix.find(only) != std::string::npos) && tc32_conv_supported(q)) {
+      halo32 = getenv("YSP_NO_HALO") == nullptr && conv_halo32_supported(q);
+      if (halo32) {
+      } else if ((!only || prefix.find(only) != std::string::npos) && tc32_conv_supported(q)) {
         tcp32 = tc32_conv_plan_create(q, dc->w_tc, dc->w_unscale);
         if (tcp32) pl->tc32_plans.push_back(tcp32);
       }
@@ -388,11 +392,12 @@ struct Builder {
       ConvP q = p;
       q.in = pl->ptr(c, in); q.out = pl->ptr(c, out); q.res = has_res ? pl->ptr(c, rres) : nullptr;
       if (halo) launch_conv_halo(q, w_tc, Ktc, c.s);
+      else if (halo32) launch_conv_halo32(q, w_tc, w_unscale, c.s);
       else if (tcp32) launch_conv_tc32(tcp32, q, c.s);
       else if (tcp) launch_conv_tc(tcp, q, c.s);
       else launch_conv_dense(q, in_dt, out_dt, c.s);
     }, {&in, &out, res}, 1,
-    StepInfo{prefix, std::string(halo ? "halo_conv" : tcp32 ? "tc32_conv" : tcp ? "tc_conv" : "conv") + std::to_string(k) + "x" + std::to_string(k) + (s == 2 ? "s2" : ""),
+    StepInfo{prefix, std::string(halo ? "halo_conv" : halo32 ? "halo32_conv" : tcp32 ? "tc32_conv" : tcp ? "tc_conv" : "conv") + std::to_string(k) + "x" + std::to_string(k) + (s == 2 ? "s2" : ""),
              tbytes(in) + tbytes(out) + (res ? tbytes(*res) : 0.0) + (double)dc->K * dc->Cout * ((tcp || halo) ? 2 : 4),
              2.0 * p.M * (double)dc->K * dc->Cout, 1});
   }

@@ -82,6 +82,10 @@ bool tc32_conv_supported(const ConvP& p);
 bool conv_halo_supported(const ConvP& p, int in_dt, int out_dt);
 void launch_conv_halo(const ConvP& p, const void* w_bf16_kmajor, int Ktc, cudaStream_t s);
 
+// conv_halo32.cu (parity mode: halo tile split once + shifted descriptor views, Cin 16 / 32, 3x3 stride 1, maps <= 64 wide)
+bool conv_halo32_supported(const ConvP& p);
+void launch_conv_halo32(const ConvP& p, const void* wpack, float w_unscale, cudaStream_t s);
+
 }  // namespace ysp
 
 namespace ysp {

@@ -55,7 +55,10 @@ __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity)
   asm volatile("{\n\t.reg .pred p;\n\tWL32:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DN32;\n\tbra WL32;\n\tDN32:\n\t}"
                ::"r"(s32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ float4 silu4(const float4& v) { return make_float4(silu_f(v.x), silu_f(v.y), silu_f(v.z), silu_f(v.w)); }
+__device__ __forceinline__ float4 silu4(const float4& v) {
+  const float2 a = silu2_f(make_float2(v.x, v.y)), b = silu2_f(make_float2(v.z, v.w));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
 }
