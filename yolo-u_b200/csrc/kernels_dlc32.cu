@@ -105,7 +105,7 @@ struct Geo {
   static constexpr int P_BYTES = (1 + RESB) * PPITCH;               // conv1 half + RESB buffers of the residual half
   static constexpr int KC = C % 32 == 0 ? 32 : 16;                  // Cin chunk of the tc32 weight pack (tc32_tiling)
   static constexpr int W_BYTES = 2 * C * C * 2;                     // hi + lo
-  static constexpr int T_FLOATS = 4 * 9 * C + 9 * C + 3 * C;        // composite weights [cls][tap][C], dw2 [tap][C], b1, b2, b3
+  static constexpr int T_FLOATS = 4 * 9 * C + 9 * C + 4 * C + 4;    // composite weights [cls][tap][C], dw2 [tap][C], b1, b2, b3, head w + b
   // ALIAS: the c tile lies over the b tiles (dead once every MMA of the tile has completed): less shared memory, one more barrier
   static constexpr int BC_BYTES = ALIAS ? (2 * B_BYTES > C_BYTES ? 2 * B_BYTES : C_BYTES) : 2 * B_BYTES + C_BYTES;
   static constexpr size_t SMEM = (size_t)P_BYTES + BC_BYTES + W_BYTES + T_FLOATS * 4 + 128;
@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) dlc32_kernel(const __grid_consta
   float* sB1 = sWk + 9 * C;                                            // b1, b2 (= c2), b3
   float* sB2 = sB1 + C;
   float* sB3 = sB2 + C;
+  float* sWo = sB3 + C;                                               // head weights [C] + bias (HEAD only)
   __shared__ __align__(8) uint64_t bar[4], pbar[3];                    // MMA row blocks done; TMA: conv1 half, residual buffers 0/1
   __shared__ uint32_t tmem_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -162,7 +163,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) dlc32_kernel(const __grid_consta
     sWc[i] = a;
   }
   for (int i = tid; i < 9 * C; i += kD32Threads) sWk[i] = p.dw2[i];
-  for (int i = tid; i < C; i += kD32Threads) { sB1[i] = p.b1[i]; sB2[i] = p.b2[i]; sB3[i] = p.b3[i]; }
+  for (int i = tid; i < C; i += kD32Threads) { sB1[i] = p.b1[i]; sB2[i] = p.b2[i]; sB3[i] = p.b3[i]; if (HEAD) sWo[i] = p.wo[(size_t)i * p.wo_ld]; }
+  if (HEAD && tid == 0) sWo[C] = p.bo[0];
 
   // phase-B item of this thread: (c4, cx, pX, pY); composite weights in registers
   constexpr int ITEMS_B = 4 * (BW / 2) * C4, PASS_B = (ITEMS_B + kD32Threads - 1) / kD32Threads;
@@ -430,17 +432,26 @@ __global__ void __launch_bounds__(NT, 512 / NT) dlc32_kernel(const __grid_consta
       }
       const int X = X0 + ox;
       if (HEAD) {
-        float4 wo = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) wo = make_float4(p.wo[(c4 * 4 + 0) * p.wo_ld], p.wo[(c4 * 4 + 1) * p.wo_ld], p.wo[(c4 * 4 + 2) * p.wo_ld], p.wo[(c4 * 4 + 3) * p.wo_ld]);
-        const float bo = p.bo[0];
+        // 1x1 head: each of the C4 = 4 lanes of a pixel column holds the partial dot products of its 4 channels for 7 rows.
+        // Butterfly exchange over the lane quad (6 shuffles instead of 14): after the xor-1 step a lane keeps 4 rows, after
+        // the xor-2 step 2 rows, fully reduced -- and the stores are spread over all four lanes.
+        static_assert(!HEAD || C4 == 4, "the head reduction is written for 16 channels");
+        const float4 wo = *reinterpret_cast<const float4*>(sWo + c4 * 4);
+        float part[8];
 #pragma unroll
-        for (int o = 0; o < 7; ++o) {
-          float part = 0.f;
-          if (active) part = acc[o].x * wo.x + acc[o].y * wo.y + acc[o].z * wo.z + acc[o].w * wo.w;
+        for (int o = 0; o < 7; ++o) part[o] = active ? acc[o].x * wo.x + acc[o].y * wo.y + acc[o].z * wo.z + acc[o].w * wo.w : 0.f;
+        part[7] = 0.f;
+        const bool b0 = (lane & 1) != 0, b1 = (lane & 2) != 0;
+        float q4[4], q2[2];
 #pragma unroll
-          for (int off = 1; off < C4; off <<= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-          const int Y = Y0 + chunk * 7 + o;
-          if (active && c4 == 0 && Y < H && X < W) reinterpret_cast<float*>(p.out)[((size_t)n * H + Y) * W + X] = part + bo;
+        for (int i = 0; i < 4; ++i) q4[i] = (b0 ? part[i + 4] : part[i]) + __shfl_xor_sync(0xffffffffu, b0 ? part[i] : part[i + 4], 1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) q2[i] = (b1 ? q4[i + 2] : q4[i]) + __shfl_xor_sync(0xffffffffu, b1 ? q4[i] : q4[i + 2], 2);
+        const int r0 = (b0 ? 4 : 0) + (b1 ? 2 : 0);          // this lane's rows r0, r0 + 1 of the chunk
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int Y = Y0 + chunk * 7 + r0 + i;
+          if (active && r0 + i < 7 && Y < H && X < W) reinterpret_cast<float*>(p.out)[((size_t)n * H + Y) * W + X] = q2[i] + sWo[C];
         }
       } else if (active) {
 #pragma unroll
