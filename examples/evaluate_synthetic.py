@@ -1,6 +1,6 @@
 """The reference's evaluation loop (evaluate_model.py:134-187) on this library, with synthetic volumes.
 
-    python examples/evaluate_synthetic.py [--volumes 4] [--slices 155] [--batch 256] [--mode bf16]
+    python examples/evaluate_synthetic.py [--volumes 4] [--slices 155] [--batch 256] [--mode tc32]
     torchrun --nproc-per-node N examples/evaluate_synthetic.py ...      # contiguous-by-volume shards, ONE metric all-reduce
 
 Per batch: detector -> sigmoid(P3 class logit) bottleneck -> NMS -> YOLO-Seg++ -> sigmoid > 0.5 -> Dice / TP / FP / FN,
@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--volumes", type=int, default=4)
     ap.add_argument("--slices", type=int, default=155)
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default="tc32", choices=["tc32", "bf16", "fp32"])
     args = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)

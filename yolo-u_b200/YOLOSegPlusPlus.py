@@ -91,7 +91,7 @@ class YOLOSegPlusPlus(nn.Module):
     """
 
     def __init__(self, predictor, verbose: bool = False, target_modules_indices: List[int] = [2, 4, 6],
-                 mode: str = "fp32", use_logits: bool = True):
+                 mode: str = "tc32", use_logits: bool = True):
         super().__init__()
         self.encoder = nn.ModuleList(module for module in predictor.model.model.model[0:5])
         for param in self.encoder.parameters():

@@ -12,13 +12,13 @@ from .engine import Engine
 
 
 class B200Detector:
-    def __init__(self, det_state_dict: Mapping[str, torch.Tensor], device="cuda:0", mode: str = "fp32", engine: Engine = None):
+    def __init__(self, det_state_dict: Mapping[str, torch.Tensor], device="cuda:0", mode: str = "tc32", engine: Engine = None):
         self.engine = engine if engine is not None else Engine(device, mode)
         self.engine.load_state_dict("det", det_state_dict)
         self.engine.finalize(det=True, seg=False)
 
     @classmethod
-    def from_predictor(cls, predictor, device="cuda:0", mode: str = "fp32"):
+    def from_predictor(cls, predictor, device="cuda:0", mode: str = "tc32"):
         """predictor.model = AutoBackend; predictor.model.model = DetectionModel (state_dict keys 'model.N...')."""
         return cls(predictor.model.model.state_dict(), device, mode)
 

@@ -20,7 +20,7 @@ from .metrics import dice_from_counts
 
 class Predictor:
     def __init__(self, det_state_dict: Mapping[str, torch.Tensor], seg_state_dict: Mapping[str, torch.Tensor],
-                 device="cuda:0", mode: str = "fp32"):
+                 device="cuda:0", mode: str = "tc32"):
         self.engine = Engine(device, mode)
         self.engine.load_state_dict("det", det_state_dict)
         self.engine.load_state_dict("seg", seg_state_dict)
@@ -28,7 +28,7 @@ class Predictor:
         self._out = {}
 
     @classmethod
-    def from_modules(cls, predictor, segpp, device="cuda:0", mode: str = "fp32"):
+    def from_modules(cls, predictor, segpp, device="cuda:0", mode: str = "tc32"):
         return cls(predictor.model.model.state_dict(), segpp.state_dict(), device, mode)
 
     @torch.no_grad()
