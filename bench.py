@@ -52,78 +52,76 @@ def load_peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  Polls NVML in-process
-    every 10 ms (nvidia_ml_py; the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints) -- a
-    freshly spawned nvidia-smi needs longer to start than a 100-250 ms timed region lasts.  Falls back to nvidia-smi -lms."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  A child process polls NVML
+    every 5 ms for the whole run (nvidia_ml_py: the counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints)
+    and time-stamps every sample; `window(t0, t1)` reports the samples that fall inside a timed region.  (A thread in this
+    process is starved by the launch loop holding the GIL; a freshly spawned nvidia-smi needs longer to start than a 100-250 ms
+    timed region lasts.)"""
     BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
+    CHILD = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+rf = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+while True:
+    try:
+        print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(rf(h)), nv.nvmlDeviceGetPowerUsage(h) / 1e3, flush=True)
+    except Exception:
+        pass
+    time.sleep(0.005)
+"""
 
     def __init__(self, gpu_index: int):
-        self.idx, self.rows, self.proc, self.nv, self.stop_flag = gpu_index, [], None, None, False
-        self.sm, self.mx, self.mask, self.power = [], None, 0, []
+        self.idx, self.rows, self.proc, self.mx = gpu_index, [], None, None
 
     def start(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
             idx = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].strip().isdigit() else self.idx
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
-            self.nv = pynvml
-            self.t = threading.Thread(target=self._poll, daemon=True)
-            self.t.start()
-            return
-        except Exception:
-            self.nv = None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen([sys.executable, "-c", self.CHILD, str(idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
-
-    def _poll(self):
-        while not self.stop_flag:
-            try:
-                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
-                self.mask |= int(self.reasons_fn(self.h))
-                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
-            except Exception:
-                pass
-            time.sleep(0.01)
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            f = line.split()
+            try:
+                if f[0] == "max":
+                    self.mx = float(f[1])
+                else:
+                    self.rows.append((float(f[0]), float(f[1]), int(f[2]), float(f[3])))
+            except (ValueError, IndexError):
+                pass
 
-    def stop(self):
-        if self.nv is not None:
-            self.stop_flag = True
-            self.t.join(1.0)
-            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
-                    "reasons": sorted(n for n, b in self.BITS if self.mask & b), "samples": len(self.sm),
-                    "power_w_max": max(self.power) if self.power else None, "source": "nvml, 10 ms poll inside the timed region"}
+    def window(self, t0: float, t1: float):
+        """Statistics of the samples taken inside [t0, t1] (time.time() stamps of the timed region)."""
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml sampler unavailable"], "samples": 0}
+        time.sleep(0.02)                                  # let the reader thread drain the pipe
+        rows = [r for r in list(self.rows) if t0 <= r[0] <= t1]
+        mask = 0
+        for r in rows:
+            mask |= r[2]
+        return {"sm_mhz": statistics.median(r[1] for r in rows) if rows else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(n for n, b in self.BITS if mask & b), "samples": len(rows),
+                "power_w_max": max(r[3] for r in rows) if rows else None,
+                "source": "nvml polled every 5 ms by a child process; samples inside the timed region only"}
+
+    def stop(self, t0: float = 0.0, t1: float = 1e18):
+        out = self.window(t0, t1)
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(2)
+            except Exception:
+                self.proc.kill()
+            self.proc = None
+        return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -303,6 +301,7 @@ def main_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B, K, Wm = args.batch, args.steps, args.warmup
     peaks = load_peaks()
+    sampler = ClockSampler(local).start() if rank == 0 else None      # polls for the whole run; windows are cut per timed region
 
     det_sd, seg_sd = synth_state_dicts(0)
     det_sd, seg_sd = calibrate(det_sd, seg_sd, device=dev)
@@ -364,20 +363,19 @@ def main_ours(args):
         for i in range(Wm):
             P.predict_raw(xs[i % nbuf], tg)
         barrier()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
         l0 = eng.launches_total
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        tw0 = time.time()
         ev[0].record()
         for i in range(K):
             P.predict_raw(xs[i % nbuf], tg)
             ev[i + 1].record()
         torch.cuda.synchronize()
+        tw1 = time.time()
         ms = ev[0].elapsed_time(ev[K])
         per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(K))
         barrier()
-        rec["clocks"] = sampler.stop() if rank == 0 else None
+        rec["clocks"] = sampler.window(tw0, tw1) if rank == 0 else None
         rec["gpu_launches"] = eng.launches_total - l0
         ms = max_over_ranks(ms)
         rec["ms_per_step"] = ms / K
@@ -488,6 +486,8 @@ def main_ours(args):
         cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{n} batches of 4 slices in {dt:.1f}s (oracle/ CPU restatement, torch CPU fp32, os.cpu_count={os.cpu_count()})"}
 
+    if sampler is not None:
+        sampler.stop()
     if rank == 0:
         line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -540,6 +540,7 @@ def main_eval(args):
         dist.init_process_group("nccl", device_id=dev)
     NV, NS = args.volumes, 155
     B, K, Wm = args.batch, args.steps, args.warmup
+    sampler = ClockSampler(local).start() if rank == 0 else None
     det_sd, seg_sd = calibrate(*synth_state_dicts(0), device=dev)
     P = ysp.Predictor(det_sd, seg_sd, device=dev, mode=args.mode)
     lo, hi = ysp.shard_slices(NV, NS, world, rank)
@@ -607,13 +608,11 @@ def main_eval(args):
             ms, wall = (float(v) for v in t.tolist())
         return res, ms, wall
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = P.engine.launches_total
+    tw0 = time.time()
     res, ms, wall = timed(evaluate_device)
     launches = (P.engine.launches_total - l0) * K // (K + Wm)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(tw0, time.time()) if rank == 0 else None
     res_h, ms_h, wall_h = timed(evaluate_host)
     total = NV * NS
     same = all(res[k] == res_h[k] for k in ("TP", "FP", "FN", "slices")) and abs(res["dice"] - res_h["dice"]) < 1e-12
@@ -655,6 +654,7 @@ def main_train(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, K, Wm = args.batch, args.steps, args.warmup
+    sampler = ClockSampler(local).start() if rank == 0 else None
     _, seg_sd = synth_state_dicts(0)
     tr = SegHeadTrainer(seg_sd, batch_size=B, image_size=H, lr=1e-4, epochs=100, loss=args.loss, device=dev,
                         encoder_mode=args.mode)
@@ -674,18 +674,17 @@ def main_train(args):
     for i in range(Wm):
         tr.step(xs[i % nbuf], tg, lgs[i % nbuf])
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
     e0.record()
     for i in range(K):
         loss, _ = tr.step(xs[i % nbuf], tg, lgs[i % nbuf])
     e1.record()
     torch.cuda.synchronize()
+    tw1 = time.time()
     ms = e0.elapsed_time(e1)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -759,6 +758,7 @@ def main_nms(args):
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
     B, A, K, Wm = 1024, 8400, args.steps, args.warmup
+    sampler = ClockSampler(0).start()
     g = torch.Generator().manual_seed(5)
 
     def make():
@@ -784,16 +784,16 @@ def main_nms(args):
     for i in range(Wm):
         run(preds[i % 3])
     torch.cuda.synchronize()
-    sampler = ClockSampler(0)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
     e0.record()
     for i in range(K):
         run(preds[i % 3])
     e1.record()
     torch.cuda.synchronize()
+    tw1 = time.time()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(tw0, tw1)
     kept = int(oc.sum())
     # end to end through the public call
     for i in range(2):

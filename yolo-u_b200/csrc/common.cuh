@@ -103,6 +103,8 @@ struct ConvP {
   int cout_store;           // >= Cout: channels [Cout, cout_store) are written as act(0) = 0 (zero channel padding)
   int in_zpad;              // input view has zero-filled channels up to a multiple of 16 (tensor-core K padding)
   int in_pw, in_ph;         // memory pitch of the input view in pixels (0 = dense H x W); tensor-core path only
+  const float* in_scale;    // optional per-(slice, input channel) factor [N][Cin] applied to the input on load (the ECA gate);
+                            // conv_tc32 flat 1x1 path only
 };
 
 struct DwP {

@@ -45,6 +45,7 @@ struct T32Params {
   uint32_t idesc, stg_bytes, op_bytes, b_bytes, slot_bytes;
   int S1, S2, tmem_cols;
   int w_resident; uint32_t w_bytes;
+  const float* in_scale; int sc_hw, sc_c;   // optional input factor [N][sc_c] per slice of sc_hw pixels (flat 1x1 only): the ECA gate
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -103,6 +104,32 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 
 constexpr int kMaxS = 8;
 
+// One converter thread, one k-iteration: its fp32 row of KC channels in the (swizzled) staging slot -> fp16 hi / lo rows of the
+// operand tiles.  KC is a template parameter so that all 16-byte loads are issued before the first conversion.
+template <int KC, bool SCALE>
+__device__ __forceinline__ void convert_row(const uint8_t* src, uint8_t* dh, uint32_t xr, const float* sc) {
+  constexpr int NG = KC / 8;
+  uint8_t* dl = dh + 128u * KC * 2u;
+  float4 v[2 * NG];
+#pragma unroll
+  for (int i = 0; i < 2 * NG; ++i) v[i] = *reinterpret_cast<const float4*>(src + (((uint32_t)i ^ xr) << 4));
+  if (SCALE) {
+#pragma unroll
+    for (int i = 0; i < 2 * NG; ++i) {
+      const float4 f = *reinterpret_cast<const float4*>(sc + 4 * i);
+      v[i].x *= f.x; v[i].y *= f.y; v[i].z *= f.z; v[i].w *= f.w;
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    uint4 h, l;
+    split2(v[2 * g].x, v[2 * g].y, h.x, l.x); split2(v[2 * g].z, v[2 * g].w, h.y, l.y);
+    split2(v[2 * g + 1].x, v[2 * g + 1].y, h.z, l.z); split2(v[2 * g + 1].z, v[2 * g + 1].w, h.w, l.w);
+    *reinterpret_cast<uint4*>(dh + g * 2048) = h;
+    *reinterpret_cast<uint4*>(dl + g * 2048) = l;
+  }
+}
+
 }  // namespace
 
 struct Tc32ConvPlan {
@@ -116,6 +143,9 @@ struct Tc32ConvPlan {
 
 constexpr int kT32Threads = 320;   // warp0 TMA, warp1 MMA, warps 2-5 converters, warps 6-9 epilogue
 
+// SCALE: the converter multiplies its fp32 row by a per-(slice, channel) factor (the folded ECA gate); a separate instantiation
+// so the common path carries neither the branch nor the registers (the runtime-branch version slowed EVERY conv by 5-8 %)
+template <bool SCALE>
 __global__ void __launch_bounds__(kT32Threads, 2)
 conv_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const T32Params p) {
   extern __shared__ uint8_t smem_raw32[];
@@ -228,25 +258,22 @@ conv_tc32_kernel(const __grid_constant__ CUtensorMap tmA, const T32Params p) {
     const int r = (warp - 2) * 32 + lane;
     const uint32_t row_bytes = (uint32_t)p.Kc * 4u;             // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
     const uint32_t xr = ((r * row_bytes) >> 7) & ((row_bytes >> 4) - 1u);
-    const int ngrp = p.Kc >> 3;
     int s = 0, t = 0; uint32_t ph_s = 0, ph_t = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const float* scrow = nullptr;                             // this row's ECA gate vector (flat 1x1 convs only)
+      if (SCALE) {
+        long long pix = (long long)(tile / p.n_tiles_n) * 128 + r;
+        if (pix >= p.M) pix = p.M - 1;
+        scrow = p.in_scale + (size_t)(pix / p.sc_hw) * p.sc_c;
+      }
       for (int it = 0; it < kiters; ++it) {
         mbar_wait(&full_bar[s], ph_s);
         mbar_wait(&opfree_bar[t], ph_t ^ 1);
         tc_fence_after();
         const uint8_t* src = stg + (size_t)s * p.stg_bytes + (size_t)r * row_bytes;
         uint8_t* dh = ops + (size_t)t * p.slot_bytes + (size_t)r * 16;
-        uint8_t* dl = dh + 128u * p.Kc * 2u;
-        for (int g = 0; g < ngrp; ++g) {
-          const float4 v0 = *reinterpret_cast<const float4*>(src + (((uint32_t)(2 * g) ^ xr) << 4));
-          const float4 v1 = *reinterpret_cast<const float4*>(src + (((uint32_t)(2 * g + 1) ^ xr) << 4));
-          uint4 h, l;
-          split2(v0.x, v0.y, h.x, l.x); split2(v0.z, v0.w, h.y, l.y);
-          split2(v1.x, v1.y, h.z, l.z); split2(v1.z, v1.w, h.w, l.w);
-          *reinterpret_cast<uint4*>(dh + (size_t)g * 2048) = h;
-          *reinterpret_cast<uint4*>(dl + (size_t)g * 2048) = l;
-        }
+        if (p.Kc == 32) convert_row<32, SCALE>(src, dh, xr, SCALE ? scrow + it * 32 : nullptr);
+        else convert_row<16, SCALE>(src, dh, xr, SCALE ? scrow + it * 16 : nullptr);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) { mbar_arrive(&sfree_bar[s]); mbar_arrive(&opfull_bar[t]); }
@@ -459,6 +486,7 @@ Tc32ConvPlan* tc32_conv_plan_create(const ConvP& c, const void* wpack, float w_u
   p.bias = c.bias; p.res_cs = c.res_cs; p.out_cs = c.out_cs; p.act = c.act;
   p.wpack = reinterpret_cast<const uint8_t*>(wpack);
   p.w_unscale = w_unscale;
+  p.in_scale = nullptr; p.sc_hw = c.H * c.W; p.sc_c = c.Cin;
   pl->in_cs = c.in_cs; pl->H = c.H; pl->W = c.W; pl->NB = c.N;
   pl->pw = c.in_pw ? c.in_pw : c.W; pl->ph = c.in_ph ? c.in_ph : c.H;
   pl->smem = (size_t)p.w_bytes + (size_t)p.S1 * p.stg_bytes + (size_t)p.S2 * p.slot_bytes + 1024;
@@ -467,16 +495,20 @@ Tc32ConvPlan* tc32_conv_plan_create(const ConvP& c, const void* wpack, float w_u
   pl->grid = total < ctas_per_sm * num_sms32() ? total : ctas_per_sm * num_sms32();
   if (pl->smem > 224 * 1024) { delete pl; return nullptr; }
   static unsigned long long attr_done = 0;
-  ensure_dyn_smem(conv_tc32_kernel, 224 * 1024, attr_done, "conv_tc32_kernel");
+  ensure_dyn_smem(conv_tc32_kernel<false>, 224 * 1024, attr_done, "conv_tc32_kernel");
+  static unsigned long long attr_done_s = 0;
+  ensure_dyn_smem(conv_tc32_kernel<true>, 224 * 1024, attr_done_s, "conv_tc32_kernel<scale>");
   return pl;
 }
 
 void tc32_conv_plan_destroy(Tc32ConvPlan* p) { delete p; }
+bool tc32_conv_plan_flat(const Tc32ConvPlan* p) { return p && p->p.flat != 0; }
 
 void launch_conv_tc32(const Tc32ConvPlan* pl, const ConvP& c, cudaStream_t s) {
   if (pl->last_in != c.in && !encode_A32(pl, c.in)) return;
   T32Params p = pl->p;
   p.res = reinterpret_cast<const float*>(c.res); p.out = reinterpret_cast<float*>(c.out);
+  p.in_scale = p.flat ? c.in_scale : nullptr;
   static const bool no_pdl = getenv("YSP_NO_PDL") != nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl->grid); cfg.blockDim = dim3(kT32Threads); cfg.dynamicSmemBytes = pl->smem; cfg.stream = s;
@@ -484,7 +516,8 @@ void launch_conv_tc32(const Tc32ConvPlan* pl, const ConvP& c, cudaStream_t s) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
-  cudaLaunchKernelEx(&cfg, conv_tc32_kernel, pl->tmA, p);
+  if (p.in_scale) cudaLaunchKernelEx(&cfg, conv_tc32_kernel<true>, pl->tmA, p);
+  else cudaLaunchKernelEx(&cfg, conv_tc32_kernel<false>, pl->tmA, p);
 }
 
 }  // namespace ysp

@@ -270,6 +270,8 @@ static int pack_vec(ysp_handle* h, const std::string& key, float** out) {
 enum { X_IMG = 0, X_Y = 1, X_P3 = 2, X_P4 = 3, X_P5 = 4, X_LOGITS = 5, X_OUT = 6, X_BOTT = 7, X_IMG_U8 = 8, X_E1 = 9 };
 
 struct Builder {
+  std::map<int, TRef> pending_gate;          // buffer id -> ECA gate [N][C] not yet applied: the consumer conv folds it into its operand load
+  int folding_buf = -1;                      // buffer whose pending gate the op being emitted applies
   ysp_handle* h; Plan* plan; int dt; std::string ns; double bn_eps; int rc = 0;
   int cur_lane = 0, cur_region = 0;
   // independent branches: fork(); lane(k); ...; lane(j); ...; join();  -- steps in different lanes may run concurrently
@@ -303,7 +305,12 @@ struct Builder {
   static double tbytes(const TRef& t) { return (double)t.N * t.H * t.W * t.C * esize(t.dt); }
   void emit(std::function<void(RunCtx&)> f, std::initializer_list<const TRef*> uses, int nlaunch = 1,
             StepInfo info = StepInfo()) {
-    for (auto* t : uses) if (t) touch(*t);
+    for (auto* t : uses) {
+      if (!t) continue;
+      if (t->buf >= 0 && pending_gate.count(t->buf) && t->buf != folding_buf && !rc)
+        rc = fail(YSP_EINVAL, "step %s reads a tensor whose ECA gate is still pending (only a flat tc32 1x1 conv can fold it)", info.name.c_str());
+      touch(*t);
+    }
     plan->steps.push_back(std::move(f));
     plan->lane.push_back(cur_region ? cur_lane : 0);
     plan->region.push_back(cur_region);
@@ -387,20 +394,31 @@ struct Builder {
         if (tcp32) pl->tc32_plans.push_back(tcp32);
       }
     }
+    TRef gate; bool has_gate = false;
+    if (in.buf >= 0 && pending_gate.count(in.buf)) {
+      if (!tcp32 || !tc32_conv_plan_flat(tcp32) || in.co != 0 || in.C != pending_gate[in.buf].C) {
+        rc = fail(YSP_EINVAL, "conv %s: its input carries a pending ECA gate but the conv is not a flat tc32 1x1 conv", prefix.c_str());
+        return;
+      }
+      gate = pending_gate[in.buf]; has_gate = true;
+      folding_buf = in.buf;
+    }
     if ((in.pw || in.ph) && !tcp && !halo && !tcp32) { rc = fail(YSP_EINVAL, "conv %s: pitched input needs the tensor-core path", prefix.c_str()); return; }
     emit([=](RunCtx& c) {
       ConvP q = p;
       q.in = pl->ptr(c, in); q.out = pl->ptr(c, out); q.res = has_res ? pl->ptr(c, rres) : nullptr;
+      q.in_scale = has_gate ? (const float*)pl->ptr(c, gate) : nullptr;
       if (halo) launch_conv_halo(q, w_tc, Ktc, c.s);
       else if (halo32) launch_conv_halo32(q, w_tc, w_unscale, c.s);
       else if (tcp32) launch_conv_tc32(tcp32, q, c.s);
       else if (tcp) launch_conv_tc(tcp, q, c.s);
       else launch_conv_dense(q, in_dt, out_dt, c.s);
-    }, {&in, &out, res}, 1,
+    }, {&in, &out, res, has_gate ? &gate : nullptr}, 1,
     StepInfo{prefix, std::string(halo ? "halo_conv" : halo32 ? "halo32_conv" : tcp32 ? "tc32_conv" : tcp ? "tc_conv" : "conv") + std::to_string(k) + "x" + std::to_string(k) + (s == 2 ? "s2" : ""),
              tbytes(in) + tbytes(out) + (res ? tbytes(*res) : 0.0) + (double)dc->K * dc->Cout * ((tcp || halo) ? 2 : 4),
              2.0 * p.M * (double)dc->K * dc->Cout, 1});
-  }
+    if (has_gate) { pending_gate.erase(in.buf); folding_buf = -1; }      // applied: later readers would see the UNscaled tensor,
+  }                                                                        // so there must be none (checked in emit for pending ones)
 
   void dw(const std::string& prefix, TRef in, TRef out, int k, int act, const TRef* res = nullptr, int grp = 0,
           int grp_stride = 0) {
@@ -451,6 +469,19 @@ struct Builder {
     if ((rc = pack_vec(h, ns + "." + key, &w3))) return;
     TRef mean = alloc(x.N, 1, 1, x.C, DT_F32);
     Plan* pl = plan; int d = dt;
+    // Parity mode with the fused decoder: only the gate is computed here; the one consumer of the scaled tensor (the low-res
+    // [conv1 | residual] GEMM of the next DoubleLightConv) multiplies by it while converting its operands, so the
+    // read-modify-write pass over the tensor disappears.  YSP_NO_ECA_FOLD=1: the two-pass form.
+    if (h->tc32() && x.buf >= 0 && x.co == 0 && eca_gate_f32_supported(x.C, x.cs) && getenv("YSP_NO_ECA_FOLD") == nullptr &&
+        getenv("YSP_NO_FUSE") == nullptr && getenv("YSP_NO_TC") == nullptr) {
+      folding_buf = x.buf;
+      emit([=](RunCtx& c) {
+        launch_eca_gate_f32(pl->ptr(c, x), x.N, x.H * x.W, x.C, x.cs, w3, (float*)pl->ptr(c, mean), c.s);
+      }, {&x, &mean}, 1, StepInfo{key, "eca_gate", tbytes(x), 1.0 * x.N * x.H * x.W * x.C, 1});
+      folding_buf = -1;
+      pending_gate[x.buf] = mean;
+      return;
+    }
     emit([=](RunCtx& c) {
       launch_eca(pl->ptr(c, x), x.N, x.H * x.W, x.C, x.cs, w3, (float*)pl->ptr(c, mean), d, c.s);
     }, {&x, &mean}, 2, StepInfo{key, "eca", 3.0 * tbytes(x), 2.0 * x.N * x.H * x.W * x.C, 2});

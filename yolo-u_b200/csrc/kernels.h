@@ -13,6 +13,9 @@ void launch_add(const EwP& p, int dt, cudaStream_t s);                       // 
 void launch_up_nearest2(const EwP& p, int dt, cudaStream_t s);               // out[oy,ox] = a[oy/2,ox/2]
 void launch_up_bilinear2(const EwP& p, int dt, cudaStream_t s);              // torch bilinear x2, align_corners=False
 void launch_eca(void* x, int N, int HW, int C, int cs, const float* w3, float* mean_ws, int dt, cudaStream_t s);
+// ECA gate only (fp32): gate[n][c] = sigmoid(conv1d_k3(mean_hw(x)));  the consumer applies it (ConvP::in_scale)
+bool eca_gate_f32_supported(int C, int cs);
+void launch_eca_gate_f32(const void* x, int N, int HW, int C, int cs, const float* w3, float* gate, cudaStream_t s);
 void launch_attention(const void* qkv, void* out, int B, int Ntok, int C, int heads, int area, int qkv_cs,
                       int out_cs, int dt, cudaStream_t s);
 void launch_nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, int out_cs, int dt, cudaStream_t s);
@@ -75,6 +78,7 @@ Tc32Tiling tc32_tiling(int Cin, int Cout, int taps);   // block shape of the pac
 struct Tc32ConvPlan;
 Tc32ConvPlan* tc32_conv_plan_create(const ConvP& p, const void* wpack, float w_unscale);
 void tc32_conv_plan_destroy(Tc32ConvPlan*);
+bool tc32_conv_plan_flat(const Tc32ConvPlan*);          // flat 1x1 path (the only one that applies ConvP::in_scale)
 void launch_conv_tc32(const Tc32ConvPlan* plan, const ConvP& p, cudaStream_t s);
 bool tc32_conv_supported(const ConvP& p);
 

@@ -593,6 +593,47 @@ __global__ void __launch_bounds__(512) eca_gate_bf16_kernel(const bf16* __restri
     gate[(size_t)blockIdx.x * C + c] = sigmoid_f(z);
   }
 }
+// fp32 twin of eca_gate_bf16_kernel (parity mode): one CTA per slice pools with 16-byte loads (4 channels per thread) and
+// finishes mean -> conv1d k3 -> sigmoid itself.  The consumer conv multiplies by the gate while it converts its operands
+// (conv_tc32.cu, ConvP::in_scale), so the scaled tensor is never written.
+__global__ void __launch_bounds__(512) eca_gate_f32_kernel(const float* __restrict__ x, int HW, int C, int cs,
+                                                           const float* __restrict__ w3, float* gate) {
+  pdl_sync();
+  extern __shared__ float esm32[];             // [lanes][C] partial sums, then [C] means
+  const int G = C >> 2, lanes = blockDim.x / G;
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  const float* xb = x + (size_t)blockIdx.x * HW * cs + g * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane < lanes) {
+    int i = lane;
+    for (; i + 3 * lanes < HW; i += 4 * lanes) {           // four independent 16-byte loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(xb + (size_t)(i + u * lanes) * cs);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+    }
+    for (; i < HW; i += lanes) {
+      const float4 v = *reinterpret_cast<const float4*>(xb + (size_t)i * cs);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(esm32 + lane * C + g * 4) = a;
+  }
+  __syncthreads();
+  float* mean = esm32 + lanes * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += esm32[l * C + c];
+    mean[c] = t / (float)HW;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float z = w3[1] * mean[c];
+    if (c > 0) z += w3[0] * mean[c - 1];
+    if (c + 1 < C) z += w3[2] * mean[c + 1];
+    gate[(size_t)blockIdx.x * C + c] = sigmoid_f(z);
+  }
+}
 __global__ void __launch_bounds__(256) eca_scale_bf16_kernel(bf16* x, int HW, int C, int cs, const float* __restrict__ gate,
                                                              unsigned total) {
   pdl_sync();
@@ -628,6 +669,12 @@ void launch_eca(void* x, int N, int HW, int C, int cs, const float* w3, float* m
     launch_pdl(eca_mean_kernel<bf16>, g, dim3(256), 0, s, (const bf16*)x, HW, C, cs, mean_ws);
     launch_pdl(eca_scale_kernel<bf16>, dim3(cdiv(total, 256)), dim3(256), 0, s, (bf16*)x, HW, C, cs, (const float*)mean_ws, w3, total);
   }
+}
+
+bool eca_gate_f32_supported(int C, int cs) { return C % 4 == 0 && cs % 4 == 0 && C <= 512; }
+void launch_eca_gate_f32(const void* x, int N, int HW, int C, int cs, const float* w3, float* gate, cudaStream_t s) {
+  const int G = C >> 2, lanes = 512 / G;
+  launch_pdl(eca_gate_f32_kernel, dim3(N), dim3(512), (size_t)(lanes + 1) * C * 4, s, (const float*)x, HW, C, cs, w3, gate);
 }
 
 // =====================================================================================================================
