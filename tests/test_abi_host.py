@@ -43,6 +43,19 @@ def test_library_sass_is_blackwell_native():
     assert "sm_100a" in sass
     for mnemonic, least in (("UTCHMMA", 100), ("UTMALDG", 4), ("LDTM", 8), ("UTCBAR", 4), ("LDGSTS", 8), ("FFMA2", 100)):
         assert len(re.findall(r"\b" + mnemonic + r"\b", sass)) >= least, mnemonic
+    # per kernel: every conv / decoder / attention kernel of the two tensor-core modes issues tcgen05 MMAs (UTCHMMA) and reads
+    # its accumulators from TMEM (LDTM); the parity-mode kernels convert with the saturating F2FP
+    per_fn = {}
+    for blk in sass.split("Function : ")[1:]:
+        per_fn[blk.split("\n", 1)[0].strip()] = blk
+    for kern in ("conv_tc32_kernel", "conv_halo32_kernel", "dlc32_kernel", "attention_tc_kernel", "conv_tc_kernel", "conv_halo_kernel",
+                 "dlc_tc_kernel"):
+        bodies = [b for n, b in per_fn.items() if kern in n]
+        assert bodies, f"no SASS for {kern}"
+        for b in bodies:
+            assert "UTCHMMA" in b and "LDTM" in b, kern
+    assert all("F2FP.SATFINITE" in b for n, b in per_fn.items() if "conv_tc32_kernel" in n or "dlc32_kernel" in n)
+    assert any("UTMALDG" in b for n, b in per_fn.items() if "dlc32_kernel" in n)            # dlc32's P tiles arrive by TMA
 
 
 def test_library_has_no_work_skipping_switch():

@@ -74,7 +74,14 @@ def non_max_suppression(prediction, conf_thres: float = 0.25, iou_thres: float =
 
 class TorchNMS:
     """nms.py:169-337.  `nms` and `batched_nms` run ysp_nms_core; `fast_nms` (an approximate variant the pipeline
-    never calls) is out of scope."""
+    never calls) is out of scope.
+
+    Semantics pinned to `torchvision.ops.nms` (the back end `non_max_suppression` takes whenever torchvision is imported,
+    nms.py:151-154, which is the case in evaluate_model.py): stable descending sort (ties -> lower index first) and a box is
+    suppressed iff IoU > threshold.  For a degenerate pair (both boxes of zero area: union 0, IoU = 0/0 = NaN) the
+    comparison is false and the box is KEPT, as torchvision does; the reference's own pure-torch `TorchNMS.nms` keeps
+    `iou <= thr` (nms.py:288-294) and would therefore drop it, and it breaks score ties with an unstable argsort
+    (SURVEY F7).  Zero-area duplicate boxes are the only inputs on which the two differ for distinct scores."""
 
     @staticmethod
     def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torch.Tensor:
