@@ -26,22 +26,20 @@ namespace ysp {
 
 namespace {
 
-constexpr int TH = 14, TW = 30;            // output tile (hi-res pixels)
-constexpr int AR = 18, AP = 34;            // u tile: rows, pitch (pixels); b tile uses the same pitch and 18 rows
-constexpr int XR = 11, XC = 19;            // low-res x tile incl. halo
+// Tile geometry for NBLK column blocks of 8 pixels (NBLK = 4: 14 x 30 outputs, 320 threads; NBLK = 2: 14 x 14 outputs, 160 threads
+// and twice as many co-resident CTAs -- the CTA-wide barriers between the phases then synchronise half as many warps)
+constexpr int TH = 14;                     // output rows per tile
+constexpr int AR = 18;                     // u / b tile rows
+constexpr int XR = 11;                     // low-res x tile rows incl. halo
+__host__ __device__ constexpr int tw_of(int nblk) { return 8 * nblk - 2; }       // output columns
+__host__ __device__ constexpr int ap_of(int nblk) { return 8 * nblk + 2; }       // u / b tile pitch (pixels)
+__host__ __device__ constexpr int xc_of(int nblk) { return tw_of(nblk) / 2 + 4; } // low-res x tile columns
 // Bytes of one 8-channel plane of the u / b tile (= the descriptors' LBO).  With 8 planes (CIN = 64) the pitch is padded by
 // 16 B so that the 8 lanes of a quarter-warp, which write the 8 planes of one pixel in phase 1, hit 8 different 16-byte
 // bank groups (unpadded: 9792 = 64 mod 128 -> 4-way conflicts; ncu r6: 22.6 M store wavefronts for 5.6 M ideal).
-__host__ __device__ constexpr int plane_bytes(int cin) { return AR * AP * 16 + (cin == 64 ? 16 : 0); }
+__host__ __device__ constexpr int plane_bytes(int cin, int nblk) { return AR * ap_of(nblk) * 16 + (cin == 64 ? 16 : 0); }
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
-}
-__device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
-}
 // Descriptor = {lo: start>>4 | (LBO>>4)<<16, hi: SBO>>4 | version<<14}.  Only the start address changes between the MMAs
 // of a tile, by compile-time byte offsets: the issuing thread adds (offset >> 4) to the low word -- one IADD per operand.
 __device__ __forceinline__ void umma2(uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, bool acc) {
@@ -102,12 +100,15 @@ __device__ __forceinline__ uint4 lerp8(const uint4& a, __nv_bfloat162 wa, const 
 #define PROBE(bit) false
 #endif
 
-constexpr int kDlcThreads = 320;            // warps 0-7: CUDA-core phases + epilogues; warps 8-9: MMA issue
+// warps 0 .. 2 NBLK - 1: CUDA-core phases + epilogues; then ISSUERS MMA-issue warps (a whole number of warps: 320 / 160 threads)
+__host__ __device__ constexpr int dlc_threads(int nblk) { return 32 * (2 * nblk + (nblk == 4 ? 2 : 1)); }
 
-template <int CIN, int C, bool HEAD>
-__global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(DlcTcP p) {
+template <int CIN, int C, bool HEAD, int NBLK>
+__global__ void __launch_bounds__(dlc_threads(NBLK), (C <= 16 ? 2 : 1) * (4 / NBLK)) dlc_tc_kernel(DlcTcP p) {
+  constexpr int kDlcThreads = dlc_threads(NBLK), EW = 2 * NBLK;      // EW = epilogue / CUDA-core warps
+  constexpr int TW = tw_of(NBLK), AP = ap_of(NBLK), XC = xc_of(NBLK);
   constexpr int KP1 = CIN / 8, KP2 = C / 8;          // 8-channel planes of u and of b
-  constexpr int PLANE = plane_bytes(CIN);
+  constexpr int PLANE = plane_bytes(CIN, NBLK);
   constexpr int W1B = 9 * KP1 * C * 16, W2B = 9 * KP2 * C * 16, WRB = KP1 * C * 16;
   extern __shared__ __align__(128) uint8_t dsm[];
   uint8_t* sU = dsm;                                 // [KP1][AR][AP] x 16 B
@@ -123,8 +124,8 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
   __shared__ __align__(8) uint64_t bar1[4], bar2[4];   // per column block: conv1(+residual) done / conv2 done
   __shared__ uint32_t tmem_s;
   // TMEM columns: D1[h][r] (h = column block, r = tap row: three independent accumulation chains, summed in the epilogue --
-  // a chain of tiny dependent MMAs costs ~190 cycles per link) at (3h + r) * C, re-used for D2[h][r]; Dr[h] at (12 + h) * C
-  constexpr uint32_t TCOLS = 16 * C <= 256 ? 256 : 512;
+  // a chain of tiny dependent MMAs costs ~190 cycles per link) at (3h + r) * C, re-used for D2[h][r]; Dr[h] at (3 NBLK + h) * C
+  constexpr uint32_t TCOLS = 4 * NBLK * C <= 32 ? 32 : (4 * NBLK * C <= 64 ? 64 : (4 * NBLK * C <= 128 ? 128 : (4 * NBLK * C <= 256 ? 256 : 512)));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = 2 * p.h, W = 2 * p.w;
   const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
@@ -239,10 +240,10 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
   // ---- phase 2: conv1 (D1[h][r], h = 8-pixel column block of the 16 x 32 b region) and the residual 1x1 (Dr[h]),
   //      issued block by block by warp 8 with one commit per block, so the epilogue of block h (warps 0-7 below)
   //      overlaps the MMAs of blocks h+1..  All descriptors are base + compile-time offset. ----
-  constexpr int ISSUERS = C <= 16 ? 1 : 2;            // wide layers need two issuing threads to keep the tensor pipe fed
-  if (warp >= 8 && warp < 8 + ISSUERS && lane == 0) {
+  constexpr int ISSUERS = (C <= 16 || NBLK < 4) ? 1 : 2;   // wide layers need two issuing threads to keep the tensor pipe fed
+  if (warp >= EW && warp < EW + ISSUERS && lane == 0) {
 #pragma unroll
-    for (int h = warp - 8; h < 4; h += ISSUERS) {
+    for (int h = warp - EW; h < NBLK; h += ISSUERS) {
       const uint32_t a_lo = ((s32(sU) & 0x3FFFF) >> 4) + (uint32_t)(8 * h) + (((uint32_t)PLANE >> 4) << 16);
       const uint32_t w_lo = ((s32(sW1) & 0x3FFFF) >> 4) + (((uint32_t)(C * 16) >> 4) << 16);
       const uint32_t r_lo = ((s32(sWr) & 0x3FFFF) >> 4) + (((uint32_t)(C * 16) >> 4) << 16);
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       }
 #pragma unroll
       for (int ks = 0; ks < CIN / 16; ++ks)            // residual: output pixel (oy, ox) <-> u(oy + 2, ox + 2)
-        umma2(tmem + (12 + h) * C, a_lo + (((2 * ks) * PLANE) >> 4) + 2 * AP + 2, a_hi, r_lo + (((2 * ks) * C * 16) >> 4), b_hi, idesc, ks != 0);
+        umma2(tmem + (3 * NBLK + h) * C, a_lo + (((2 * ks) * PLANE) >> 4) + 2 * AP + 2, a_hi, r_lo + (((2 * ks) * C * 16) >> 4), b_hi, idesc, ks != 0);
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar1[h])) : "memory");
     }
   }
@@ -266,8 +267,8 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
   const int row = q * 32 + lane;                      // M row: (by = row / 8, bxl = row % 8)
   const int by = row >> 3, bxl = row & 7;
 #pragma unroll 1
-  for (int hh = 0; hh < 2 && warp < 8; ++hh) {
-    const int h = (warp >> 2) + 2 * hh;               // blocks complete in order 0,1,2,3: warps 0-3 take 0 and 2, warps 4-7 take 1 and 3
+  for (int hh = 0; hh < 2 && warp < EW; ++hh) {
+    const int h = (warp >> 2) + (EW / 4) * hh;        // blocks complete in order: NBLK = 4: warps 0-3 take 0 and 2, warps 4-7 take 1 and 3
     mbar_wait_parity(&bar1[h], tpar);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int bx = 8 * h + bxl;
@@ -304,10 +305,10 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
   __syncthreads();
 
   // ---- phase 4: conv2 on the b tile: D2[h][r], output pixel (oy, 8h + oxl) <-> b(oy + r, 8h + oxl + s) ----
-  if (warp >= 8 && warp < 8 + ISSUERS && lane == 0) {
+  if (warp >= EW && warp < EW + ISSUERS && lane == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-    for (int h = warp - 8; h < 4; h += ISSUERS) {
+    for (int h = warp - EW; h < NBLK; h += ISSUERS) {
       const uint32_t a_lo = ((s32(sB) & 0x3FFFF) >> 4) + (uint32_t)(8 * h) + (((uint32_t)PLANE >> 4) << 16);
       const uint32_t w_lo = ((s32(sW2) & 0x3FFFF) >> 4) + (((uint32_t)(C * 16) >> 4) << 16);
 #pragma unroll
@@ -328,8 +329,8 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
   // ---- phase 5: epilogue 2: out = SiLU(D2 + bias_eff2) + Dr + cr;  head: logit = wo . out + bo ----
   const int oy = by, oxl = bxl;
 #pragma unroll 1
-  for (int hh = 0; hh < 2 && warp < 8; ++hh) {
-    const int h = (warp >> 2) + 2 * hh;
+  for (int hh = 0; hh < 2 && warp < EW; ++hh) {
+    const int h = (warp >> 2) + (EW / 4) * hh;
     mbar_wait_parity(&bar2[h], tpar);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int ox = 8 * h + oxl;
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(kDlcThreads, C <= 16 ? 2 : 1) dlc_tc_kernel(Dl
       ld16(tmem + ((uint32_t)(q * 32) << 16) + (3 * h) * C + c0, v);
       ld16(tmem + ((uint32_t)(q * 32) << 16) + (3 * h + 1) * C + c0, v1);
       ld16(tmem + ((uint32_t)(q * 32) << 16) + (3 * h + 2) * C + c0, v2);
-      ld16(tmem + ((uint32_t)(q * 32) << 16) + (12 + h) * C + c0, rsd);
+      ld16(tmem + ((uint32_t)(q * 32) << 16) + (3 * NBLK + h) * C + c0, rsd);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       float f[16];
 #pragma unroll
@@ -443,18 +444,26 @@ bool dlc_tc_supported(int Cin, int C, bool head) {
   return (Cin == 32 && C == 16 && head) || (Cin == 64 && C == 32 && !head);
 }
 
-template <int CIN, int C, bool HEAD>
-static void dlc_tc_launch(const DlcTcP& p, cudaStream_t s) {
-  constexpr size_t smem = (size_t)(CIN / 8 + C / 8) * plane_bytes(CIN) + (size_t)XR * XC * CIN * 2 +
+template <int CIN, int C, bool HEAD, int NBLK>
+static void dlc_tc_launch(DlcTcP p, cudaStream_t s) {
+  constexpr int TW = tw_of(NBLK), XC = xc_of(NBLK);
+  constexpr size_t smem = (size_t)(CIN / 8 + C / 8) * plane_bytes(CIN, NBLK) + (size_t)XR * XC * CIN * 2 +
                           (size_t)(9 * (CIN / 8) * C * 8 + 9 * (C / 8) * C * 8 + (CIN / 8) * C * 8) * 2 + (size_t)20 * C * 4 + 128;
   static unsigned long long attr_done = 0;
-  ensure_dyn_smem(dlc_tc_kernel<CIN, C, HEAD>, smem, attr_done, "dlc_tc_kernel");
+  ensure_dyn_smem(dlc_tc_kernel<CIN, C, HEAD, NBLK>, smem, attr_done, "dlc_tc_kernel");
   const int H = 2 * p.h, W = 2 * p.w;
-  const int tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH) * p.N;
+  const unsigned txs = (W + TW - 1) / TW, tys = (H + TH - 1) / TH;
+  p.magic_x = txs > 1 ? (unsigned)((0x100000000ull + txs - 1) / txs) : 0u;
+  p.magic_y = tys > 1 ? (unsigned)((0x100000000ull + tys - 1) / tys) : 0u;
+  const int tiles = (int)(txs * tys) * p.N;
   static int sms = 0;
   if (!sms) { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d); if (sms <= 0) sms = 148; }
-  const int ctas = (C <= 16 ? 2 : 1) * sms;
-  launch_pdl(dlc_tc_kernel<CIN, C, HEAD>, dim3(tiles < ctas ? tiles : ctas), dim3(kDlcThreads), smem, s, p);
+  int per_sm = (C <= 16 ? 2 : 1) * (4 / NBLK);
+  const int by_smem = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > by_smem) per_sm = by_smem;
+  if (per_sm < 1) per_sm = 1;
+  const int ctas = per_sm * sms;
+  launch_pdl(dlc_tc_kernel<CIN, C, HEAD, NBLK>, dim3(tiles < ctas ? tiles : ctas), dim3(dlc_threads(NBLK)), smem, s, p);
 }
 
 void launch_dlc_tc(const DlcTcP& p0, cudaStream_t s) {
@@ -466,11 +475,18 @@ void launch_dlc_tc(const DlcTcP& p0, cudaStream_t s) {
   static const int probe = getenv("YSP_DLC_PROBE") ? atoi(getenv("YSP_DLC_PROBE")) : 0;
   p.probe = probe;
 #endif
-  const unsigned txs = (2 * p.w + TW - 1) / TW, tys = (2 * p.h + TH - 1) / TH;
-  p.magic_x = txs > 1 ? (unsigned)((0x100000000ull + txs - 1) / txs) : 0u;
-  p.magic_y = tys > 1 ? (unsigned)((0x100000000ull + tys - 1) / tys) : 0u;
-  if (p.Cin == 32 && p.C == 16) dlc_tc_launch<32, 16, true>(p, s);
-  else dlc_tc_launch<64, 32, false>(p, s);
+  // Both stages run the 14 x 30-tile / 320-thread shape.  The 14 x 14-tile / 160-thread shape (four CTAs per SM for stage 4 --
+  // the change that halved the parity-mode dlc32 kernel) measured 0.934 vs 0.914 ms here (stage 4) and 0.906 vs 0.568 ms (stage
+  // 3, one CTA per SM either way: 59 KB of weights): this kernel is bound by its chains of small MMAs, not by the barriers.
+  // YSP_DLC_TC_CFG (A/B timing): 1 = small shape for stage 4, 2 = for stage 3.
+  static const int cfg = getenv("YSP_DLC_TC_CFG") ? atoi(getenv("YSP_DLC_TC_CFG")) : 0;
+  if (p.Cin == 32 && p.C == 16) {
+    if (cfg == 1) dlc_tc_launch<32, 16, true, 2>(p, s);
+    else dlc_tc_launch<32, 16, true, 4>(p, s);
+  } else {
+    if (cfg == 2) dlc_tc_launch<64, 32, false, 2>(p, s);
+    else dlc_tc_launch<64, 32, false, 4>(p, s);
+  }
 }
 
 }  // namespace ysp
