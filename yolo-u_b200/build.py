@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libysp.so")
 SOURCES = ["engine.cu", "kernels_simt.cu", "kernels_fused.cu", "kernels_dlc_tc.cu", "kernels_dlc32.cu", "kernels_stem_attn.cu", "nms.cu", "conv_tc.cu", "conv_tc32.cu", "conv_halo.cu", "conv_halo32.cu", "attention_tc.cu",
-           "kernels_train.cu", "train.cu", "kernels_ghost.cu"]
+           "kernels_train.cu", "kernels_train_tc.cu", "train.cu", "kernels_ghost.cu"]
 HEADERS = ["common.cuh", "kernels.h", "kernels_train.h", os.path.join("..", "..", "include", "ysp.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]

@@ -74,6 +74,14 @@ __device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint3
   const float2 d = __ffma2_rn(f, make_float2(-1.f, -1.f), make_float2(a, b));      // (a - fa, b - fb), exact, one FFMA2
   lo = f2h2_sat(d.x, d.y);
 }
+// fp32 pair -> packed bf16 hi and mid with x = hi + mid + O(2^-18 x): the operand split of the TRAINING GEMMs, whose operands
+// (gradients of 1e-5 and below) would underflow the fp16 range; bf16 keeps the fp32 exponent, three MMAs give 2^-17 products.
+__device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint32_t& mid) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float fa = __uint_as_float(hi << 16), fb = __uint_as_float(hi & 0xffff0000u);
+  const float2 d = __ffma2_rn(make_float2(fa, fb), make_float2(-1.f, -1.f), make_float2(a, b));      // exact
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(d.y), "f"(d.x));
+}
 // Packed SiLU of two values (FMUL2 / FADD2 around the four MUFU ops): bit-identical to silu_f per lane, 8 instead of 10 issue slots
 __device__ __forceinline__ float2 silu2_f(float2 x) {
   const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));

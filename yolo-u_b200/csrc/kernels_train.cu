@@ -200,6 +200,7 @@ static void pw_gemm_launch(const float* A, int lda, const float* W, int ldw, int
 
 void launch_pw_gemm(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc,
                     long long M, int I, int J, int beta, cudaStream_t s, double* sums, InTf tf, PwDual du) {
+  if (launch_pw_gemm_tc(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums, tf, du)) return;   // tensor cores (fp16 hi/lo splits)
   if (J <= 16) pw_gemm_launch<16>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums, tf, du);
   else if (J <= 32) pw_gemm_launch<32>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums, tf, du);
   else pw_gemm_launch<64>(A, lda, W, ldw, trans, bias, C, ldc, M, I, J, beta, s, sums, tf, du);

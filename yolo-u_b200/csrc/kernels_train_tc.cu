@@ -1,0 +1,347 @@
+// kernels_train_tc.cu -- the 1x1-conv GEMMs of the seg-head TRAINING step (forward and input gradient) on tcgen05 tensor cores.
+//
+//   C[m][j] = beta * C[m][j] + bias[j] + sum_i A[m][i] * Wop(i, j)          (same contract as pw_gemm_kernel, kernels_train.cu)
+//
+// ncu of the FFMA version (profiles/r7_train_gemm.md): the 32 pointwise GEMMs of a step take 8.8 ms of its 23 ms at ~1 TB/s of
+// DRAM traffic -- compute-bound on the fp32 pipe (K, N = 16..144), not bandwidth-bound.  Here every operand is split into bf16
+// hi + mid (x = hi + mid to 2^-18; bf16 because the gradient operands, 1e-5 and below, underflow the fp16 range that the inference
+// path's hi/lo split uses) and each product is three bf16 MMAs (hi.hi + mid.hi + hi.mid) with fp32 accumulation in TMEM: products
+// accurate to 2^-17, far inside the 2e-3 gradient tolerance checked against torch autograd (the reference itself trains under fp16
+// autocast, train.py:302-341), and the GEMM runs at the rate of its loads:
+//   * prologue (once per persistent CTA): the weight matrix -- either orientation, the optional second reduction range (A2/W2)
+//     and the optional rider columns (Jsplit/Wb) -- is split and stored as the B operand
+//     [8-k plane][n][8] (K-major, no swizzle);
+//   * per 128-row tile: 256 threads load the fp32 rows (two threads per row, alternate 8-channel planes), apply the optional
+//     input transform x = act(z * sc + sh) (the producer's BatchNorm + SiLU, never materialised), split, store the A operand
+//     [8-k plane][row] x 16 B; one thread issues 3 * K/16 MMAs (M = 128, N = padded J); 8 warps read the accumulator back
+//     (tcgen05.ld), un-scale, add bias / the previous C (beta), store; BatchNorm statistics (column sum and sum of squares of the
+//     bias-free product) go through a column-major shared-memory tile and are accumulated per thread across the CTA's tiles.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "kernels.h"
+#include "kernels_train.h"
+
+namespace ysp {
+
+namespace {
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWLT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DNT;\n\tbra WLT;\n\tDNT:\n\t}"
+               ::"r"(s32(bar)), "r"(parity) : "memory");
+}
+
+struct GemmTcP {
+  const float* A0; int lda0; const float* W0; int ldw0; int trans; const float* bias; float* C; int ldc;
+  long long M; int I0, J, beta; double* sums; InTf tf; PwDual du;
+  int K0, K2, Kt, N, tcols, NB;      // padded reduction ranges (K0 + K2 = Kt), padded columns, TMEM columns, 128-row blocks per iteration
+  int a_half, b_half, out_pitch;     // bytes of one A / B half (hi or lo); floats per column of the statistics tile
+};
+
+constexpr int kGT = 256;
+
+// weight of (reduction index k in the padded range, output column j); 0 in the padding
+__device__ __forceinline__ float weight_at(const GemmTcP& p, int k, int j) {
+  if (j >= p.J) return 0.f;
+  if (k < p.K0) {
+    if (k >= p.I0) return 0.f;
+    if (p.du.Jsplit && j >= p.du.Jsplit) return p.du.Wb[(size_t)(j - p.du.Jsplit) * p.du.ldwb + k];   // rider: forward layout [Cout][Cin]
+    return p.trans ? p.W0[(size_t)k * p.ldw0 + j] : p.W0[(size_t)j * p.ldw0 + k];
+  }
+  const int k2 = k - p.K0;
+  if (k2 >= p.du.I2) return 0.f;
+  return p.trans ? p.du.W2[(size_t)k2 * p.du.ldw2 + j] : p.du.W2[(size_t)j * p.du.ldw2 + k2];
+}
+
+}  // namespace
+
+// F16 = true: fp16 hi/lo operands (22 mantissa bits; weights scaled by a power of two so their lo parts stay normal) -- the FORWARD
+// GEMMs, whose A operand is an O(1) activation and whose result must reproduce the fp32 loss to 1e-5.  F16 = false: bf16 hi/mid
+// operands (17-bit products, fp32 exponent range) -- the INPUT-GRADIENT GEMMs, whose A operand holds gradients of 1e-5 and below
+// that underflow fp16 (measured: 0.2 % gradient errors and a training curve that drifts from the fp32 one with fp16 operands).
+template <bool F16>
+__global__ void __launch_bounds__(kGT, 2) pw_gemm_tc_kernel(const GemmTcP p) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  uint8_t* sA = gsm;                                         // hi [Kt/8][128] x 16 B, then lo; re-used as the statistics tile
+  uint8_t* sB = gsm + 2 * p.a_half;                          // hi [Kt/8][N] x 16 B, then lo
+  float* sSc = reinterpret_cast<float*>(sB + 2 * p.b_half);  // input transform scale / shift [K0]
+  float* sSh = sSc + p.K0;
+  float* sBias = sSh + p.K0;                                 // [N]
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_s;
+  __shared__ float red[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool tfon = p.tf.gamma != nullptr;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_s)), "r"((uint32_t)p.tcols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // ---- weights -> B operand (fp16: scaled by 2^e so that the lo parts stay normal) ----
+  float wmax = 0.f;
+  if (F16) {
+    for (int e = tid; e < p.Kt * p.N; e += kGT) wmax = fmaxf(wmax, fabsf(weight_at(p, e % p.Kt, e / p.Kt)));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) red[warp] = wmax;
+  }
+  for (int i = tid; i < p.K0; i += kGT) {
+    float sc = 1.f, sh = 0.f;
+    if (tfon && i < p.I0) { sc = p.tf.gamma[i] * p.tf.invstd[i]; sh = p.tf.beta[i] - p.tf.mean[i] * sc; }
+    sSc[i] = sc; sSh[i] = sh;
+  }
+  for (int j = tid; j < p.N; j += kGT) {
+    float b = 0.f;
+    if (j < p.J) {
+      if (p.du.Jsplit && j >= p.du.Jsplit) b = p.du.biasb ? p.du.biasb[j - p.du.Jsplit] : 0.f;
+      else b = p.bias ? p.bias[j] : 0.f;
+    }
+    sBias[j] = b;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  int e2 = 0;
+  if (F16) {
+    wmax = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
+    if (wmax > 0.f) { int ex; frexpf(wmax, &ex); e2 = 14 - ex; }         // max |w| * 2^e2 in [2^13, 2^14)
+  }
+  const float wsc = ldexpf(1.f, e2), unscale = ldexpf(1.f, -e2);
+  for (int e = tid; e < (p.Kt >> 1) * p.N; e += kGT) {                    // two consecutive k per thread: one 32-bit store per half
+    const int kp = e % (p.Kt >> 1), j = e / (p.Kt >> 1), k = 2 * kp;
+    uint32_t hi, lo;
+    if (F16) split2_f16(weight_at(p, k, j) * wsc, weight_at(p, k + 1, j) * wsc, hi, lo);
+    else split2_bf16(weight_at(p, k, j), weight_at(p, k + 1, j), hi, lo);
+    const uint32_t off = (uint32_t)(k >> 3) * (uint32_t)(p.N * 16) + (uint32_t)j * 16u + (uint32_t)(k & 7) * 2u;
+    *reinterpret_cast<uint32_t*>(sB + off) = hi;
+    *reinterpret_cast<uint32_t*>(sB + p.b_half + off) = lo;
+  }
+  const uint32_t tmem = tmem_s;
+  const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // D = F32, A = B = F16 / BF16
+  const int row = tid & 127, hsel = tid >> 7;                // A load: two threads per row, alternate 8-channel planes
+  const int q = warp & 3, chalf = warp >> 2;                 // epilogue: TMEM lane quarter, alternate 16-column chunks
+  const bool vecA0 = ((p.lda0 | p.I0) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.A0) & 15) == 0;
+  const bool vecA2 = p.du.A2 && ((p.du.lda2 | p.du.I2) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.du.A2) & 15) == 0;
+  const bool vecC = ((p.ldc | p.J | p.du.Jsplit | p.du.ldcb) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(p.du.Cb) & 15) == 0;
+  const int Jstat = p.du.Jsplit ? p.du.Jsplit : p.J;
+  // statistics: thread -> (column sj, row part sp of 1, 2 or 4); accumulated in double across the CTA's tiles
+  const int nparts = kGT / p.N >= 4 ? 4 : (kGT / p.N >= 2 ? 2 : 1);
+  const int sj = tid % p.N, sp = tid / p.N;
+  const int rows_per_part = (128 * p.NB) / nparts;
+  double cs1 = 0.0, cs2 = 0.0;
+  uint32_t par = 0;
+  const int planes = p.Kt >> 3;
+  const int blk_bytes = planes * 2048;                       // one 128-row block of the hi (or lo) A tile
+  const long long mtiles = (p.M + 128 * p.NB - 1) / (128 * p.NB);
+#pragma unroll 1
+  for (long long mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+    const long long mbase = mt * 128 * p.NB;
+    // ---- A operand: NB row blocks x this thread's planes; loads of two items are in flight before the first conversion ----
+    const int items = p.NB * ((planes - hsel + 1) >> 1);     // (block, plane) pairs of this thread
+#pragma unroll 1
+    for (int it0 = 0; it0 < items; it0 += 2) {
+      float v[2][8];
+      int dst[2];
+      bool tfm[2];
+      int k0s[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int it = it0 + u;
+        dst[u] = -1; tfm[u] = false; k0s[u] = 0;
+        if (it < items) {
+          const int per = (planes - hsel + 1) >> 1;
+          const int blk = it / per, g = hsel + 2 * (it - blk * per);
+          const long long m = mbase + blk * 128 + row;
+          const int k0 = g * 8;
+          const bool part2 = k0 >= p.K0;
+          const float* src = part2 ? p.du.A2 + m * p.du.lda2 + (k0 - p.K0) : p.A0 + m * p.lda0 + k0;
+          const int valid = part2 ? p.du.I2 - (k0 - p.K0) : p.I0 - k0;       // channels of this plane that exist
+          if (m < p.M && valid >= 8 && (part2 ? vecA2 : vecA0)) {
+            const float4 a = *reinterpret_cast<const float4*>(src), bq = *reinterpret_cast<const float4*>(src + 4);
+            v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = bq.x; v[u][5] = bq.y; v[u][6] = bq.z; v[u][7] = bq.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[u][j] = (m < p.M && j < valid) ? src[j] : 0.f;
+          }
+          dst[u] = blk * blk_bytes + g * 2048 + row * 16;
+          tfm[u] = tfon && !part2 && m < p.M;
+          k0s[u] = k0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (dst[u] < 0) continue;
+        if (tfm[u]) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (k0s[u] + j < p.I0) {
+              float x = fmaf(v[u][j], sSc[k0s[u] + j], sSh[k0s[u] + j]);
+              if (p.tf.act) x = x / (1.f + expf(-x));
+              v[u][j] = x;
+            }
+          }
+        }
+        uint4 h, l;
+        if (F16) {
+          split2_f16(v[u][0], v[u][1], h.x, l.x); split2_f16(v[u][2], v[u][3], h.y, l.y);
+          split2_f16(v[u][4], v[u][5], h.z, l.z); split2_f16(v[u][6], v[u][7], h.w, l.w);
+        } else {
+          split2_bf16(v[u][0], v[u][1], h.x, l.x); split2_bf16(v[u][2], v[u][3], h.y, l.y);
+          split2_bf16(v[u][4], v[u][5], h.z, l.z); split2_bf16(v[u][6], v[u][7], h.w, l.w);
+        }
+        *reinterpret_cast<uint4*>(sA + dst[u]) = h;
+        *reinterpret_cast<uint4*>(sA + p.a_half + dst[u]) = l;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a0 = s32(sA), b0 = s32(sB);
+      // per row block two accumulators: the hi.hi products and the two cross terms (lo.hi + hi.lo) -- the tensor core truncates
+      // its fp32 accumulation, so the long chain carries only K/16 steps and the small terms cannot disturb it; block-major
+      // inner loop so consecutive MMAs never hit the same accumulator
+      for (int ks = 0; ks < (p.Kt >> 4); ++ks) {
+        const uint64_t bh = desc_nosw(b0 + ks * 2 * p.N * 16, (uint32_t)p.N * 16u, 128u);
+        const uint64_t bl = desc_nosw(b0 + p.b_half + ks * 2 * p.N * 16, (uint32_t)p.N * 16u, 128u);
+        for (int term = 0; term < 3; ++term)
+          for (int blk = 0; blk < p.NB; ++blk) {
+            const uint64_t ad = desc_nosw(a0 + (term == 1 ? p.a_half : 0) + blk * blk_bytes + ks * 4096, 2048u, 128u);
+            umma_f16(tmem + (2 * blk + (term ? 1 : 0)) * p.N, ad, term == 2 ? bl : bh, idesc, term == 2 ? 1u : (ks ? 1u : 0u));
+          }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar)) : "memory");
+    }
+    mbar_wait_parity(&bar, par);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    par ^= 1;
+    // ---- epilogue: row = TMEM lane, alternate 16-column chunks per warp half; the A tiles are dead -> statistics tile ----
+    float* sOut = reinterpret_cast<float*>(sA);              // [column][out_pitch] (column-major: conflict-free both ways)
+    for (int blk = 0; blk < p.NB; ++blk) {
+      const int erow = q * 32 + lane;
+      const long long em = mbase + blk * 128 + erow;
+      for (int c0 = chalf * 16; c0 < p.N; c0 += 32) {
+        uint32_t v[16], w[16];
+        ld16(tmem + ((uint32_t)(q * 32) << 16) + (2 * blk) * p.N + c0, v);
+        ld16(tmem + ((uint32_t)(q * 32) << 16) + (2 * blk + 1) * p.N + c0, w);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = (__uint_as_float(v[j]) + __uint_as_float(w[j])) * unscale;
+        if (p.sums) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sOut[(c0 + j) * p.out_pitch + blk * 128 + erow] = f[j];
+        }
+        if (em < p.M && c0 < p.J) {
+          const bool second = p.du.Jsplit && c0 >= p.du.Jsplit;            // Jsplit is a multiple of 16 when the tensor-core path is taken
+          float* crow = second ? p.du.Cb + em * p.du.ldcb + (c0 - p.du.Jsplit) : p.C + em * p.ldc + c0;
+          const int nvalid = (second ? p.J : (p.du.Jsplit ? p.du.Jsplit : p.J)) - c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] += sBias[c0 + j];
+          if (vecC && nvalid >= 16) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              float4 o = make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+              float4* op = reinterpret_cast<float4*>(crow) + j4;
+              if (p.beta) { const float4 pv = *op; o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w; }
+              *op = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < nvalid) crow[j] = p.beta ? crow[j] + f[j] : f[j];
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                                         // accumulators read by everyone; statistics tile complete
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (p.sums) {
+      if (sp < nparts && sj < Jstat) {
+        const float* col = sOut + sj * p.out_pitch + sp * rows_per_part;
+        float a1 = 0.f, a2 = 0.f;
+        for (int r = 0; r < rows_per_part; ++r) { const float x = col[r]; a1 += x; a2 = fmaf(x, x, a2); }   // rows >= M hold exact zeros
+        cs1 += a1; cs2 += a2;
+      }
+      __syncthreads();                                       // the next tile's A operand overwrites the statistics tile
+    }
+  }
+  if (p.sums && sp < nparts && sj < Jstat) {
+    atomicAdd(&p.sums[sj], cs1);
+    atomicAdd(&p.sums[Jstat + sj], cs2);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tcols) : "memory");
+  }
+}
+
+// true when the launch was taken (tensor-core path); false -> the caller runs the FFMA kernel
+bool launch_pw_gemm_tc(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc, long long M,
+                       int I, int J, int beta, cudaStream_t s, double* sums, InTf tf, PwDual du) {
+  static const bool off = getenv("YSP_TRAIN_NO_TC") != nullptr;
+  if (off || M < 128) return false;
+  GemmTcP p = {};
+  p.A0 = A; p.lda0 = lda; p.W0 = W; p.ldw0 = ldw; p.trans = trans; p.bias = bias; p.C = C; p.ldc = ldc; p.M = M; p.I0 = I; p.J = J;
+  p.beta = beta; p.sums = sums; p.tf = tf; p.du = du;
+  p.K0 = (I + 15) / 16 * 16; p.K2 = du.A2 ? (du.I2 + 15) / 16 * 16 : 0; p.Kt = p.K0 + p.K2;
+  p.N = (J + 15) / 16 * 16;
+  if (p.N > 256 || p.Kt > 288 || J < 8) return false;                        // narrow outputs (the 16 -> 1 head) stay on CUDA cores
+  if (du.Jsplit && (du.Jsplit & 15)) return false;                            // rider columns must start on a 16-column chunk
+  if (sums && p.N > kGT) return false;
+  // rows per iteration: as many 128-row blocks as keep the A tiles near 64 KB and the 2 NB accumulators inside 256 TMEM columns
+  // (two CTAs per SM): the narrow GEMMs of the full-resolution stages move 16 KB per block and were latency-bound one block at a time
+  p.NB = 1;
+  while (p.NB < 4 && 2 * (2 * p.NB) * p.N <= 256 && (size_t)(2 * p.NB) * (p.Kt / 8) * 2048 * 2 <= 64 * 1024 && (long long)256 * p.NB * 296 <= M) p.NB *= 2;
+  p.tcols = 32;
+  while (p.tcols < 2 * p.NB * p.N) p.tcols <<= 1;
+  if (p.tcols > 512) return false;
+  p.a_half = p.NB * (p.Kt / 8) * 2048;
+  p.b_half = (p.Kt / 8) * p.N * 16;
+  p.out_pitch = 128 * p.NB + 1;
+  const size_t stats_bytes = sums ? (size_t)p.N * p.out_pitch * 4 : 0;
+  const size_t a_bytes = std::max<size_t>(2 * (size_t)p.a_half, stats_bytes);
+  if (a_bytes > 2 * (size_t)p.a_half) p.a_half = (int)((a_bytes / 2 + 127) / 128 * 128);     // the statistics tile needs more room than the A tiles
+  const size_t smem = 2 * (size_t)p.a_half + 2 * (size_t)p.b_half + (size_t)(2 * p.K0 + p.N) * 4 + 128;
+  if (smem > 200 * 1024) return false;
+  static unsigned long long attr_done = 0;
+  ensure_dyn_smem(pw_gemm_tc_kernel<true>, 200 * 1024, attr_done, "pw_gemm_tc_kernel<f16>");
+  static unsigned long long attr_done_b = 0;
+  ensure_dyn_smem(pw_gemm_tc_kernel<false>, 200 * 1024, attr_done_b, "pw_gemm_tc_kernel<bf16>");
+  static int sms = 0;
+  if (!sms) { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d); if (sms <= 0) sms = 148; }
+  int per_sm = (int)std::min<size_t>(std::min<size_t>(512 / p.tcols, (220 * 1024) / (smem + 1024)), 2);
+  if (per_sm < 1) per_sm = 1;
+  const long long mtiles = (M + 128 * p.NB - 1) / (128 * p.NB);
+  const int grid = (int)std::min<long long>(mtiles, (long long)sms * per_sm);
+  if (trans) pw_gemm_tc_kernel<false><<<grid, kGT, smem, s>>>(p);      // input gradient: bf16 hi/mid operands
+  else pw_gemm_tc_kernel<true><<<grid, kGT, smem, s>>>(p);            // forward: fp16 hi/lo operands
+  return true;
+}
+
+}  // namespace ysp
