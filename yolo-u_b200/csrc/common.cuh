@@ -51,6 +51,14 @@ __device__ __forceinline__ float silu_f(float x) {
   return x * r;
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// MUFU sigmoid (ex2.approx + rcp.approx, ~3e-7): activation DERIVATIVES of the training step; the mask threshold, the loss and the
+// detector's class scores keep the exact sigmoid_f
+__device__ __forceinline__ float sigmoid_mufu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 __device__ __forceinline__ float apply_act(float x, int act) { return act == ACT_SILU ? silu_f(x) : x; }
 // SiLU(x) = h + h*tanh(h), h = x/2: one MUFU op (tanh.approx, rel. error ~2^-11 -- below bf16 resolution).  Used wherever
 // the result is stored as bf16 (throughput mode); the fp32 parity mode keeps the exact expf form above.

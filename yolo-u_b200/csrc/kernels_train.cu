@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256, 4) pw_gemm_kernel(const float* __restrict
               const int ig = i0 + i;
               v.x = fmaf(v.x, sSc[ig], sSh[ig]); v.y = fmaf(v.y, sSc[ig + 1], sSh[ig + 1]);
               v.z = fmaf(v.z, sSc[ig + 2], sSh[ig + 2]); v.w = fmaf(v.w, sSc[ig + 3], sSh[ig + 3]);
-              if (tf.act) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w)); }
+              if (tf.act) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
             }
             As[i][r] = v.x; As[i + 1][r] = v.y; As[i + 2][r] = v.z; As[i + 3][r] = v.w;
           }
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256, 4) pw_gemm_kernel(const float* __restrict
             float v = 0.f;
             if (m < M && i0 + i < I) {
               v = A[m * lda + i0 + i];
-              if (xf) { v = fmaf(v, sSc[i0 + i], sSh[i0 + i]); if (tf.act) v = v / (1.f + expf(-v)); }
+              if (xf) { v = fmaf(v, sSc[i0 + i], sSh[i0 + i]); if (tf.act) v = silu_f(v); }
             }
             As[i][r] = v;
           }
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) pw_wgrad_kernel(const float* __restrict__
     if (xf && rb + r < r1) {       // columns beyond the matrix have sc = sh = 0 and stay 0 (SiLU(0) = 0)
       v.x = fmaf(v.x, sSc[c], sSh[c]); v.y = fmaf(v.y, sSc[c + 1], sSh[c + 1]);
       v.z = fmaf(v.z, sSc[c + 2], sSh[c + 2]); v.w = fmaf(v.w, sSc[c + 3], sSh[c + 3]);
-      if (tf.act) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w)); }
+      if (tf.act) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
     }
     *reinterpret_cast<float4*>(dst + r * dld + c) = v;
   };
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(256) dw_tiled_kernel(const float* __restrict__
         if (tfon && inimg[u]) {        // the conv zero-pads the TRANSFORMED tensor: only in-image pixels are mapped
           const float4 sc = *reinterpret_cast<const float4*>(sSc + qq * 4), sh = *reinterpret_cast<const float4*>(sSh + qq * 4);
           v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-          if (tf.act) { v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w)); }
+          if (tf.act) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
         }
         *reinterpret_cast<float4*>(sIn + pp * PS + qq * 4) = v;
       }
@@ -658,7 +658,7 @@ bool launch_dw_fwd_stats(const float* X, int ldx, const float* W, float* Y, int 
 //   MODE 3  products:         v1 = a*b                            (ECA backward: d gate)
 // =====================================================================================================================
 __device__ __forceinline__ float silu_grad(float t) {
-  float sg = 1.f / (1.f + expf(-t));
+  const float sg = sigmoid_mufu(t);
   return sg * (1.f + t * (1.f - sg));
 }
 
@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float t = fmaf(z[j], sc[j], sh[j]);
-      o[j] = (act ? t / (1.f + expf(-t)) : t) + r[j];
+      o[j] = (act ? silu_f(t) : t) + r[j];
     }
     *reinterpret_cast<float4*>(Y + m * ldy + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
   }

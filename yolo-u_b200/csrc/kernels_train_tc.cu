@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kGT, 2) pw_gemm_tc_kernel(const GemmTcP p) {
   float* sSc = reinterpret_cast<float*>(sB + 2 * p.b_half);  // input transform scale / shift [K0]
   float* sSh = sSc + p.K0;
   float* sBias = sSh + p.K0;                                 // [N]
+  double* sAcc = reinterpret_cast<double*>(sBias + p.N + ((2 * p.K0 + p.N) & 1));   // [2][N] column sum / sum of squares (8-byte aligned)
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_s;
   __shared__ float red[8];
@@ -145,33 +146,31 @@ __global__ void __launch_bounds__(kGT, 2) pw_gemm_tc_kernel(const GemmTcP p) {
   const bool vecC = ((p.ldc | p.J | p.du.Jsplit | p.du.ldcb) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(p.du.Cb) & 15) == 0;
   const int Jstat = p.du.Jsplit ? p.du.Jsplit : p.J;
-  // statistics: thread -> (column sj, row part sp of 1, 2 or 4); accumulated in double across the CTA's tiles
-  const int nparts = kGT / p.N >= 4 ? 4 : (kGT / p.N >= 2 ? 2 : 1);
-  const int sj = tid % p.N, sp = tid / p.N;
-  const int rows_per_part = (128 * p.NB) / nparts;
-  double cs1 = 0.0, cs2 = 0.0;
+  for (int i = tid; i < 2 * p.N; i += kGT) sAcc[i] = 0.0;     // BatchNorm statistics of this CTA's rows (double)
   uint32_t par = 0;
   const int planes = p.Kt >> 3;
+  const int nbs = p.NB == 4 ? 2 : (p.NB == 2 ? 1 : 0);
   const int blk_bytes = planes * 2048;                       // one 128-row block of the hi (or lo) A tile
   const long long mtiles = (p.M + 128 * p.NB - 1) / (128 * p.NB);
 #pragma unroll 1
   for (long long mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
     const long long mbase = mt * 128 * p.NB;
-    // ---- A operand: NB row blocks x this thread's planes; loads of two items are in flight before the first conversion ----
+    // ---- A operand: NB row blocks x this thread's planes; the loads of UB items (32 B each) are in flight before the first
+    //      conversion: 256 threads x 4 x 32 B x 2 CTAs = 64 KB per SM, what the HBM latency-bandwidth product needs ----
+    constexpr int UB = 4;
     const int items = p.NB * ((planes - hsel + 1) >> 1);     // (block, plane) pairs of this thread
 #pragma unroll 1
-    for (int it0 = 0; it0 < items; it0 += 2) {
-      float v[2][8];
-      int dst[2];
-      bool tfm[2];
-      int k0s[2];
+    for (int it0 = 0; it0 < items; it0 += UB) {
+      float v[UB][8];
+      int dst[UB];
+      bool tfm[UB];
+      int k0s[UB];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < UB; ++u) {
         const int it = it0 + u;
         dst[u] = -1; tfm[u] = false; k0s[u] = 0;
         if (it < items) {
-          const int per = (planes - hsel + 1) >> 1;
-          const int blk = it / per, g = hsel + 2 * (it - blk * per);
+          const int blk = it & (p.NB - 1), g = hsel + 2 * (it >> nbs);     // NB is 1, 2 or 4
           const long long m = mbase + blk * 128 + row;
           const int k0 = g * 8;
           const bool part2 = k0 >= p.K0;
@@ -190,16 +189,18 @@ __global__ void __launch_bounds__(kGT, 2) pw_gemm_tc_kernel(const GemmTcP p) {
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < UB; ++u) {
         if (dst[u] < 0) continue;
-        if (tfm[u]) {
+        if (tfm[u]) {                                        // x = act(z * sc + sh); channels past I0 have sc = 1, sh = 0 and z = 0
+          const float4 c0 = *reinterpret_cast<const float4*>(sSc + k0s[u]), c1 = *reinterpret_cast<const float4*>(sSc + k0s[u] + 4);
+          const float4 h0 = *reinterpret_cast<const float4*>(sSh + k0s[u]), h1 = *reinterpret_cast<const float4*>(sSh + k0s[u] + 4);
+          const float sc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (k0s[u] + j < p.I0) {
-              float x = fmaf(v[u][j], sSc[k0s[u] + j], sSh[k0s[u] + j]);
-              if (p.tf.act) x = x / (1.f + expf(-x));
-              v[u][j] = x;
-            }
+          for (int j = 0; j < 8; j += 2) {
+            float2 x = __ffma2_rn(make_float2(v[u][j], v[u][j + 1]), make_float2(sc[j], sc[j + 1]), make_float2(sh[j], sh[j + 1]));
+            if (p.tf.act) x = silu2_f(x);                      // MUFU SiLU (3e-7), as every fp32-storage inference kernel
+            const bool e0 = k0s[u] + j < p.I0, e1 = k0s[u] + j + 1 < p.I0;
+            v[u][j] = e0 ? x.x : 0.f; v[u][j + 1] = e1 ? x.y : 0.f;
           }
         }
         uint4 h, l;
@@ -259,7 +260,10 @@ __global__ void __launch_bounds__(kGT, 2) pw_gemm_tc_kernel(const GemmTcP p) {
           float* crow = second ? p.du.Cb + em * p.du.ldcb + (c0 - p.du.Jsplit) : p.C + em * p.ldc + c0;
           const int nvalid = (second ? p.J : (p.du.Jsplit ? p.du.Jsplit : p.J)) - c0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] += sBias[c0 + j];
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + 4 * j4);
+            f[4 * j4] += b4.x; f[4 * j4 + 1] += b4.y; f[4 * j4 + 2] += b4.z; f[4 * j4 + 3] += b4.w;
+          }
           if (vecC && nvalid >= 16) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
@@ -280,18 +284,23 @@ __global__ void __launch_bounds__(kGT, 2) pw_gemm_tc_kernel(const GemmTcP p) {
     __syncthreads();                                         // accumulators read by everyone; statistics tile complete
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (p.sums) {
-      if (sp < nparts && sj < Jstat) {
-        const float* col = sOut + sj * p.out_pitch + sp * rows_per_part;
+      // column sums of the bias-free product: a warp per column, lanes stride over the rows (consecutive addresses), shuffle
+      // reduction, lane 0 adds into the CTA's double accumulators (each column is owned by one warp: no atomics)
+      const int rows = 128 * p.NB;
+      for (int col = warp; col < Jstat; col += kGT / 32) {
+        const float* cp = sOut + col * p.out_pitch;
         float a1 = 0.f, a2 = 0.f;
-        for (int r = 0; r < rows_per_part; ++r) { const float x = col[r]; a1 += x; a2 = fmaf(x, x, a2); }   // rows >= M hold exact zeros
-        cs1 += a1; cs2 += a2;
+        for (int r = lane; r < rows; r += 32) { const float x = cp[r]; a1 += x; a2 = fmaf(x, x, a2); }   // rows >= M hold exact zeros
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+        if (lane == 0) { sAcc[col] += (double)a1; sAcc[p.N + col] += (double)a2; }
       }
       __syncthreads();                                       // the next tile's A operand overwrites the statistics tile
     }
   }
-  if (p.sums && sp < nparts && sj < Jstat) {
-    atomicAdd(&p.sums[sj], cs1);
-    atomicAdd(&p.sums[Jstat + sj], cs2);
+  if (p.sums) {
+    for (int col = warp; col < Jstat; col += kGT / 32)
+      if (lane == 0) { atomicAdd(&p.sums[col], sAcc[col]); atomicAdd(&p.sums[Jstat + col], sAcc[p.N + col]); }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -313,7 +322,6 @@ bool launch_pw_gemm_tc(const float* A, int lda, const float* W, int ldw, int tra
   p.N = (J + 15) / 16 * 16;
   if (p.N > 256 || p.Kt > 288 || J < 8) return false;                        // narrow outputs (the 16 -> 1 head) stay on CUDA cores
   if (du.Jsplit && (du.Jsplit & 15)) return false;                            // rider columns must start on a 16-column chunk
-  if (sums && p.N > kGT) return false;
   // rows per iteration: as many 128-row blocks as keep the A tiles near 64 KB and the 2 NB accumulators inside 256 TMEM columns
   // (two CTAs per SM): the narrow GEMMs of the full-resolution stages move 16 KB per block and were latency-bound one block at a time
   p.NB = 1;
@@ -327,7 +335,7 @@ bool launch_pw_gemm_tc(const float* A, int lda, const float* W, int ldw, int tra
   const size_t stats_bytes = sums ? (size_t)p.N * p.out_pitch * 4 : 0;
   const size_t a_bytes = std::max<size_t>(2 * (size_t)p.a_half, stats_bytes);
   if (a_bytes > 2 * (size_t)p.a_half) p.a_half = (int)((a_bytes / 2 + 127) / 128 * 128);     // the statistics tile needs more room than the A tiles
-  const size_t smem = 2 * (size_t)p.a_half + 2 * (size_t)p.b_half + (size_t)(2 * p.K0 + p.N) * 4 + 128;
+  const size_t smem = 2 * (size_t)p.a_half + 2 * (size_t)p.b_half + (size_t)(2 * p.K0 + p.N + 1) * 4 + (size_t)2 * p.N * 8 + 128;
   if (smem > 200 * 1024) return false;
   static unsigned long long attr_done = 0;
   ensure_dyn_smem(pw_gemm_tc_kernel<true>, 200 * 1024, attr_done, "pw_gemm_tc_kernel<f16>");
