@@ -54,7 +54,6 @@ struct GemmTcP {
   int a_half, b_half, out_pitch;     // bytes of one A / B half (hi or lo); floats per column of the statistics tile
 };
 
-constexpr int kGT = 256;
 
 // weight of (reduction index k in the padded range, output column j); 0 in the padding
 __device__ __forceinline__ float weight_at(const GemmTcP& p, int k, int j) {
@@ -75,8 +74,11 @@ __device__ __forceinline__ float weight_at(const GemmTcP& p, int k, int j) {
 // GEMMs, whose A operand is an O(1) activation and whose result must reproduce the fp32 loss to 1e-5.  F16 = false: bf16 hi/mid
 // operands (17-bit products, fp32 exponent range) -- the INPUT-GRADIENT GEMMs, whose A operand holds gradients of 1e-5 and below
 // that underflow fp16 (measured: 0.2 % gradient errors and a training curve that drifts from the fp32 one with fp16 operands).
-template <bool F16>
-__global__ void __launch_bounds__(kGT, 2) pw_gemm_tc_kernel(const GemmTcP p) {
+// kGT threads per CTA (512 / kGT CTAs per SM: 113 registers per thread): the phases of an iteration (load + convert, MMA, epilogue,
+// statistics) run one after the other inside a CTA, so several small CTAs overlap them better than two large ones.
+template <bool F16, int kGT>
+__global__ void __launch_bounds__(kGT, 512 / kGT) pw_gemm_tc_kernel(const GemmTcP p) {
+  static_assert(kGT == 256, "the weight-range reduction and the lane-quarter mapping assume eight warps");
   extern __shared__ __align__(128) uint8_t gsm[];
   uint8_t* sA = gsm;                                         // hi [Kt/8][128] x 16 B, then lo; re-used as the statistics tile
   uint8_t* sB = gsm + 2 * p.a_half;                          // hi [Kt/8][N] x 16 B, then lo
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(kGT, 2) pw_gemm_tc_kernel(const GemmTcP p) {
     for (int e = tid; e < p.Kt * p.N; e += kGT) wmax = fmaxf(wmax, fabsf(weight_at(p, e % p.Kt, e / p.Kt)));
 #pragma unroll
     for (int o = 16; o; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane == 0) red[warp] = wmax;
+    if (lane == 0) red[warp] = wmax;                          // kGT = 256: eight warps
   }
   for (int i = tid; i < p.K0; i += kGT) {
     float sc = 1.f, sh = 0.f;
@@ -139,8 +141,9 @@ __global__ void __launch_bounds__(kGT, 2) pw_gemm_tc_kernel(const GemmTcP p) {
   }
   const uint32_t tmem = tmem_s;
   const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // D = F32, A = B = F16 / BF16
-  const int row = tid & 127, hsel = tid >> 7;                // A load: two threads per row, alternate 8-channel planes
-  const int q = warp & 3, chalf = warp >> 2;                 // epilogue: TMEM lane quarter, alternate 16-column chunks
+  const int row = tid & 127, hsel = tid >> 7;                // A load: kGT / 128 threads per row, interleaved 8-channel planes
+  constexpr int PSTEP = kGT / 128;
+  const int q = warp & 3, chalf = warp >> 2;                 // epilogue: TMEM lane quarter, interleaved 16-column chunks
   const bool vecA0 = ((p.lda0 | p.I0) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.A0) & 15) == 0;
   const bool vecA2 = p.du.A2 && ((p.du.lda2 | p.du.I2) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.du.A2) & 15) == 0;
   const bool vecC = ((p.ldc | p.J | p.du.Jsplit | p.du.ldcb) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(kGT, 2) pw_gemm_tc_kernel(const GemmTcP p) {
     // ---- A operand: NB row blocks x this thread's planes; the loads of UB items (32 B each) are in flight before the first
     //      conversion: 256 threads x 4 x 32 B x 2 CTAs = 64 KB per SM, what the HBM latency-bandwidth product needs ----
     constexpr int UB = 4;
-    const int items = p.NB * ((planes - hsel + 1) >> 1);     // (block, plane) pairs of this thread
+    const int items = p.NB * ((planes - hsel + PSTEP - 1) / PSTEP);   // (block, plane) pairs of this thread
 #pragma unroll 1
     for (int it0 = 0; it0 < items; it0 += UB) {
       float v[UB][8];
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(kGT, 2) pw_gemm_tc_kernel(const GemmTcP p) {
         const int it = it0 + u;
         dst[u] = -1; tfm[u] = false; k0s[u] = 0;
         if (it < items) {
-          const int blk = it & (p.NB - 1), g = hsel + 2 * (it >> nbs);     // NB is 1, 2 or 4
+          const int blk = it & (p.NB - 1), g = hsel + PSTEP * (it >> nbs);   // NB is 1, 2 or 4
           const long long m = mbase + blk * 128 + row;
           const int k0 = g * 8;
           const bool part2 = k0 >= p.K0;
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(kGT, 2) pw_gemm_tc_kernel(const GemmTcP p) {
     for (int blk = 0; blk < p.NB; ++blk) {
       const int erow = q * 32 + lane;
       const long long em = mbase + blk * 128 + erow;
-      for (int c0 = chalf * 16; c0 < p.N; c0 += 32) {
+      for (int c0 = chalf * 16; c0 < p.N; c0 += 16 * PSTEP) {
         uint32_t v[16], w[16];
         ld16(tmem + ((uint32_t)(q * 32) << 16) + (2 * blk) * p.N + c0, v);
         ld16(tmem + ((uint32_t)(q * 32) << 16) + (2 * blk + 1) * p.N + c0, w);
@@ -322,10 +325,13 @@ bool launch_pw_gemm_tc(const float* A, int lda, const float* W, int ldw, int tra
   p.N = (J + 15) / 16 * 16;
   if (p.N > 256 || p.Kt > 288 || J < 8) return false;                        // narrow outputs (the 16 -> 1 head) stay on CUDA cores
   if (du.Jsplit && (du.Jsplit & 15)) return false;                            // rider columns must start on a 16-column chunk
-  // rows per iteration: as many 128-row blocks as keep the A tiles near 64 KB and the 2 NB accumulators inside 256 TMEM columns
-  // (two CTAs per SM): the narrow GEMMs of the full-resolution stages move 16 KB per block and were latency-bound one block at a time
+  // Rows per iteration: as many 128-row blocks (1, 2 or 4) as keep the A tiles within 64 KB and the 2 NB accumulators within 256
+  // TMEM columns (two 256-thread CTAs per SM) -- the narrow GEMMs of the full-resolution stages move 16 KB per block and are
+  // latency-bound one block at a time.  (Four 128-thread CTAs per SM, the shape that halved the inference decoder kernel,
+  // measured the same here: 19.5 ms per step either way.)
   p.NB = 1;
-  while (p.NB < 4 && 2 * (2 * p.NB) * p.N <= 256 && (size_t)(2 * p.NB) * (p.Kt / 8) * 2048 * 2 <= 64 * 1024 && (long long)256 * p.NB * 296 <= M) p.NB *= 2;
+  for (int c = 2; c <= 4; c *= 2)
+    if (2 * c * p.N <= 256 && (size_t)(2 * c) * (p.Kt / 8) * 2048 <= 64 * 1024 && (long long)128 * c * 592 <= M) p.NB = c;
   p.tcols = 32;
   while (p.tcols < 2 * p.NB * p.N) p.tcols <<= 1;
   if (p.tcols > 512) return false;
@@ -337,18 +343,17 @@ bool launch_pw_gemm_tc(const float* A, int lda, const float* W, int ldw, int tra
   if (a_bytes > 2 * (size_t)p.a_half) p.a_half = (int)((a_bytes / 2 + 127) / 128 * 128);     // the statistics tile needs more room than the A tiles
   const size_t smem = 2 * (size_t)p.a_half + 2 * (size_t)p.b_half + (size_t)(2 * p.K0 + p.N + 1) * 4 + (size_t)2 * p.N * 8 + 128;
   if (smem > 200 * 1024) return false;
-  static unsigned long long attr_done = 0;
-  ensure_dyn_smem(pw_gemm_tc_kernel<true>, 200 * 1024, attr_done, "pw_gemm_tc_kernel<f16>");
-  static unsigned long long attr_done_b = 0;
-  ensure_dyn_smem(pw_gemm_tc_kernel<false>, 200 * 1024, attr_done_b, "pw_gemm_tc_kernel<bf16>");
   static int sms = 0;
   if (!sms) { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d); if (sms <= 0) sms = 148; }
+  const long long mtiles = (M + 128 * p.NB - 1) / (128 * p.NB);
   int per_sm = (int)std::min<size_t>(std::min<size_t>(512 / p.tcols, (220 * 1024) / (smem + 1024)), 2);
   if (per_sm < 1) per_sm = 1;
-  const long long mtiles = (M + 128 * p.NB - 1) / (128 * p.NB);
   const int grid = (int)std::min<long long>(mtiles, (long long)sms * per_sm);
-  if (trans) pw_gemm_tc_kernel<false><<<grid, kGT, smem, s>>>(p);      // input gradient: bf16 hi/mid operands
-  else pw_gemm_tc_kernel<true><<<grid, kGT, smem, s>>>(p);            // forward: fp16 hi/lo operands
+  static unsigned long long attr_f = 0, attr_b = 0;
+  ensure_dyn_smem(pw_gemm_tc_kernel<true, 256>, 200 * 1024, attr_f, "pw_gemm_tc_kernel<f16>");
+  ensure_dyn_smem(pw_gemm_tc_kernel<false, 256>, 200 * 1024, attr_b, "pw_gemm_tc_kernel<bf16>");
+  if (trans) pw_gemm_tc_kernel<false, 256><<<grid, 256, smem, s>>>(p);      // input gradient: bf16 hi/mid operands
+  else pw_gemm_tc_kernel<true, 256><<<grid, 256, smem, s>>>(p);            // forward: fp16 hi/lo operands
   return true;
 }
 
