@@ -688,26 +688,38 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     float f1[4] = {0, 0, 0, 0}, f2[4] = {0, 0, 0, 0};
     int cnt = 0;
-    for (long long m = r0 + lane; m < r1; m += lanes) {
-      float4 a4 = *reinterpret_cast<const float4*>(A + m * lda + q * 4);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-      float b[4] = {0, 0, 0, 0};
-      if (MODE == 1 || MODE == 3) {
-        float4 b4 = *reinterpret_cast<const float4*>(Bv + m * ldb + q * 4);
-        b[0] = b4.x; b[1] = b4.y; b[2] = b4.z; b[3] = b4.w;
+    // four rows per iteration: all eight 16-byte loads are issued before the arithmetic (one row at a time left a single load
+    // pair in flight per thread: 3.2 TB/s where the apply kernel streams the same tensors at 5.7 TB/s)
+    constexpr int UR = 4;
+    for (long long m0 = r0 + lane; m0 < r1; m0 += (long long)UR * lanes) {
+      float4 a4[UR], b4[UR];
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        const long long m = m0 + (long long)u * lanes;
+        a4[u] = make_float4(0.f, 0.f, 0.f, 0.f); b4[u] = a4[u];
+        if (m < r1) {
+          a4[u] = *reinterpret_cast<const float4*>(A + m * lda + q * 4);
+          if (MODE == 1 || MODE == 3) b4[u] = *reinterpret_cast<const float4*>(Bv + m * ldb + q * 4);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (MODE == 0) { f1[j] += a[j]; f2[j] = fmaf(a[j], a[j], f2[j]); }
-        if (MODE == 1) {   // a = dy, b = z
-          float zh = (b[j] - mu[j]) * is[j];
-          float dt = act ? a[j] * silu_grad(fmaf(ga[j], zh, be[j])) : a[j];
-          f1[j] += dt; f2[j] = fmaf(dt, zh, f2[j]);
+      for (int u = 0; u < UR; ++u) {
+        if (m0 + (long long)u * lanes >= r1) break;
+        const float a[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w};
+        const float b[4] = {b4[u].x, b4[u].y, b4[u].z, b4[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (MODE == 0) { f1[j] += a[j]; f2[j] = fmaf(a[j], a[j], f2[j]); }
+          if (MODE == 1) {   // a = dy, b = z
+            float zh = (b[j] - mu[j]) * is[j];
+            float dt = act ? a[j] * silu_grad(fmaf(ga[j], zh, be[j])) : a[j];
+            f1[j] += dt; f2[j] = fmaf(dt, zh, f2[j]);
+          }
+          if (MODE == 2) f1[j] += a[j];
+          if (MODE == 3) f1[j] = fmaf(a[j], b[j], f1[j]);
         }
-        if (MODE == 2) f1[j] += a[j];
-        if (MODE == 3) f1[j] = fmaf(a[j], b[j], f1[j]);
       }
-      if (++cnt == 16) {   // short fp32 runs, long double runs
+      if (++cnt == 4) {   // short fp32 runs (16 rows), long double runs
 #pragma unroll
         for (int j = 0; j < 4; ++j) { s1[j] += f1[j]; s2[j] += f2[j]; f1[j] = f2[j] = 0.f; }
         cnt = 0;
