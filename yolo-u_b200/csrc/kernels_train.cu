@@ -318,6 +318,7 @@ static void pw_wgrad_launch(const float* D, int ldd, const float* X, int ldx, fl
 
 void launch_pw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I, int J,
                      cudaStream_t s, InTf tf) {
+  if (launch_pw_wgrad_tc(D, ldd, X, ldx, dW, ldw, M, I, J, s, tf)) return;      // tensor cores (bf16 hi/mid splits, MN-major operands)
   const int cj = J <= 16 ? 16 : J <= 32 ? 32 : 64, ci = I <= 16 ? 16 : I <= 32 ? 32 : 64;
 #define YSP_WG(a, b) if (cj == a && ci == b) return pw_wgrad_launch<a, b>(D, ldd, X, ldx, dW, ldw, M, I, J, s, tf)
   YSP_WG(16, 16); YSP_WG(16, 32); YSP_WG(16, 64); YSP_WG(32, 16); YSP_WG(32, 32); YSP_WG(32, 64);

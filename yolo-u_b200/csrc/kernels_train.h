@@ -25,6 +25,8 @@ void launch_pw_gemm(const float* A, int lda, const float* W, int ldw, int trans,
 // tcgen05 version (kernels_train_tc.cu): returns false when the shape is outside its envelope (the caller runs the FFMA kernel)
 bool launch_pw_gemm_tc(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc,
                        long long M, int I, int J, int beta, cudaStream_t s, double* sums, InTf tf, PwDual du);
+bool launch_pw_wgrad_tc(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I, int J,
+                        cudaStream_t s, InTf tf);
 void launch_pw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I, int J,
                      cudaStream_t s, InTf tf = InTf());
 void launch_dw_conv(const float* X, int ldx, const float* W, float* Y, int ldy, int N, int H, int Wd, int C, int k,

@@ -357,4 +357,206 @@ bool launch_pw_gemm_tc(const float* A, int lda, const float* W, int ldw, int tra
   return true;
 }
 
+// =====================================================================================================================
+// Weight gradient of a 1x1 conv on tcgen05:   dW[j][i] += sum_m D[m][j] * X'[m][i]        (X' = optional input transform of X)
+//
+// As a GEMM the reduction runs over PIXELS: A = D^T (M' = output channels, K' = pixels), B = X'^T (N' = input channels).  Both
+// tensors are pixel-major in memory, i.e. their 8-channel groups are contiguous for a fixed pixel -- exactly the canonical
+// MN-MAJOR no-swizzle UMMA layout ((8 MN elements = 16 B contiguous) x (8 K rows at 16 B) core matrices): the SAME shared-memory
+// tiles [8-channel plane][pixel] x 16 B that every K-major kernel of this library builds are read here with the instruction
+// descriptor's a_major / b_major bits set, SBO = plane pitch (next 8 channels), LBO = 128 B (next 8 pixels).  No transposition.
+//   * per 128-pixel tile: 256 threads load their rows of D and X (two threads per pixel, alternate planes), transform, split into
+//     bf16 hi / mid (gradients underflow fp16), store; one thread issues 8 k-steps x 3 MMAs (M = 128, N = padded I) that
+//     ACCUMULATE ACROSS TILES in TMEM (hi.hi in one accumulator, the cross terms in a second); tiles are double-buffered so the
+//     next tile is loaded while the MMAs of this one run;
+//   * every 32 tiles and at the end the accumulators are flushed with float atomics into dW (pre-zeroed by the caller).
+// Rows j >= J of the A operand are whatever follows the D tile in shared memory: their accumulator rows are never read.
+// =====================================================================================================================
+namespace {
+struct WgradTcP {
+  const float* D; int ldd; const float* X; int ldx; float* dW; int ldw; long long M; int I, J; InTf tf;
+  int JP, IP, N, tcols, tile_bytes, nbuf;    // 8-channel planes of D and X (IP even), padded I, TMEM columns, bytes per tile buffer
+};
+}  // namespace
+
+__global__ void __launch_bounds__(256, 2) pw_wgrad_tc_kernel(const WgradTcP p) {
+  extern __shared__ __align__(128) uint8_t wsm[];
+  // tile buffer b: [D hi JP planes][X hi IP planes][D mid JP planes][X mid IP planes], plane = 128 pixels x 16 B
+  float* sSc = reinterpret_cast<float*>(wsm + (size_t)p.nbuf * p.tile_bytes + 32 * 1024);   // behind the buffers + the A over-read margin
+  float* sSh = sSc + p.IP * 8;
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ uint32_t tmem_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool tfon = p.tf.gamma != nullptr;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_s)), "r"((uint32_t)p.tcols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < p.IP * 8; i += 256) {
+    float sc = 1.f, sh = 0.f;
+    if (tfon && i < p.I) { sc = p.tf.gamma[i] * p.tf.invstd[i]; sh = p.tf.beta[i] - p.tf.mean[i] * sc; }
+    sSc[i] = sc; sSh[i] = sh;
+  }
+  // the over-read margin of the A operand must hold finite numbers nowhere in particular; zero it once (it also covers the
+  // first use of a buffer's unused tail)
+  for (int i = tid; i < (p.nbuf * p.tile_bytes + 32 * 1024) / 16; i += 256) reinterpret_cast<uint4*>(wsm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_s;
+  // D = F32, A = B = BF16, both MN-major (bits 15, 16), N = padded I, M = 128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const int row = tid & 127, hsel = tid >> 7;
+  const bool vecD = ((p.ldd | p.J) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0;
+  const bool vecX = ((p.ldx | p.I) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0;
+  const int planes = p.JP + p.IP, half_bytes = planes * 2048;
+  const long long mtiles = (p.M + 127) / 128;
+  uint32_t par[2] = {0u, 0u};
+  int used[2] = {0, 0};                                    // MMAs in flight on a buffer
+  bool fresh = true;                                       // the accumulators start from zero
+  int since_flush = 0, t = 0;
+  auto flush = [&]() {
+    // consume the outstanding per-buffer commits (a commit covers every MMA issued before it): afterwards nothing is in flight
+    for (int bb = 0; bb < 2; ++bb)
+      if (used[bb]) { mbar_wait_parity(&bar[bb], par[bb]); par[bb] ^= 1; used[bb] = 0; }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3, chalf = warp >> 2, j = q * 32 + lane;
+    for (int c0 = chalf * 16; c0 < p.N; c0 += 32) {
+      uint32_t v[16], w[16];
+      ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+      ld16(tmem + ((uint32_t)(q * 32) << 16) + p.N + c0, w);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (j < p.J) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < p.I) atomicAdd(&p.dW[(size_t)j * p.ldw + c0 + i], __uint_as_float(v[i]) + __uint_as_float(w[i]));
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    fresh = true; since_flush = 0;
+  };
+#pragma unroll 1
+  for (long long mt = blockIdx.x; mt < mtiles; mt += gridDim.x, ++t) {
+    const int b = p.nbuf > 1 ? (t & 1) : 0;
+    if (used[b]) {                                         // the MMAs that last read this buffer
+      mbar_wait_parity(&bar[b], par[b]);
+      par[b] ^= 1; used[b] = 0;
+    }
+    uint8_t* buf = wsm + (size_t)b * p.tile_bytes;
+    const long long m = mt * 128 + row;
+    constexpr int UB = 4;
+    const int items = (planes - hsel + 1) >> 1;
+#pragma unroll 1
+    for (int it0 = 0; it0 < items; it0 += UB) {
+      float v[UB][8];
+      int gs[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int it = it0 + u;
+        gs[u] = -1;
+        if (it < items) {
+          const int g = hsel + 2 * it;
+          gs[u] = g;
+          const bool isx = g >= p.JP;
+          const int k0 = (isx ? g - p.JP : g) * 8;
+          const float* src = isx ? p.X + m * p.ldx + k0 : p.D + m * p.ldd + k0;
+          const int valid = (isx ? p.I : p.J) - k0;
+          if (m < p.M && valid >= 8 && (isx ? vecX : vecD)) {
+            const float4 a = *reinterpret_cast<const float4*>(src), bq = *reinterpret_cast<const float4*>(src + 4);
+            v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = bq.x; v[u][5] = bq.y; v[u][6] = bq.z; v[u][7] = bq.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[u][j] = (m < p.M && j < valid) ? src[j] : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        if (gs[u] < 0) continue;
+        const int g = gs[u];
+        if (tfon && g >= p.JP && m < p.M) {
+          const int k0 = (g - p.JP) * 8;
+          const float4 c0 = *reinterpret_cast<const float4*>(sSc + k0), c1 = *reinterpret_cast<const float4*>(sSc + k0 + 4);
+          const float4 h0 = *reinterpret_cast<const float4*>(sSh + k0), h1 = *reinterpret_cast<const float4*>(sSh + k0 + 4);
+          const float sc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            float2 x = __ffma2_rn(make_float2(v[u][j], v[u][j + 1]), make_float2(sc[j], sc[j + 1]), make_float2(sh[j], sh[j + 1]));
+            if (p.tf.act) x = silu2_f(x);
+            v[u][j] = k0 + j < p.I ? x.x : 0.f; v[u][j + 1] = k0 + j + 1 < p.I ? x.y : 0.f;
+          }
+        }
+        uint4 h, l;
+        split2_bf16(v[u][0], v[u][1], h.x, l.x); split2_bf16(v[u][2], v[u][3], h.y, l.y);
+        split2_bf16(v[u][4], v[u][5], h.z, l.z); split2_bf16(v[u][6], v[u][7], h.w, l.w);
+        *reinterpret_cast<uint4*>(buf + g * 2048 + row * 16) = h;
+        *reinterpret_cast<uint4*>(buf + half_bytes + g * 2048 + row * 16) = l;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t dh = s32(buf), xh = dh + p.JP * 2048, dm = dh + half_bytes, xm = dm + p.JP * 2048;
+      for (int ks = 0; ks < 8; ++ks) {                       // 16 pixels per step: +256 B inside every plane
+        const uint64_t ah = desc_nosw(dh + ks * 256, 128u, 2048u), am = desc_nosw(dm + ks * 256, 128u, 2048u);
+        const uint64_t bh = desc_nosw(xh + ks * 256, 128u, 2048u), bm = desc_nosw(xm + ks * 256, 128u, 2048u);
+        const uint32_t acc0 = (fresh && ks == 0) ? 0u : 1u;
+        umma_f16(tmem, ah, bh, idesc, acc0);                 // hi . hi
+        umma_f16(tmem + p.N, am, bh, idesc, acc0);           // mid . hi
+        umma_f16(tmem + p.N, ah, bm, idesc, 1u);             // hi . mid
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&bar[b])) : "memory");
+    }
+    used[b] = 1; fresh = false;
+    if (++since_flush == 32) flush();
+  }
+  if (since_flush) flush();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tcols) : "memory");
+  }
+}
+
+bool launch_pw_wgrad_tc(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I, int J, cudaStream_t s,
+                        InTf tf) {
+  static const bool off = getenv("YSP_TRAIN_NO_TC") != nullptr || getenv("YSP_TRAIN_NO_WGRAD_TC") != nullptr;
+  // widest layers only (I + J >= 128; measured 19.16 -> 18.95 ms per step, any lower threshold was slower): the FFMA kernel already streams the narrow full-resolution ones (J = 16, I = 32) at 3-4 TB/s, and 24 MMAs
+  // with 7/8 of the M = 128 rows unused per 24 KB tile would make those tensor-pipe-bound
+  static const int minw = getenv("YSP_WGRAD_TC_MINW") ? atoi(getenv("YSP_WGRAD_TC_MINW")) : 128;
+  if (off || M < 4096 || J > 128 || J < 8 || I < 8 || I + J < minw) return false;
+  WgradTcP p = {};
+  p.D = D; p.ldd = ldd; p.X = X; p.ldx = ldx; p.dW = dW; p.ldw = ldw; p.M = M; p.I = I; p.J = J; p.tf = tf;
+  p.JP = (J + 7) / 8;
+  p.N = (I + 15) / 16 * 16;
+  p.IP = p.N / 8;
+  if (p.N > 256) return false;
+  p.tcols = 32;
+  while (p.tcols < 2 * p.N) p.tcols <<= 1;
+  p.tile_bytes = 2 * (p.JP + p.IP) * 2048;
+  p.nbuf = 2 * (size_t)p.tile_bytes + 32 * 1024 + (size_t)p.IP * 64 + 256 <= 200 * 1024 ? 2 : 1;
+  const size_t smem = (size_t)p.nbuf * p.tile_bytes + 32 * 1024 + (size_t)p.IP * 64 + 256;
+  if (smem > 200 * 1024) return false;
+  static unsigned long long attr_done = 0;
+  ensure_dyn_smem(pw_wgrad_tc_kernel, 200 * 1024, attr_done, "pw_wgrad_tc_kernel");
+  static int sms = 0;
+  if (!sms) { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d); if (sms <= 0) sms = 148; }
+  int per_sm = (int)std::min<size_t>(std::min<size_t>(512 / p.tcols, (220 * 1024) / (smem + 1024)), 2);
+  if (per_sm < 1) per_sm = 1;
+  const long long mtiles = (M + 127) / 128;
+  const int grid = (int)std::min<long long>(mtiles, (long long)sms * per_sm);
+  pw_wgrad_tc_kernel<<<grid, 256, smem, s>>>(p);
+  return true;
+}
+
 }  // namespace ysp
