@@ -51,7 +51,7 @@ struct Dlc {                  // Upsample(bilinear x2) + DoubleLightConv
   int Cin, C;
   ConvBN p, q, p2, q2;
   Lin r;
-  float* u;
+  const float* xl; int ldxl, h, w;      // the low-resolution input (read again by the weight gradients)
 };
 
 struct Ctx {
@@ -285,35 +285,61 @@ void ghost_bwd(Ctx& c, Ghost& g, const float* dout, int ldd, float* dxin, int ld
 }
 
 // ---- Upsample + DoubleLightConv ---------------------------------------------------------------------------------------------
+// Both 1x1 convs that read the upsampled tensor (conv.0.conv1 and residual_conv) run at LOW resolution: bilinear x2 is linear
+// with unit weight sums, so  conv1x1(up2(x)) + b == up2(conv1x1(x) + b)  (the identity the inference decoder uses,
+// DESIGN §4).  The upsampled Cin-channel tensor is never formed: one GEMM over a quarter of the rows writes
+// plow = [conv1 | residual_conv + bias], two up2 passes write z_p and r at full resolution, and the backward takes the
+// adjoint route -- up2^T of the two C-channel gradients, then weight / bias / input gradients from GEMMs over the low-res
+// rows.  Per full-resolution row this moves 2C + C (+ C for the statistics) floats forward and 2C + 2C backward where the
+// direct form moved 4 Cin + 2C and 6 Cin + 5C (Cin = 2C).
 void dlc_fwd(Ctx& c, Dlc& d, const float* xl, int ldx, int N, int h, int w, float* out, int ldo) {
   const int H = 2 * h, W = 2 * w;
-  const long long M = (long long)N * H * W;
-  d.u = c.alloc((size_t)M * d.Cin);
+  const long long M = (long long)N * H * W, Ml = (long long)N * h * w;
+  d.xl = xl; d.ldxl = ldx; d.h = h; d.w = w;
+  float* plow = c.alloc((size_t)Ml * 2 * d.C);
   float* r = c.alloc((size_t)M * d.C);
   const bool lazy = dw_tiled_shape(H, W, 3);
-  static const bool no_dual = getenv("YSP_TRAIN_NO_DUAL") != nullptr;      // A/B switch: the two GEMM fusions off
-  const bool ride = lazy && d.C % 4 == 0 && !no_dual;      // the two-output GEMM splits its columns in groups of four
+  static const bool no_dual = getenv("YSP_TRAIN_NO_DUAL") != nullptr;      // A/B switch: the two-output GEMM off
+  ConvBN& u = d.p;
+  u.x = xl; u.ldx = ldx; u.N = N; u.H = H; u.W = W; u.src = nullptr;
+  u.z = c.alloc((size_t)M * d.C);
+  u.mean = c.alloc(d.C);
+  u.invstd = c.alloc(d.C);
+  double* sums = c.sums(2 * (size_t)d.C);
+  c.need_dz((size_t)M * d.C);
+  float* pb = lazy ? nullptr : c.alloc((size_t)M * d.C);
   if (!c.dry) {
-    launch_up2(xl, ldx, d.u, d.Cin, N, h, w, d.Cin, c.s);
-    c.launches += 1;
-    c.acct((double)M * (d.Cin * 0.25 + d.Cin));
-    if (!ride) {
-      launch_pw_gemm(d.u, d.Cin, c.P + d.r.w, d.Cin, 0, c.P + d.r.b, r, d.C, M, d.Cin, d.C, 0, c.s);   // residual_conv
+    if (!no_dual) {
+      PwDual du;
+      du.Jsplit = d.C; du.Wb = c.P + d.r.w; du.ldwb = d.Cin; du.biasb = c.P + d.r.b; du.Cb = plow + d.C; du.ldcb = 2 * d.C;
+      launch_pw_gemm(xl, ldx, c.P + u.w, d.Cin, 0, nullptr, plow, 2 * d.C, Ml, d.Cin, 2 * d.C, 0, c.s, nullptr, InTf(), du);
+    } else {
+      launch_pw_gemm(xl, ldx, c.P + u.w, d.Cin, 0, nullptr, plow, 2 * d.C, Ml, d.Cin, d.C, 0, c.s);
+      launch_pw_gemm(xl, ldx, c.P + d.r.w, d.Cin, 0, c.P + d.r.b, plow + d.C, 2 * d.C, Ml, d.Cin, d.C, 0, c.s);
       c.launches += 1;
-      c.acct((double)M * (d.Cin + d.C));
+    }
+    launch_up2(plow, 2 * d.C, u.z, d.C, N, h, w, d.C, c.s);
+    launch_up2(plow + d.C, 2 * d.C, r, d.C, N, h, w, d.C, c.s);
+    BnRef bn = {c.P + u.g, c.P + u.b, u.mean, u.invstd};
+    launch_col_reduce(0, u.z, d.C, nullptr, 0, bn, 0, sums, d.C, 1, M, c.s);
+    launch_bn_finalize(sums, d.C, M, kBnEps, c.momentum, u.mean, u.invstd, c.S ? c.S + u.rm : nullptr,
+                       c.S ? c.S + u.rv : nullptr, c.s);
+    c.launches += 5;
+    c.acct((double)Ml * (d.Cin + 2 * d.C) + (double)Ml * 2 * d.C + (double)M * 2 * d.C + (double)M * d.C);
+    if (!lazy) {
+      launch_bn_apply(u.z, d.C, bn, 0, nullptr, 0, pb, d.C, d.C, M, c.s);
+      c.launches += 1;
+      c.acct((double)M * d.C * 2);
     }
   }
-  // the three inner normalised tensors are never written: each consumer applies its producer's BN (+SiLU) on load
+  // the inner normalised tensors are never written: each consumer applies its producer's BN (+SiLU) on load
   if (lazy) {
-    convbn_fwd(c, d.p, d.u, d.Cin, N, H, W, nullptr, 0, nullptr, 0, nullptr, ride ? &d.r : nullptr, r);      // conv.0.conv1 and residual_conv: one GEMM
     convbn_fwd(c, d.q, nullptr, 0, N, H, W, nullptr, 0, nullptr, 0, &d.p);
     convbn_fwd(c, d.p2, nullptr, 0, N, H, W, nullptr, 0, nullptr, 0, &d.q);
     convbn_fwd(c, d.q2, nullptr, 0, N, H, W, out, ldo, r, d.C, &d.p2);                               // out = conv(x) + residual
   } else {
-    float* pb = c.alloc((size_t)M * d.C);
     float* qb = c.alloc((size_t)M * d.C);
     float* p2b = c.alloc((size_t)M * d.C);
-    convbn_fwd(c, d.p, d.u, d.Cin, N, H, W, pb, d.C, nullptr, 0);
     convbn_fwd(c, d.q, pb, d.C, N, H, W, qb, d.C, nullptr, 0);
     convbn_fwd(c, d.p2, qb, d.C, N, H, W, p2b, d.C, nullptr, 0);
     convbn_fwd(c, d.q2, p2b, d.C, N, H, W, out, ldo, r, d.C);                                        // out = conv(x) + residual
@@ -321,31 +347,34 @@ void dlc_fwd(Ctx& c, Dlc& d, const float* xl, int ldx, int N, int h, int w, floa
 }
 
 void dlc_bwd(Ctx& c, Dlc& d, const float* dout, int ldd, float* dxl, int lddx) {
-  const int N = d.p.N, H = d.p.H, W = d.p.W;
-  const long long M = (long long)N * H * W;
+  const int N = d.p.N, H = d.p.H, W = d.p.W, h = d.h, w = d.w;
+  const long long M = (long long)N * H * W, Ml = (long long)N * h * w;
   float* d1 = c.alloc((size_t)M * d.C);
   float* d2 = c.alloc((size_t)M * d.C);
-  float* dU = c.alloc((size_t)M * d.Cin);
+  float* dpl = c.alloc((size_t)Ml * 2 * d.C);        // gradient of plow: [d conv1 | d residual_conv]
   double* bs = c.sums(2 * (size_t)d.C);
+  double* ps = c.sums(2 * (size_t)d.C);
   convbn_bwd(c, d.q2, dout, ldd, d1, d.C, 0, d.C);
   convbn_bwd(c, d.p2, d1, d.C, d2, d.C, 0, d.C);
   convbn_bwd(c, d.q, d2, d.C, d1, d.C, 0, d.C);
-  // dU = dz_p * W_p + dout * W_r: both input-gradient GEMMs of the upsampled tensor as one two-operand GEMM
-  static const bool no_dual = getenv("YSP_TRAIN_NO_DUAL") != nullptr;
-  convbn_bwd(c, d.p, d1, d.C, dU, d.Cin, 0, d.Cin, no_dual ? nullptr : &d.r, dout, ldd);
   if (c.dry) return;
-  BnRef none = {};
-  launch_col_reduce(2, dout, ldd, nullptr, 0, none, 0, bs, d.C, 1, M, c.s);
+  // conv.0.conv1: BatchNorm backward at full resolution, everything after it on the low-resolution rows
+  ConvBN& u = d.p;
+  BnRef bn = {c.P + u.g, c.P + u.b, u.mean, u.invstd}, none = {};
+  launch_col_reduce(1, d1, d.C, u.z, d.C, bn, 0, ps, d.C, 1, M, c.s);
+  launch_bn_bwd_apply(d1, d.C, u.z, d.C, bn, 0, ps, c.dz, d.C, c.G + u.g, c.G + u.b, d.C, M, c.s);
+  launch_up2_bwd(c.dz, d.C, dpl, 2 * d.C, N, h, w, d.C, c.s);
+  launch_up2_bwd(dout, ldd, dpl + d.C, 2 * d.C, N, h, w, d.C, c.s);
+  launch_col_reduce(2, dpl + d.C, 2 * d.C, nullptr, 0, none, 0, bs, d.C, 1, Ml, c.s);     // d bias: up2^T preserves column sums
   launch_add_sums(bs, c.G + d.r.b, d.C, 1, c.s);
-  launch_pw_wgrad(dout, ldd, d.u, d.Cin, c.G + d.r.w, d.Cin, M, d.Cin, d.C, c.s);
-  if (no_dual) {
-    launch_pw_gemm(dout, ldd, c.P + d.r.w, d.Cin, 1, nullptr, dU, d.Cin, M, d.C, d.Cin, 1, c.s);
-    c.launches += 1;
-    c.acct((double)M * (d.C + 2 * d.Cin));
-  }
-  launch_up2_bwd(dU, d.Cin, dxl, lddx, N, H / 2, W / 2, d.Cin, c.s);
-  c.launches += 4;
-  c.acct((double)M * (d.C + (d.C + d.Cin) + d.Cin * 1.25));
+  launch_pw_wgrad(dpl, 2 * d.C, d.xl, d.ldxl, c.G + u.w, d.Cin, Ml, d.Cin, d.C, c.s);
+  launch_pw_wgrad(dpl + d.C, 2 * d.C, d.xl, d.ldxl, c.G + d.r.w, d.Cin, Ml, d.Cin, d.C, c.s);
+  // dxl = d conv1 * W_p + d residual * W_r: one two-operand GEMM
+  PwDual du;
+  du.A2 = dpl + d.C; du.lda2 = 2 * d.C; du.W2 = c.P + d.r.w; du.ldw2 = d.Cin; du.I2 = d.C;
+  launch_pw_gemm(dpl, 2 * d.C, c.P + u.w, d.Cin, 1, nullptr, dxl, lddx, Ml, d.C, d.Cin, 0, c.s, nullptr, InTf(), du);
+  c.launches += 9;
+  c.acct((double)M * d.C * (2 + 3 + 1 + 1) + (double)Ml * (2 * d.C + d.C + 2 * (d.C + d.Cin) + 2 * d.C + d.Cin));
 }
 
 // ---- whole step -----------------------------------------------------------------------------------------------------------
