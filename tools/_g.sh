@@ -1,8 +1,7 @@
-set -x
 mkdir -p gpurun_out/r8
 timeout 600 python -m pytest tests/test_gpu_train.py tests/test_gpu_train_ddp.py -x -q -m gpu > gpurun_out/r8/pytest_train.log 2>&1; echo "pytest rc=$?"
 tail -15 gpurun_out/r8/pytest_train.log
-for v in "" "YSP_TRAIN_NO_DUAL=1"; do
+for v in "" "YSP_TRAIN_NO_DWFUSE=1"; do
   env $v timeout 300 python bench.py --workload train --steps 20 --warmup 3 --no-cpu 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('$v', d['value'], d['ms_per_step'], d['loss'], d['gpu_launches'], d['roofline'])"
+import json,sys; d=json.loads(sys.stdin.read()); print('$v', d['value'], d['ms_per_step'], d['loss'], d['gpu_launches'], d['roofline']['achieved'])"
 done

@@ -12,6 +12,7 @@
 // Weights stay in PyTorch's own layouts ([Cout][Cin] and [C][k*k]) so the flat parameter buffer IS the state_dict.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "kernels_train.h"
@@ -652,16 +653,275 @@ bool launch_dw_fwd_stats(const float* X, int ldx, const float* W, float* Y, int 
 }
 
 // =====================================================================================================================
+__device__ __forceinline__ float silu_grad(float t) {
+  const float sg = sigmoid_mufu(t);
+  return sg * (1.f + t * (1.f - sg));
+}
+
+// Backward of a depthwise ConvBN unit in ONE pass (the DoubleLightConv units, K = 3): BatchNorm backward, input gradient,
+// weight gradient and -- for the unit that PRODUCED the conv input -- that unit's BatchNorm-backward sums.
+//   dz = gamma * invstd * (dt - S1/M - zhat * S2/M),  dt = dy * act'(gamma * zhat + beta)      (S1, S2: col_reduce MODE 1)
+//   dx[p]      = sum_tap W[tap] * dz[p - tap]                                                  (zero padding)
+//   dW[c][tap] = sum_p dz[p] * x'[p + tap],  x' = producer's BN (+act) applied to its raw output (InTf), zero outside the image
+//   producer sums: sum dx * act_p'(.), sum dx * act_p'(.) * zhat_p
+// The unfused chain (bn_bwd_apply -> dz, dw_tiled<2>(dz, x), dw_tiled<1>(dz) and col_reduce<1>(dx, z_p) for the producer) moved
+// 3 + 2.3 + 2.3 + 2 floats per element; here dy, z, x come in once with a one-pixel halo (3 x 1.27) and dx goes out: 4.8.
+// dz is computed at the halo pixels too (each CTA recomputes its border), never written.  Same tiling as dw_tiled_kernel:
+// CTA = one 16-channel group, persistent over 16x16-pixel tiles, thread = one channel quad x 4 consecutive pixels.
+// =====================================================================================================================
+struct DwBwdP {
+  const float* DY; int ldd; const float* Z; int ldz; BnRef bn; int act; const double* sums;
+  const float* X; int ldx; InTf tf; const float* W; float* DX; int lddx; float* dW; float* dgamma; float* dbeta; double* psums;
+  int N, H, Wd, C; double invM;
+};
+
+template <int K>
+__global__ void __launch_bounds__(256, 2) dw_bwd_fused_kernel(const DwBwdP p) {
+  constexpr int TY = 16, TX = 16, IH = TY + K - 1, IW = TX + K - 1, PS = 20, KK = K * K, PAD = K / 2;
+  extern __shared__ __align__(16) float fsm[];
+  float* sDz = fsm;                      // [IH*IW][PS]  dz with halo
+  float* sIn = sDz + IH * IW * PS;       // [IH*IW][PS]  x' with halo
+  float* sW = sIn + IH * IW * PS;        // [KK][16] flipped taps
+  float* sWa = sW + KK * 16;             // [16][KK] block accumulators of dW
+  __shared__ double sRed[2][16];
+  __shared__ __align__(16) float sBn[6][16];      // this unit: mean, invstd, gamma, beta, S1/M, S2/M
+  __shared__ __align__(16) float sPr[4][16];      // producer: scale, shift (x' = z * sc + sh), mean, invstd
+  const int tid = threadIdx.x;
+  const int H = p.H, Wd = p.Wd, C = p.C;
+  const int tiles_x = (Wd + TX - 1) / TX, tiles_y = (H + TY - 1) / TY;
+  const int ntiles = p.N * tiles_y * tiles_x;
+  const int cg = blockIdx.y * 16;
+  const int nq = min(4, (C - cg) >> 2);
+  const int q = tid & 3, txi = (tid >> 2) & 3, ty = tid >> 4;
+  const bool tfon = p.tf.gamma != nullptr;
+  for (int e = tid; e < KK * 16; e += 256) {
+    const int tp = e >> 4, c = e & 15;
+    sW[(KK - 1 - tp) * 16 + c] = (cg + c < C) ? p.W[(size_t)(cg + c) * KK + tp] : 0.f;
+  }
+  for (int e = tid; e < 16 * KK; e += 256) sWa[e] = 0.f;
+  if (tid < 32) sRed[tid >> 4][tid & 15] = 0.0;
+  if (tid < 16) {
+    const int ch = cg + tid;
+    const bool ok = ch < C;
+    sBn[0][tid] = ok ? p.bn.mean[ch] : 0.f; sBn[1][tid] = ok ? p.bn.invstd[ch] : 0.f;
+    sBn[2][tid] = ok ? p.bn.gamma[ch] : 0.f; sBn[3][tid] = ok ? p.bn.beta[ch] : 0.f;
+    sBn[4][tid] = ok ? (float)(p.sums[ch] * p.invM) : 0.f; sBn[5][tid] = ok ? (float)(p.sums[C + ch] * p.invM) : 0.f;
+    float sc = 1.f, sh = 0.f, mu = 0.f, is = 0.f;
+    if (tfon && ok) { is = p.tf.invstd[ch]; mu = p.tf.mean[ch]; sc = p.tf.gamma[ch] * is; sh = p.tf.beta[ch] - mu * sc; }
+    sPr[0][tid] = sc; sPr[1][tid] = sh; sPr[2][tid] = mu; sPr[3][tid] = is;
+    if (blockIdx.x == 0 && ok) {          // d gamma = S2, d beta = S1 (accumulated: the flat gradient buffer is pre-zeroed)
+      p.dbeta[ch] += (float)p.sums[ch]; p.dgamma[ch] += (float)p.sums[C + ch];
+    }
+  }
+  __syncthreads();
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  float wacc[KK][4];
+#pragma unroll
+  for (int tp = 0; tp < KK; ++tp) wacc[tp][0] = wacc[tp][1] = wacc[tp][2] = wacc[tp][3] = 0.f;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int t = tile;
+    const int tx0 = (t % tiles_x) * TX; t /= tiles_x;
+    const int ty0 = (t % tiles_y) * TY;
+    const int n = t / tiles_y;
+    __syncthreads();
+    constexpr int TOT = IH * IW * 4, NL = (TOT + 255) / 256;     // every item of a thread has channel quad q (256 % 4 == 0)
+    {
+      // ---- dz tile: dy and z of HB items in flight before the arithmetic ----
+      constexpr int HB = (NL + 1) / 2;
+      const float4 mu = *reinterpret_cast<const float4*>(&sBn[0][q * 4]), is = *reinterpret_cast<const float4*>(&sBn[1][q * 4]);
+      const float4 ga = *reinterpret_cast<const float4*>(&sBn[2][q * 4]), be = *reinterpret_cast<const float4*>(&sBn[3][q * 4]);
+      const float4 m1 = *reinterpret_cast<const float4*>(&sBn[4][q * 4]), m2 = *reinterpret_cast<const float4*>(&sBn[5][q * 4]);
+#pragma unroll
+      for (int u0 = 0; u0 < NL; u0 += HB) {
+        float4 dv[HB], zv[HB];
+        bool in[HB];
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+          const int i = tid + (u0 + u) * 256, pp = i >> 2;
+          const int iy = ty0 + pp / IW - PAD, ix = tx0 + pp % IW - PAD;
+          dv[u] = make_float4(0.f, 0.f, 0.f, 0.f); zv[u] = dv[u];
+          in[u] = u0 + u < NL && i < TOT && q < nq && iy >= 0 && iy < H && ix >= 0 && ix < Wd;
+          if (in[u]) {
+            const size_t pix = (size_t)(n * H + iy) * Wd + ix;
+            dv[u] = *reinterpret_cast<const float4*>(p.DY + pix * p.ldd + cg + q * 4);
+            zv[u] = *reinterpret_cast<const float4*>(p.Z + pix * p.ldz + cg + q * 4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+          const int i = tid + (u0 + u) * 256;
+          if (u0 + u >= NL || i >= TOT) break;
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (in[u]) {
+#define YSP_DZ(f)                                                                                       \
+  {                                                                                                     \
+    const float zh = (zv[u].f - mu.f) * is.f;                                                           \
+    const float dt = p.act ? dv[u].f * silu_grad(fmaf(ga.f, zh, be.f)) : dv[u].f;                       \
+    o.f = ga.f * is.f * (dt - m1.f - zh * m2.f);                                                        \
+  }
+            YSP_DZ(x) YSP_DZ(y) YSP_DZ(z) YSP_DZ(w)
+#undef YSP_DZ
+          }
+          *reinterpret_cast<float4*>(sDz + (i >> 2) * PS + q * 4) = o;
+        }
+      }
+    }
+    {
+      // ---- x' tile ----
+      float4 xv[NL];
+      bool in[NL];
+#pragma unroll
+      for (int u = 0; u < NL; ++u) {
+        const int i = tid + u * 256, pp = i >> 2;
+        const int iy = ty0 + pp / IW - PAD, ix = tx0 + pp % IW - PAD;
+        xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        in[u] = i < TOT && q < nq && iy >= 0 && iy < H && ix >= 0 && ix < Wd;
+        if (in[u]) xv[u] = *reinterpret_cast<const float4*>(p.X + ((size_t)(n * H + iy) * Wd + ix) * p.ldx + cg + q * 4);
+      }
+      const float4 sc = *reinterpret_cast<const float4*>(&sPr[0][q * 4]), sh = *reinterpret_cast<const float4*>(&sPr[1][q * 4]);
+#pragma unroll
+      for (int u = 0; u < NL; ++u) {
+        const int i = tid + u * 256;
+        if (i >= TOT) break;
+        float4 v = xv[u];
+        if (tfon && in[u]) {
+          v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+          if (p.tf.act) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+        }
+        *reinterpret_cast<float4*>(sIn + (i >> 2) * PS + q * 4) = v;
+      }
+    }
+    __syncthreads();
+    const int y = ty0 + ty;
+    const bool rowok = y < H && q < nq;
+    // ---- input gradient (flipped taps over the dz tile) ----
+    {
+      float4 acc[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        const float* rp = sDz + ((ty + r) * IW + txi * 4) * PS + q * 4;
+        float4 v[K + 3], w[K];
+#pragma unroll
+        for (int j = 0; j < K + 3; ++j) v[j] = *reinterpret_cast<const float4*>(rp + j * PS);
+#pragma unroll
+        for (int s2i = 0; s2i < K; ++s2i) w[s2i] = *reinterpret_cast<const float4*>(sW + (r * K + s2i) * 16 + q * 4);
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+          for (int s2i = 0; s2i < K; ++s2i) {
+            const float2 lo = __ffma2_rn(make_float2(v[o + s2i].x, v[o + s2i].y), make_float2(w[s2i].x, w[s2i].y), make_float2(acc[o].x, acc[o].y));
+            const float2 hi = __ffma2_rn(make_float2(v[o + s2i].z, v[o + s2i].w), make_float2(w[s2i].z, w[s2i].w), make_float2(acc[o].z, acc[o].w));
+            acc[o] = make_float4(lo.x, lo.y, hi.x, hi.y);
+          }
+      }
+      if (rowok) {
+        const float4 pmu = *reinterpret_cast<const float4*>(&sPr[2][q * 4]), pis = *reinterpret_cast<const float4*>(&sPr[3][q * 4]);
+        const float4 psc = *reinterpret_cast<const float4*>(&sPr[0][q * 4]), psh = *reinterpret_cast<const float4*>(&sPr[1][q * 4]);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int x = tx0 + txi * 4 + o;
+          if (x >= Wd) break;
+          const size_t pix = (size_t)(n * H + y) * Wd + x;
+          const float4 a = acc[o];
+          *reinterpret_cast<float4*>(p.DX + pix * p.lddx + cg + q * 4) = a;
+          if (p.psums) {       // the producer's BatchNorm-backward sums; its raw output at this pixel was just read (cache hit)
+            const float4 zr = *reinterpret_cast<const float4*>(p.X + pix * p.ldx + cg + q * 4);
+#define YSP_PS(f, j)                                                                                    \
+  {                                                                                                     \
+    const float zh = (zr.f - pmu.f) * pis.f;                                                            \
+    const float dt = p.tf.act ? a.f * silu_grad(fmaf(zr.f, psc.f, psh.f)) : a.f;                        \
+    s1[j] += dt; s2[j] = fmaf(dt, zh, s2[j]);                                                           \
+  }
+            YSP_PS(x, 0) YSP_PS(y, 1) YSP_PS(z, 2) YSP_PS(w, 3)
+#undef YSP_PS
+          }
+        }
+      }
+    }
+    // ---- weight gradient: dz at the centre pixels against the x' window ----
+    {
+      float4 d[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) d[o] = *reinterpret_cast<const float4*>(sDz + ((ty + PAD) * IW + txi * 4 + o + PAD) * PS + q * 4);
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        const float* rp = sIn + ((ty + r) * IW + txi * 4) * PS + q * 4;
+        float4 v[K + 3];
+#pragma unroll
+        for (int j = 0; j < K + 3; ++j) v[j] = *reinterpret_cast<const float4*>(rp + j * PS);
+#pragma unroll
+        for (int s2i = 0; s2i < K; ++s2i)
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            wacc[r * K + s2i][0] = fmaf(d[o].x, v[o + s2i].x, wacc[r * K + s2i][0]);
+            wacc[r * K + s2i][1] = fmaf(d[o].y, v[o + s2i].y, wacc[r * K + s2i][1]);
+            wacc[r * K + s2i][2] = fmaf(d[o].z, v[o + s2i].z, wacc[r * K + s2i][2]);
+            wacc[r * K + s2i][3] = fmaf(d[o].w, v[o + s2i].w, wacc[r * K + s2i][3]);
+          }
+      }
+    }
+  }
+  // ---- block reductions (lanes with equal q: xor 4, 8, 16) ----
+  __syncthreads();
+  if (p.psums) {
+    double a1[4], a2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a1[j] = s1[j]; a2[j] = s2[j];
+#pragma unroll
+      for (int m = 4; m < 32; m <<= 1) {
+        a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], m);
+        a2[j] += __shfl_xor_sync(0xffffffffu, a2[j], m);
+      }
+    }
+    if ((tid & 31) < 4 && q < nq)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { atomicAdd(&sRed[0][q * 4 + j], a1[j]); atomicAdd(&sRed[1][q * 4 + j], a2[j]); }
+  }
+#pragma unroll
+  for (int tp = 0; tp < KK; ++tp)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = wacc[tp][j];
+#pragma unroll
+      for (int m = 4; m < 32; m <<= 1) a += __shfl_xor_sync(0xffffffffu, a, m);
+      if ((tid & 31) < 4) atomicAdd(&sWa[(q * 4 + j) * KK + tp], a);
+    }
+  __syncthreads();
+  if (p.psums && tid < 32 && cg + (tid & 15) < C) atomicAdd(&p.psums[(tid >> 4) * C + cg + (tid & 15)], sRed[tid >> 4][tid & 15]);
+  for (int e = tid; e < 16 * KK; e += 256)
+    if (cg + e / KK < C) atomicAdd(&p.dW[(size_t)cg * KK + e], sWa[e]);
+}
+
+bool launch_dw_bwd_fused(const float* DY, int ldd, const float* Z, int ldz, const BnRef& bn, int act, const double* sums,
+                         const float* X, int ldx, InTf tf, const float* W, float* DX, int lddx, float* dW, float* dgamma,
+                         float* dbeta, double* psums, int N, int H, int Wd, int C, int k, cudaStream_t s) {
+  static const bool off = getenv("YSP_TRAIN_NO_DWFUSE") != nullptr;
+  if (off || k != 3 || !dw_tiled_shape(H, Wd, k) || (C & 3)) return false;
+  constexpr int K = 3;
+  constexpr size_t smem = sizeof(float) * (2 * (16 + K - 1) * (16 + K - 1) * 20 + 2 * K * K * 16);
+  static unsigned long long attr_done = 0;
+  ensure_dyn_smem(dw_bwd_fused_kernel<K>, smem, attr_done, "dw_bwd_fused_kernel");
+  DwBwdP p = {DY, ldd, Z, ldz, bn, act, sums, X, ldx, tf, W, DX, lddx, dW, dgamma, dbeta, psums, N, H, Wd, C,
+              1.0 / ((double)N * H * Wd)};
+  const int ngrp = (C + 15) / 16;
+  const int ntiles = N * ((H + 15) / 16) * ((Wd + 15) / 16);
+  static const int occ = resident_ctas(dw_bwd_fused_kernel<K>, 256, smem);
+  const int gx = std::min(ntiles, std::max(1, 148 * occ / ngrp));
+  dw_bwd_fused_kernel<K><<<dim3(gx, ngrp), 256, smem, s>>>(p);
+  return true;
+}
+
+// =====================================================================================================================
 // Per-channel reductions in double precision.  sums layout: [segment][2][C]; segment = image (SEG=1) or whole batch.
 //   MODE 0  BN statistics:    v1 = z            v2 = z*z
 //   MODE 1  BN backward:      v1 = dt           v2 = dt*zhat     dt = dy * act'(gamma*zhat+beta)
 //   MODE 2  column sums:      v1 = a                              (bias gradients, ECA average pool)
 //   MODE 3  products:         v1 = a*b                            (ECA backward: d gate)
 // =====================================================================================================================
-__device__ __forceinline__ float silu_grad(float t) {
-  const float sg = sigmoid_mufu(t);
-  return sg * (1.f + t * (1.f - sg));
-}
 
 template <int MODE>
 __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bv,

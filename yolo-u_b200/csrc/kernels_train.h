@@ -35,6 +35,11 @@ bool launch_dw_fwd_stats(const float* X, int ldx, const float* W, float* Y, int 
                          int C, int k, cudaStream_t s, InTf tf = InTf());
 void launch_dw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int N, int H, int Wd, int C, int k,
                      cudaStream_t s, InTf tf = InTf());
+// BatchNorm backward + depthwise input gradient + weight gradient (+ the producer's BN-backward sums into psums, optional) in
+// one pass; false when the shape is outside its envelope (k == 3, tiled maps) -- the caller then runs the unfused chain
+bool launch_dw_bwd_fused(const float* DY, int ldd, const float* Z, int ldz, const BnRef& bn, int act, const double* sums,
+                         const float* X, int ldx, InTf tf, const float* W, float* DX, int lddx, float* dW, float* dgamma,
+                         float* dbeta, double* psums, int N, int H, int Wd, int C, int k, cudaStream_t s);
 bool dw_tiled_shape(int H, int Wd, int k);   // true when the tiled depthwise family (the one that takes an InTf) handles it
 void launch_col_reduce(int mode, const float* A, int lda, const float* B, int ldb, const BnRef& bn, int act, double* sums,
                        int C, long long segs, long long rows_per_seg, cudaStream_t s);

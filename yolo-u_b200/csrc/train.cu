@@ -201,14 +201,27 @@ void convbn_fwd(Ctx& c, ConvBN& u, const float* x, int ldx, int N, int H, int W,
   }
 }
 
-// dy -> parameter gradients (+ input gradient into dx[:, :dx_ch], accumulated when beta)
+// dy -> parameter gradients (+ input gradient into dx[:, :dx_ch], accumulated when beta).
+// ready: this unit's BatchNorm-backward sums were already produced (by the fused backward of its consumer);
+// psums: where the fused depthwise backward leaves the sums of the unit that produced ITS input (u.src).
 void convbn_bwd(Ctx& c, ConvBN& u, const float* dy, int ldd, float* dx, int lddx, int beta, int dx_ch,
-                const Lin* rider = nullptr, const float* rider_dy = nullptr, int rider_ldd = 0) {
+                const Lin* rider = nullptr, const float* rider_dy = nullptr, int rider_ldd = 0, double* ready = nullptr,
+                double** psums = nullptr) {
   const long long M = (long long)u.N * u.H * u.W;
-  double* sums = c.sums(2 * (size_t)u.Cout);
+  double* sums = ready ? ready : c.sums(2 * (size_t)u.Cout);
+  double* ps = (psums && u.src) ? c.sums(2 * (size_t)u.src->Cout) : nullptr;
+  if (psums) *psums = nullptr;
   if (c.dry) return;
   BnRef bn = {c.P + u.g, c.P + u.b, u.mean, u.invstd};
-  launch_col_reduce(1, dy, ldd, u.z, u.Cout, bn, u.act, sums, u.Cout, 1, M, c.s);
+  if (!ready) { launch_col_reduce(1, dy, ldd, u.z, u.Cout, bn, u.act, sums, u.Cout, 1, M, c.s); c.launches += 1; c.acct((double)M * u.Cout * 2); }
+  if (u.dw && dx && !beta && dx_ch == u.Cout &&
+      launch_dw_bwd_fused(dy, ldd, u.z, u.Cout, bn, u.act, sums, u.x, u.ldx, tf_of(c, u.src), c.P + u.w, dx, lddx, c.G + u.w,
+                          c.G + u.g, c.G + u.b, ps, u.N, u.H, u.W, u.Cout, u.k, c.s)) {
+    if (psums) *psums = ps;
+    c.launches += 1;
+    c.acct((double)M * u.Cout * 4);          // dy, z, x in; dx out
+    return;
+  }
   launch_bn_bwd_apply(dy, ldd, u.z, u.Cout, bn, u.act, sums, c.dz, u.Cout, c.G + u.g, c.G + u.b, u.Cout, M, c.s);
   if (u.dw) {
     launch_dw_wgrad(c.dz, u.Cout, u.x, u.ldx, c.G + u.w, u.N, u.H, u.W, u.Cout, u.k, c.s, tf_of(c, u.src));
@@ -222,9 +235,9 @@ void convbn_bwd(Ctx& c, ConvBN& u, const float* dy, int ldd, float* dx, int lddx
       if (rider) c.acct((double)M * rider->Cout);
     }
   }
-  c.launches += dx ? 4 : 3;
-  // reduce (dy, z), apply (dy, z -> dz), wgrad (dz, x), dgrad (dz -> dx [+ dx])
-  c.acct((double)M * (u.Cout * 7 + (u.dw ? u.Cout : u.Cin) + (dx ? dx_ch * (1 + beta) : 0)));
+  c.launches += dx ? 3 : 2;
+  // apply (dy, z -> dz), wgrad (dz, x), dgrad (dz -> dx [+ dx])
+  c.acct((double)M * (u.Cout * 5 + (u.dw ? u.Cout : u.Cin) + (dx ? dx_ch * (1 + beta) : 0)));
 }
 
 // ---- C3Ghost + ECA -------------------------------------------------------------------------------------------------------
@@ -354,14 +367,17 @@ void dlc_bwd(Ctx& c, Dlc& d, const float* dout, int ldd, float* dxl, int lddx) {
   float* dpl = c.alloc((size_t)Ml * 2 * d.C);        // gradient of plow: [d conv1 | d residual_conv]
   double* bs = c.sums(2 * (size_t)d.C);
   double* ps = c.sums(2 * (size_t)d.C);
-  convbn_bwd(c, d.q2, dout, ldd, d1, d.C, 0, d.C);
-  convbn_bwd(c, d.p2, d1, d.C, d2, d.C, 0, d.C);
-  convbn_bwd(c, d.q, d2, d.C, d1, d.C, 0, d.C);
+  // the depthwise units run fused (dw_bwd_fused_kernel) and leave the BatchNorm-backward sums of their producers behind
+  double *s_p2 = nullptr, *s_p = nullptr;
+  convbn_bwd(c, d.q2, dout, ldd, d1, d.C, 0, d.C, nullptr, nullptr, 0, nullptr, &s_p2);
+  convbn_bwd(c, d.p2, d1, d.C, d2, d.C, 0, d.C, nullptr, nullptr, 0, s_p2);
+  convbn_bwd(c, d.q, d2, d.C, d1, d.C, 0, d.C, nullptr, nullptr, 0, nullptr, &s_p);
   if (c.dry) return;
   // conv.0.conv1: BatchNorm backward at full resolution, everything after it on the low-resolution rows
   ConvBN& u = d.p;
   BnRef bn = {c.P + u.g, c.P + u.b, u.mean, u.invstd}, none = {};
-  launch_col_reduce(1, d1, d.C, u.z, d.C, bn, 0, ps, d.C, 1, M, c.s);
+  if (s_p) ps = s_p;
+  else launch_col_reduce(1, d1, d.C, u.z, d.C, bn, 0, ps, d.C, 1, M, c.s);
   launch_bn_bwd_apply(d1, d.C, u.z, d.C, bn, 0, ps, c.dz, d.C, c.G + u.g, c.G + u.b, d.C, M, c.s);
   launch_up2_bwd(c.dz, d.C, dpl, 2 * d.C, N, h, w, d.C, c.s);
   launch_up2_bwd(dout, ldd, dpl + d.C, 2 * d.C, N, h, w, d.C, c.s);
