@@ -683,6 +683,8 @@ __global__ void __launch_bounds__(256, 2) dw_bwd_fused_kernel(const DwBwdP p) {
   float* sIn = sDz + IH * IW * PS;       // [IH*IW][PS]  x' with halo
   float* sW = sIn + IH * IW * PS;        // [KK][16] flipped taps
   float* sWa = sW + KK * 16;             // [16][KK] block accumulators of dW
+  float* sRd = sWa + 16 * KK;            // [IH*IW*4] x 16 B: raw dy of the NEXT tile (cp.async; item i of a thread = its own slot)
+  float* sRz = sRd + IH * IW * 16;       // raw z, same layout
   __shared__ double sRed[2][16];
   __shared__ __align__(16) float sBn[6][16];      // this unit: mean, invstd, gamma, beta, S1/M, S2/M
   __shared__ __align__(16) float sPr[4][16];      // producer: scale, shift (x' = z * sc + sh), mean, invstd
@@ -719,73 +721,82 @@ __global__ void __launch_bounds__(256, 2) dw_bwd_fused_kernel(const DwBwdP p) {
 #pragma unroll
   for (int tp = 0; tp < KK; ++tp) wacc[tp][0] = wacc[tp][1] = wacc[tp][2] = wacc[tp][3] = 0.f;
 
+  constexpr int TOT = IH * IW * 4, NL = (TOT + 255) / 256;       // every item of a thread has channel quad q (256 % 4 == 0)
+  // dy and z of a tile arrive by cp.async one tile ahead (zero-filled outside the image); a thread only ever touches its own
+  // 16-byte slots of the raw buffers, so the prefetch needs no barrier of its own
+  auto prefetch = [&](int tile) {
+    int t = tile;
+    const int tx0 = (t % tiles_x) * TX; t /= tiles_x;
+    const int ty0 = (t % tiles_y) * TY;
+    const int n = t / tiles_y;
+#pragma unroll
+    for (int u = 0; u < NL; ++u) {
+      const int i = tid + u * 256, pp = i >> 2;
+      if (i >= TOT) break;
+      const int iy = ty0 + pp / IW - PAD, ix = tx0 + pp % IW - PAD;
+      const bool in = q < nq && iy >= 0 && iy < H && ix >= 0 && ix < Wd;
+      const size_t pix = in ? (size_t)(n * H + iy) * Wd + ix : 0;
+      const uint32_t nb = in ? 16u : 0u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(sRd + i * 4)),
+                   "l"(p.DY + pix * p.ldd + cg + (in ? q * 4 : 0)), "r"(nb) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(sRz + i * 4)),
+                   "l"(p.Z + pix * p.ldz + cg + (in ? q * 4 : 0)), "r"(nb) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x);
+
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     int t = tile;
     const int tx0 = (t % tiles_x) * TX; t /= tiles_x;
     const int ty0 = (t % tiles_y) * TY;
     const int n = t / tiles_y;
     __syncthreads();
-    constexpr int TOT = IH * IW * 4, NL = (TOT + 255) / 256;     // every item of a thread has channel quad q (256 % 4 == 0)
+    // the x loads are in flight while dz is computed
+    float4 xv[NL];
+    bool xin[NL];
+#pragma unroll
+    for (int u = 0; u < NL; ++u) {
+      const int i = tid + u * 256, pp = i >> 2;
+      const int iy = ty0 + pp / IW - PAD, ix = tx0 + pp % IW - PAD;
+      xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      xin[u] = i < TOT && q < nq && iy >= 0 && iy < H && ix >= 0 && ix < Wd;
+      if (xin[u]) xv[u] = *reinterpret_cast<const float4*>(p.X + ((size_t)(n * H + iy) * Wd + ix) * p.ldx + cg + q * 4);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     {
-      // ---- dz tile: dy and z of HB items in flight before the arithmetic ----
-      constexpr int HB = (NL + 1) / 2;
+      // ---- dz tile from the raw buffers ----
       const float4 mu = *reinterpret_cast<const float4*>(&sBn[0][q * 4]), is = *reinterpret_cast<const float4*>(&sBn[1][q * 4]);
       const float4 ga = *reinterpret_cast<const float4*>(&sBn[2][q * 4]), be = *reinterpret_cast<const float4*>(&sBn[3][q * 4]);
       const float4 m1 = *reinterpret_cast<const float4*>(&sBn[4][q * 4]), m2 = *reinterpret_cast<const float4*>(&sBn[5][q * 4]);
 #pragma unroll
-      for (int u0 = 0; u0 < NL; u0 += HB) {
-        float4 dv[HB], zv[HB];
-        bool in[HB];
-#pragma unroll
-        for (int u = 0; u < HB; ++u) {
-          const int i = tid + (u0 + u) * 256, pp = i >> 2;
-          const int iy = ty0 + pp / IW - PAD, ix = tx0 + pp % IW - PAD;
-          dv[u] = make_float4(0.f, 0.f, 0.f, 0.f); zv[u] = dv[u];
-          in[u] = u0 + u < NL && i < TOT && q < nq && iy >= 0 && iy < H && ix >= 0 && ix < Wd;
-          if (in[u]) {
-            const size_t pix = (size_t)(n * H + iy) * Wd + ix;
-            dv[u] = *reinterpret_cast<const float4*>(p.DY + pix * p.ldd + cg + q * 4);
-            zv[u] = *reinterpret_cast<const float4*>(p.Z + pix * p.ldz + cg + q * 4);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < HB; ++u) {
-          const int i = tid + (u0 + u) * 256;
-          if (u0 + u >= NL || i >= TOT) break;
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (in[u]) {
+      for (int u = 0; u < NL; ++u) {
+        const int i = tid + u * 256;
+        if (i >= TOT) break;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xin[u]) {                       // same in-image predicate for all three tensors
+          const float4 dv = *reinterpret_cast<const float4*>(sRd + i * 4), zv = *reinterpret_cast<const float4*>(sRz + i * 4);
 #define YSP_DZ(f)                                                                                       \
   {                                                                                                     \
-    const float zh = (zv[u].f - mu.f) * is.f;                                                           \
-    const float dt = p.act ? dv[u].f * silu_grad(fmaf(ga.f, zh, be.f)) : dv[u].f;                       \
+    const float zh = (zv.f - mu.f) * is.f;                                                              \
+    const float dt = p.act ? dv.f * silu_grad(fmaf(ga.f, zh, be.f)) : dv.f;                             \
     o.f = ga.f * is.f * (dt - m1.f - zh * m2.f);                                                        \
   }
-            YSP_DZ(x) YSP_DZ(y) YSP_DZ(z) YSP_DZ(w)
+          YSP_DZ(x) YSP_DZ(y) YSP_DZ(z) YSP_DZ(w)
 #undef YSP_DZ
-          }
-          *reinterpret_cast<float4*>(sDz + (i >> 2) * PS + q * 4) = o;
         }
+        *reinterpret_cast<float4*>(sDz + (i >> 2) * PS + q * 4) = o;
       }
     }
     {
       // ---- x' tile ----
-      float4 xv[NL];
-      bool in[NL];
-#pragma unroll
-      for (int u = 0; u < NL; ++u) {
-        const int i = tid + u * 256, pp = i >> 2;
-        const int iy = ty0 + pp / IW - PAD, ix = tx0 + pp % IW - PAD;
-        xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        in[u] = i < TOT && q < nq && iy >= 0 && iy < H && ix >= 0 && ix < Wd;
-        if (in[u]) xv[u] = *reinterpret_cast<const float4*>(p.X + ((size_t)(n * H + iy) * Wd + ix) * p.ldx + cg + q * 4);
-      }
       const float4 sc = *reinterpret_cast<const float4*>(&sPr[0][q * 4]), sh = *reinterpret_cast<const float4*>(&sPr[1][q * 4]);
 #pragma unroll
       for (int u = 0; u < NL; ++u) {
         const int i = tid + u * 256;
         if (i >= TOT) break;
         float4 v = xv[u];
-        if (tfon && in[u]) {
+        if (tfon && xin[u]) {
           v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
           if (p.tf.act) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
         }
@@ -793,10 +804,19 @@ __global__ void __launch_bounds__(256, 2) dw_bwd_fused_kernel(const DwBwdP p) {
       }
     }
     __syncthreads();
+    if (tile + (int)gridDim.x < ntiles) prefetch(tile + gridDim.x);
     const int y = ty0 + ty;
     const bool rowok = y < H && q < nq;
     // ---- input gradient (flipped taps over the dz tile) ----
     {
+      // the producer's raw output at this thread's pixels (for its BN-backward sums): issued before the stencil
+      float4 zr[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int x = tx0 + txi * 4 + o;
+        zr[o] = (p.psums && rowok && x < Wd) ? *reinterpret_cast<const float4*>(p.X + ((size_t)(n * H + y) * Wd + x) * p.ldx + cg + q * 4)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       float4 acc[4];
 #pragma unroll
       for (int o = 0; o < 4; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -827,12 +847,11 @@ __global__ void __launch_bounds__(256, 2) dw_bwd_fused_kernel(const DwBwdP p) {
           const size_t pix = (size_t)(n * H + y) * Wd + x;
           const float4 a = acc[o];
           *reinterpret_cast<float4*>(p.DX + pix * p.lddx + cg + q * 4) = a;
-          if (p.psums) {       // the producer's BatchNorm-backward sums; its raw output at this pixel was just read (cache hit)
-            const float4 zr = *reinterpret_cast<const float4*>(p.X + pix * p.ldx + cg + q * 4);
+          if (p.psums) {       // the producer's BatchNorm-backward sums
 #define YSP_PS(f, j)                                                                                    \
   {                                                                                                     \
-    const float zh = (zr.f - pmu.f) * pis.f;                                                            \
-    const float dt = p.tf.act ? a.f * silu_grad(fmaf(zr.f, psc.f, psh.f)) : a.f;                        \
+    const float zh = (zr[o].f - pmu.f) * pis.f;                                                         \
+    const float dt = p.tf.act ? a.f * silu_grad(fmaf(zr[o].f, psc.f, psh.f)) : a.f;                     \
     s1[j] += dt; s2[j] = fmaf(dt, zh, s2[j]);                                                           \
   }
             YSP_PS(x, 0) YSP_PS(y, 1) YSP_PS(z, 2) YSP_PS(w, 3)
@@ -902,7 +921,7 @@ bool launch_dw_bwd_fused(const float* DY, int ldd, const float* Z, int ldz, cons
   static const bool off = getenv("YSP_TRAIN_NO_DWFUSE") != nullptr;
   if (off || k != 3 || !dw_tiled_shape(H, Wd, k) || (C & 3)) return false;
   constexpr int K = 3;
-  constexpr size_t smem = sizeof(float) * (2 * (16 + K - 1) * (16 + K - 1) * 20 + 2 * K * K * 16);
+  constexpr size_t smem = sizeof(float) * (2 * (16 + K - 1) * (16 + K - 1) * 20 + 2 * K * K * 16 + 2 * (16 + K - 1) * (16 + K - 1) * 16);
   static unsigned long long attr_done = 0;
   ensure_dyn_smem(dw_bwd_fused_kernel<K>, smem, attr_done, "dw_bwd_fused_kernel");
   DwBwdP p = {DY, ldd, Z, ldz, bn, act, sums, X, ldx, tf, W, DX, lddx, dW, dgamma, dbeta, psums, N, H, Wd, C,
