@@ -17,6 +17,7 @@
  *   evaluate_model.py:234-243 / YOLOSegPlusPlus.py:150 (state_dict tensors)      ysp_load_weight / ysp_finalize
  *   train.py:302-331  zero_grad / forward (train mode) / DiceLoss / backward      ysp_encoder_forward + ysp_train_step
  *   train.py:262,329  optim.AdamW(...).step()  (+ :328 clip_grad_norm_)           ysp_adamw
+ *   train.py:266,325-340  GradScaler: unscale_ / inf check of scaler.step          ysp_grad_sqnorm (+ grad_scale of ysp_train_step / ysp_adamw)
  *   train.py:346-366  validation loss                                             ysp_seg_loss (+ ysp_mask_dice)
  *   dataset.py:59-70  cv2.resize (INTER_LINEAR / INTER_NEAREST) + ToTensor         ysp_resize_u8
  *   dataset.py:86-97  objectmap z-score + sigmoid                                  ysp_objectmap_transform
@@ -199,6 +200,9 @@ int ysp_seg_loss(const float* d_logits, const float* d_target, int64_t n, int lo
  * exhausted; so callers pass 0).  d_ws8 = 8 bytes of device scratch (only read when clipping). */
 int ysp_adamw(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n, float lr, float beta1, float beta2,
               float eps, float weight_decay, int step, float grad_scale, float max_norm, void* d_ws8, void* stream);
+/* Sum of squares (double) of a flat gradient buffer -> d_out8[0].  The mixed-precision branch (train.py:325-340) needs it
+ * for GradScaler's inf/NaN check before scaler.step(): a non-finite entry makes the sum non-finite. */
+int ysp_grad_sqnorm(const float* d_grads, int64_t n, void* d_out8, void* stream);
 
 /* -- introspection (tests / profiling) ---------------------------------------------------------------------------- */
 /* keep every intermediate alive (no workspace reuse) so ysp_debug_tensor can read them; affects plans built later */

@@ -187,3 +187,44 @@ def test_validate_batch_matches_eval_mode_oracle():
     assert (pred.cpu() - ref).abs().max().item() <= 1e-3
     assert abs(loss3[0].item() - want) <= 1e-5
     assert torch.equal(counts.cpu().long(), mask_counts(pred.cpu(), tg))
+
+
+def test_mixed_precision_branch_grad_scaler():
+    """train.py:302-341 (the branch the reference runs by default): scaler.scale(loss).backward(), unscale_, scaler.step that
+    SKIPS the optimiser when a gradient is inf/NaN, scaler.update (backoff 0.5 after a skip, x2 after growth_interval clean
+    steps).  Tensors stay fp32 here, so a clean scaled step must equal the plain step up to the summation order of the
+    gradient atomics (power-of-two scaling is exact)."""
+    from yolo_u_b200.trainer import SegHeadTrainer
+    B, S = 2, 64
+    seg, plain, x, lg, tg = _setup(B, S)
+    amp = SegHeadTrainer(seg.state_dict(), batch_size=B, image_size=S, lr=1e-3, epochs=10, device="cuda:0",
+                         mixed_precision=True, growth_interval=2)
+    assert amp.scale == 2.0 ** 16 and plain.scale == 1.0
+    xc, lgc, tgc = x.cuda(), lg.cuda(), tg.cuda()
+    # scaled backward: gradients are 2**16 x the plain ones, the loss value is not scaled
+    l_amp, _ = amp.forward_backward(xc, tgc, lgc, grad_scale=amp.scale)
+    l_plain, _ = plain.forward_backward(xc, tgc, lgc)
+    assert abs(l_amp[0].item() - l_plain[0].item()) <= 1e-6
+    g_amp, g_plain = amp.grads / amp.scale, plain.grads
+    assert (g_amp - g_plain).abs().max().item() <= 2e-4 * g_plain.abs().max().item()
+    # clean steps: same trajectory as the plain trainer; the scale doubles after growth_interval = 2 of them
+    assert amp.optimizer_step() is True and plain.optimizer_step() is True
+    amp.step(xc, tgc, lgc)
+    plain.step(xc, tgc, lgc)
+    assert amp.scale == 2.0 ** 17 and amp.step_count == 2 and amp.skipped_steps == 0
+    start = SegHeadTrainer(seg.state_dict(), batch_size=B, image_size=S, device="cuda:0").params
+    rel = ((amp.params - plain.params).norm() / (plain.params - start).norm()).item()
+    assert rel <= 2e-2, rel            # Adam turns rounding-level gradient differences into +-lr moves (see above)
+    # an overflowing gradient: the step is skipped (parameters, moments and step count untouched), the scale backs off
+    before, m_before = amp.params.clone(), amp.adam_m.clone()
+    amp.forward_backward(xc, tgc, lgc, grad_scale=amp.scale)
+    amp.grads[7] = float("inf")
+    assert amp.optimizer_step() is False
+    assert torch.equal(amp.params, before) and torch.equal(amp.adam_m, m_before)
+    assert amp.scale == 2.0 ** 16 and amp.step_count == 2 and amp.skipped_steps == 1
+    amp.forward_backward(xc, tgc, lgc, grad_scale=amp.scale)
+    amp.grads[3] = float("nan")
+    assert amp.optimizer_step() is False and amp.scale == 2.0 ** 15
+    # and training goes on
+    l3, _ = amp.step(xc, tgc, lgc)
+    assert amp.step_count == 3 and torch.isfinite(l3).all()

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "ysp_encoder_forward": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]),
     "ysp_train_step": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, f32, i32, f32, vp, vp, vp, sz, vp]),
     "ysp_seg_loss": (i32, [vp, vp, i64, i32, vp, vp, vp]),
+    "ysp_grad_sqnorm": (i32, [vp, i64, vp, vp]),
     "ysp_adamw": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, f32, f32, vp, vp]),
     "ysp_last_launch_count": (i32, [vp]),
     "ysp_set_keep_intermediates": (i32, [vp, i32]),

@@ -1409,6 +1409,11 @@ void launch_adamw(float* p, const float* g, float* m, float* v, long long n, flo
                                     sqn_ws);
 }
 
+void launch_sqnorm(const float* g, long long n, double* out, cudaStream_t s) {
+  cudaMemsetAsync(out, 0, sizeof(double), s);
+  sqnorm_kernel<<<(int)std::min<long long>(cdivl(n, 256), 148 * 4), 256, 0, s>>>(g, n, out);
+}
+
 // NHWC activation view (fp32 or bf16) -> dense fp32 [M][C]  (hands the frozen encoder's skips to the trainer)
 template <typename T>
 __global__ void __launch_bounds__(256) export_view_kernel(const T* __restrict__ in, int in_cs, float* out, int C, long long M) {

@@ -63,6 +63,7 @@ void launch_loss(const float* X, const float* T, long long n, double* acc, int k
 void launch_loss_value(const float* X, const float* T, long long n, double* acc, int kind, float* loss_out, cudaStream_t s);
 void launch_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                   float wd, int step, float gscale, float max_norm, double* sqn_ws, cudaStream_t s);
+void launch_sqnorm(const float* g, long long n, double* out, cudaStream_t s);
 void launch_export_view(const void* in, int in_cs, int dt, float* out, int C, long long M, cudaStream_t s);
 
 }  // namespace ysp

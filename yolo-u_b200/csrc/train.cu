@@ -544,6 +544,14 @@ int ysp_seg_loss(const float* d_logits, const float* d_target, int64_t n, int lo
   return 0;
 }
 
+int ysp_grad_sqnorm(const float* d_grads, int64_t n, void* d_out8, void* stream) {
+  if (!d_grads || !d_out8 || n <= 0) return tfail(YSP_EINVAL, "ysp_grad_sqnorm: bad arguments");
+  launch_sqnorm(d_grads, (long long)n, (double*)d_out8, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return tfail(YSP_ECUDA, "ysp_grad_sqnorm: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int ysp_adamw(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n, float lr, float beta1, float beta2,
               float eps, float weight_decay, int step, float grad_scale, float max_norm, void* d_ws8, void* stream) {
   if (!d_params || !d_grads || !d_m || !d_v || n < 0 || step < 1) return tfail(YSP_EINVAL, "ysp_adamw: bad arguments");

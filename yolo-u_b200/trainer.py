@@ -1,5 +1,5 @@
 """Seg-head training step (BASELINE cfg 4) -- host side of the reference's `Trainer.train`
-loop body (/root/reference/train.py:302-331, the non-AMP branch) over libysp's `ysp_train_*` entries.
+loop body (/root/reference/train.py:302-360, both branches) over libysp's `ysp_train_*` entries.
 
 What the reference does per batch                       what happens here
   img/mask/heatmaps .float().to(device)   :317-319      tensors arrive on the device (fp32)
@@ -15,6 +15,16 @@ What the reference does per batch                       what happens here
                                                          into the optimiser's gradient scale; BN statistics stay local
   scheduler = CosineAnnealingLR(T_max=epochs), stepped per epoch :264, :398      `scheduler_step()`
   torch.save(model.state_dict(), best.pth) :428          `state_dict()` returns the reference's keys and layouts
+
+`mixed_precision=True` follows the branch the reference runs by default (train.py:302-341): the loss gradient is multiplied
+by the GradScaler's scale (`scaler.scale(loss).backward()` :325), the flat gradient buffer is checked for inf/NaN and
+unscaled inside the optimiser (`scaler.unscale_` / `scaler.step` :328-336: a non-finite gradient SKIPS the step), and
+`scaler.update()` (:339) halves the scale after a skipped step and doubles it after `growth_interval` clean ones
+(torch.amp.GradScaler defaults: 2**16, x2, x0.5, 2000).  What autocast changes in the reference is the arithmetic (fp16
+convs); here the 1x1 convs run on tcgen05 with split fp16 / bf16 operands and fp32 accumulation and every tensor is
+stored in fp32, i.e. at or above the reference's precision, so the scaler's job reduces to its control flow -- power-of-two
+scaling is exact in fp32, and a clean mixed-precision step equals the plain step up to the summation order of the
+gradient atomics (tested).
 
 There is no autograd and no PyTorch fallback: parameters, gradients, Adam moments and BN running statistics are flat
 fp32 device buffers whose sub-tensors are views named by the reference's state_dict keys."""
@@ -36,7 +46,8 @@ class SegHeadTrainer:
     def __init__(self, seg_state_dict: Mapping[str, torch.Tensor], batch_size: int, image_size=240, lr: float = 1e-4,
                  epochs: int = 100, loss: str = "dice", device="cuda:0", encoder_mode="fp32", betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 1e-2, max_norm: float = 0.0, bn_momentum: float = 0.1,
-                 process_group=None):
+                 process_group=None, mixed_precision: bool = False, init_scale: float = 2.0 ** 16, growth_factor: float = 2.0,
+                 backoff_factor: float = 0.5, growth_interval: int = 2000):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             from ._lib import YspError
@@ -53,6 +64,11 @@ class SegHeadTrainer:
         self.betas, self.eps, self.weight_decay, self.max_norm = betas, eps, weight_decay, max_norm
         self.bn_momentum = bn_momentum
         self.pg = process_group
+        # torch.amp.GradScaler state (train.py:266); inert unless mixed_precision
+        self.mixed_precision = bool(mixed_precision)
+        self.scale = float(init_scale) if self.mixed_precision else 1.0
+        self.growth_factor, self.backoff_factor, self.growth_interval = float(growth_factor), float(backoff_factor), int(growth_interval)
+        self._growth_tracker, self.skipped_steps = 0, 0
         # frozen encoder through the inference engine (its decoder weights are only needed to finalise the handle)
         self._frozen = {k: v.detach().clone() for k, v in seg_state_dict.items() if k.startswith("encoder.") or k == "param"}
         self.engine = Engine(self.device, encoder_mode)
@@ -162,24 +178,41 @@ class SegHeadTrainer:
             self._nbt[k] += 1
         return self._loss, pred
 
-    def optimizer_step(self):
-        """All-reduce (if a process group is up) + AdamW on the flat buffers."""
+    def optimizer_step(self) -> bool:
+        """All-reduce (if a process group is up) + AdamW on the flat buffers.  With mixed_precision this is
+        scaler.unscale_ + scaler.step + scaler.update (train.py:328-339): returns False when the step was skipped because a
+        gradient was inf/NaN (one 8-byte D2H per step, the same host sync torch's scaler.step makes)."""
         import torch.distributed as dist
         world = 1
         if dist.is_available() and dist.is_initialized():
             world = dist.get_world_size(self.pg)
             if world > 1:
                 dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.pg)
+        if self.mixed_precision:
+            with torch.cuda.device(self.device):
+                check(lib().ysp_grad_sqnorm(self.grads.data_ptr(), self.grads.numel(), self._scratch.data_ptr(),
+                                            _stream_ptr(self.device)))
+            if not math.isfinite(float(self._scratch.item())):       # every rank sees the same all-reduced buffer
+                self.scale *= self.backoff_factor
+                self._growth_tracker = 0
+                self.skipped_steps += 1
+                return False
         self.step_count += 1
         with torch.cuda.device(self.device):
             check(lib().ysp_adamw(self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr(),
                                   self.params.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                  self.step_count, 1.0 / world, self.max_norm, self._scratch.data_ptr(),
+                                  self.step_count, 1.0 / (world * self.scale), self.max_norm, self._scratch.data_ptr(),
                                   _stream_ptr(self.device)))
+        if self.mixed_precision:
+            self._growth_tracker += 1
+            if self._growth_tracker == self.growth_interval:
+                self.scale *= self.growth_factor
+                self._growth_tracker = 0
+        return True
 
     def step(self, img, mask, heatmaps, want_pred: bool = False):
         """One iteration of train.py:317-329.  Returns the device loss tensor {total, dice, bce} (no sync) and pred."""
-        loss, pred = self.forward_backward(img, mask, heatmaps, want_pred=want_pred)
+        loss, pred = self.forward_backward(img, mask, heatmaps, grad_scale=self.scale, want_pred=want_pred)
         self.optimizer_step()
         return loss, pred
 
