@@ -53,6 +53,8 @@ void launch_add_sums(const double* sums, float* g, int n, int fold, cudaStream_t
 void launch_add_copy(const float* A, int lda, const float* B, int ldb, float* O, int ldo, int C, long long M, cudaStream_t s);
 void launch_up2(const float* X, int ldx, float* Y, int ldy, int N, int h, int w, int C, cudaStream_t s);
 void launch_up2_bwd(const float* DY, int ldd, float* DX, int ldx, int N, int h, int w, int C, cudaStream_t s);
+void launch_up2_split(const float* X, int ldx, float* Y0, int ldy0, int C0, float* Y1, int ldy1, int C1, int N, int h, int w,
+                      double* sums, cudaStream_t s);
 void launch_eca_gate(const double* pool, const float* w3, float* mean, float* gate, int N, int C, long long HW, cudaStream_t s);
 void launch_eca_gate_bwd(const double* dsum, const float* w3, const float* mean, const float* gate, float* dmean, float* dw3,
                          int N, int C, long long HW, cudaStream_t s);
