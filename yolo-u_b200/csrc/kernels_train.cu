@@ -1272,6 +1272,97 @@ void launch_up2_split(const float* X, int ldx, float* Y0, int ldy0, int C0, floa
       X, ldx, Y0, ldy0, C0, Y1, ldy1, N, h, w, C, sums);
 }
 
+// up2^T for the DoubleLightConv backward, tiled: DX [N,h,w][C0 + C1] = up2^T of [ BatchNorm-backward(DY0, Z0) | DY1 ].
+// The gather form above reads every full-resolution element four times (once per low-res pixel that uses it); here a CTA
+// stages the 18x18 full-resolution patch of an 8x8 low-res tile ONCE in shared memory (border slots hold the clamped pixel, which
+// is exactly the adjoint's clamped OUTPUT index), and for the first C0 channels forms dz = gamma*invstd*(dy - S1/M - zhat*S2/M) of
+// conv.0.conv1 (no activation) while staging, so neither dz nor a second pass over dy / z exists.  CTA = 16-channel group x
+// tile; thread = one low-res pixel x channel quad; pixel pitch 24 floats (stride-2 pixel reads of a quarter-warp hit distinct banks).
+struct Up2BwdP {
+  const float* DY0; int ldd0; const float* Z0; int ldz0; BnRef bn; const double* sums; double invM; float* dgamma; float* dbeta;
+  int C0; const float* DY1; int ldd1; float* DX; int ldx; int N, h, w, tiles_x, tiles_y;
+};
+__global__ void __launch_bounds__(256) up2_bwd_tiled_kernel(const Up2BwdP p) {
+  constexpr int TL = 8, TH = 2 * TL + 2, PS = 24;
+  __shared__ __align__(16) float sT[TH * TH * PS];
+  const int tid = threadIdx.x, q = tid & 3;
+  const int H = 2 * p.h, Wd = 2 * p.w;
+  int t = blockIdx.x;
+  const int lx0 = (t % p.tiles_x) * TL; t /= p.tiles_x;
+  const int ly0 = (t % p.tiles_y) * TL;
+  const int n = t / p.tiles_y;
+  const int cg = blockIdx.y * 16;                      // channel group inside [C0 + C1]
+  const bool first = cg < p.C0;
+  float k1[4] = {1.f, 1.f, 1.f, 1.f}, k0[4] = {0.f, 0.f, 0.f, 0.f}, kz[4] = {0.f, 0.f, 0.f, 0.f}, mus[4] = {0.f, 0.f, 0.f, 0.f};
+  if (first) {                                         // dz = k1 * dy + kz * (z - mean) + k0
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = cg + q * 4 + j;
+      const float mu = p.bn.mean[c], is = p.bn.invstd[c], ga = p.bn.gamma[c];
+      const float m1 = (float)(p.sums[c] * p.invM), m2 = (float)(p.sums[p.C0 + c] * p.invM);
+      k1[j] = ga * is; kz[j] = -ga * is * is * m2; k0[j] = -ga * is * m1; mus[j] = mu;
+      if (blockIdx.x == 0 && tid < 4) { p.dbeta[c] += (float)p.sums[c]; p.dgamma[c] += (float)p.sums[p.C0 + c]; }
+    }
+  }
+  const float* D = first ? p.DY0 + cg + q * 4 : p.DY1 + (cg - p.C0) + q * 4;
+  const int ld = first ? p.ldd0 : p.ldd1;
+  const size_t nb = (size_t)n * H * Wd;
+  constexpr int TOT = TH * TH * 4, NL = (TOT + 255) / 256;
+  float4 dv[NL], zv[NL];
+  int pr = (tid >> 2) / TH, pc = (tid >> 2) % TH;      // patch row / column of item u: 64 pixels further each time, no division
+#pragma unroll
+  for (int u = 0; u < NL; ++u) {
+    const int i = tid + u * 256;
+    dv[u] = make_float4(0.f, 0.f, 0.f, 0.f); zv[u] = dv[u];
+    if (i < TOT) {
+      const int oy = min(max(2 * ly0 - 1 + pr, 0), H - 1), ox = min(max(2 * lx0 - 1 + pc, 0), Wd - 1);
+      pr += 64 / TH; pc += 64 % TH;
+      if (pc >= TH) { pc -= TH; ++pr; }
+      const size_t pix = nb + (size_t)oy * Wd + ox;
+      dv[u] = *reinterpret_cast<const float4*>(D + pix * ld);
+      if (first) zv[u] = *reinterpret_cast<const float4*>(p.Z0 + pix * p.ldz0 + cg + q * 4);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < NL; ++u) {
+    const int i = tid + u * 256;
+    if (i >= TOT) break;
+    float4 o = dv[u];
+    if (first) {
+      o.x = fmaf(k1[0], o.x, fmaf(kz[0], zv[u].x - mus[0], k0[0])); o.y = fmaf(k1[1], o.y, fmaf(kz[1], zv[u].y - mus[1], k0[1]));
+      o.z = fmaf(k1[2], o.z, fmaf(kz[2], zv[u].z - mus[2], k0[2])); o.w = fmaf(k1[3], o.w, fmaf(kz[3], zv[u].w - mus[3], k0[3]));
+    }
+    *reinterpret_cast<float4*>(sT + (i >> 2) * PS + q * 4) = o;
+  }
+  __syncthreads();
+  const int lx = (tid >> 2) & 7, ly = tid >> 5;
+  const int jx = lx0 + lx, jy = ly0 + ly;
+  if (jx >= p.w || jy >= p.h) return;
+  const float wt[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(sT + ((2 * ly + a) * TH + 2 * lx + c) * PS + q * 4);
+      row.x = fmaf(wt[c], v.x, row.x); row.y = fmaf(wt[c], v.y, row.y); row.z = fmaf(wt[c], v.z, row.z); row.w = fmaf(wt[c], v.w, row.w);
+    }
+    acc.x = fmaf(wt[a], row.x, acc.x); acc.y = fmaf(wt[a], row.y, acc.y); acc.z = fmaf(wt[a], row.z, acc.z); acc.w = fmaf(wt[a], row.w, acc.w);
+  }
+  *reinterpret_cast<float4*>(p.DX + ((size_t)(n * p.h + jy) * p.w + jx) * p.ldx + cg + q * 4) = acc;
+}
+// false when the channel counts are not multiples of 16 (the caller runs bn_bwd_apply + up2_bwd)
+bool launch_up2_bwd_tiled(const float* DY0, int ldd0, const float* Z0, int ldz0, const BnRef& bn, const double* sums, long long M,
+                          float* dgamma, float* dbeta, int C0, const float* DY1, int ldd1, int C1, float* DX, int ldx, int N,
+                          int h, int w, cudaStream_t s) {
+  static const bool off = getenv("YSP_TRAIN_NO_UP2T") != nullptr;
+  if (off || (C0 & 15) || (C1 & 15) || ((ldd0 | ldz0 | ldd1 | ldx) & 3)) return false;
+  Up2BwdP p = {DY0, ldd0, Z0, ldz0, bn, sums, 1.0 / (double)M, dgamma, dbeta, C0, DY1, ldd1, DX, ldx, N, h, w, (w + 7) / 8, (h + 7) / 8};
+  up2_bwd_tiled_kernel<<<dim3((unsigned)(N * p.tiles_x * p.tiles_y), (unsigned)((C0 + C1) / 16)), 256, 0, s>>>(p);
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // ECA (YOLOSegPlusPlus.py:60-88): gate[n][c] = sigmoid(sum_j w3[j] * mean[n][c+j-1]);  y = x * gate.
 // eca_gate: pooled sums (double, [n][2][C], slot 0) -> mean, gate.  eca_gate_bwd: dgate sums (slot 0 of dsum) ->

@@ -55,6 +55,9 @@ void launch_up2(const float* X, int ldx, float* Y, int ldy, int N, int h, int w,
 void launch_up2_bwd(const float* DY, int ldd, float* DX, int ldx, int N, int h, int w, int C, cudaStream_t s);
 void launch_up2_split(const float* X, int ldx, float* Y0, int ldy0, int C0, float* Y1, int ldy1, int C1, int N, int h, int w,
                       double* sums, cudaStream_t s);
+bool launch_up2_bwd_tiled(const float* DY0, int ldd0, const float* Z0, int ldz0, const BnRef& bn, const double* sums, long long M,
+                          float* dgamma, float* dbeta, int C0, const float* DY1, int ldd1, int C1, float* DX, int ldx, int N,
+                          int h, int w, cudaStream_t s);
 void launch_eca_gate(const double* pool, const float* w3, float* mean, float* gate, int N, int C, long long HW, cudaStream_t s);
 void launch_eca_gate_bwd(const double* dsum, const float* w3, const float* mean, const float* gate, float* dmean, float* dw3,
                          int N, int C, long long HW, cudaStream_t s);

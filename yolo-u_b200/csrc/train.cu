@@ -376,11 +376,16 @@ void dlc_bwd(Ctx& c, Dlc& d, const float* dout, int ldd, float* dxl, int lddx) {
   BnRef bn = {c.P + u.g, c.P + u.b, u.mean, u.invstd}, none = {};
   if (s_p) ps = s_p;
   else launch_col_reduce(1, d1, d.C, u.z, d.C, bn, 0, ps, d.C, 1, M, c.s);
-  // (forming dz inside up2^T -- BN backward applied as the gradient is loaded -- measured 0.8 ms SLOWER per step: the gather
-  // reads every full-resolution element four times, and doing that on two tensors instead of one costs more than the pass saved)
-  launch_bn_bwd_apply(d1, d.C, u.z, d.C, bn, 0, ps, c.dz, d.C, c.G + u.g, c.G + u.b, d.C, M, c.s);
-  launch_up2_bwd(c.dz, d.C, dpl, 2 * d.C, N, h, w, d.C, c.s);
-  launch_up2_bwd(dout, ldd, dpl + d.C, 2 * d.C, N, h, w, d.C, c.s);
+  // up2^T of [BN-backward(d1, z_p) | dout] from shared-memory tiles: dz of conv.0.conv1 is formed as it is staged, never written.
+  // (The same fusion inside the GATHER form of up2^T measured 0.8 ms slower per step: it reads every full-resolution element
+  // four times, on two tensors instead of one.)
+  if (!launch_up2_bwd_tiled(d1, d.C, u.z, d.C, bn, ps, M, c.G + u.g, c.G + u.b, d.C, dout, ldd, d.C, dpl, 2 * d.C, N, h, w, c.s)) {
+    launch_bn_bwd_apply(d1, d.C, u.z, d.C, bn, 0, ps, c.dz, d.C, c.G + u.g, c.G + u.b, d.C, M, c.s);
+    launch_up2_bwd(c.dz, d.C, dpl, 2 * d.C, N, h, w, d.C, c.s);
+    launch_up2_bwd(dout, ldd, dpl + d.C, 2 * d.C, N, h, w, d.C, c.s);
+    c.launches += 2;
+    c.acct((double)M * d.C * 2);
+  }
   launch_col_reduce(2, dpl + d.C, 2 * d.C, nullptr, 0, none, 0, bs, d.C, 1, Ml, c.s);     // d bias: up2^T preserves column sums
   launch_add_sums(bs, c.G + d.r.b, d.C, 1, c.s);
   launch_pw_wgrad(dpl, 2 * d.C, d.xl, d.ldxl, c.G + u.w, d.Cin, Ml, d.Cin, d.C, c.s);
@@ -389,8 +394,8 @@ void dlc_bwd(Ctx& c, Dlc& d, const float* dout, int ldd, float* dxl, int lddx) {
   PwDual du;
   du.A2 = dpl + d.C; du.lda2 = 2 * d.C; du.W2 = c.P + d.r.w; du.ldw2 = d.Cin; du.I2 = d.C;
   launch_pw_gemm(dpl, 2 * d.C, c.P + u.w, d.Cin, 1, nullptr, dxl, lddx, Ml, d.C, d.Cin, 0, c.s, nullptr, InTf(), du);
-  c.launches += 8 + (s_p ? 0 : 1);
-  c.acct((double)M * d.C * ((s_p ? 0 : 2) + 3 + 1 + 1) + (double)Ml * (2 * d.C + d.C + 2 * (d.C + d.Cin) + 2 * d.C + d.Cin));
+  c.launches += 6 + (s_p ? 0 : 1);
+  c.acct((double)M * d.C * ((s_p ? 0 : 2) + 3) + (double)Ml * (2 * d.C + d.C + 2 * (d.C + d.Cin) + 2 * d.C + d.Cin));
 }
 
 // ---- whole step -----------------------------------------------------------------------------------------------------------
