@@ -356,32 +356,40 @@ def main_ours(args):
                 "tolerance": {"logits_max_abs": 1e-3, "dice_max_abs": 1e-4, "nms_keep": "bit-exact"}}
 
     def measure(mode, profile):
-        P = ysp.Predictor(det_sd, seg_sd, device=dev, mode=mode)
+        # `engines` handles over the same weights take alternate batches on their own streams (Predictor(replicas=...)): every
+        # step is still one full pass of the path over one B-slice batch, the tail of step i runs under the kernels of step i+1
+        P = ysp.Predictor(det_sd, seg_sd, device=dev, mode=mode, replicas=args.engines)
         eng = P.engine
         rec = {"mode": mode, "dtype": DTYPE_OF[mode]}
         # ---- device-resident throughput (`value`) ------------------------------------------------------------------
-        for i in range(Wm):
-            P.predict_raw(xs[i % nbuf], tg)
+        for i in range(max(Wm, 2 * args.engines)):
+            P.submit_raw(xs[i % nbuf], tg)
+        P.join()
         barrier()
-        l0 = eng.launches_total
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        l0 = P.launches_total
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        done = []
         tw0 = time.time()
         ev[0].record()
         for i in range(K):
-            P.predict_raw(xs[i % nbuf], tg)
-            ev[i + 1].record()
+            o_last, e_done = P.submit_raw(xs[i % nbuf], tg)
+            done.append(e_done)
+        P.join()
+        ev[1].record()
         torch.cuda.synchronize()
         tw1 = time.time()
-        ms = ev[0].elapsed_time(ev[K])
-        per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(K))
+        ms = ev[0].elapsed_time(ev[1])
+        marks = [ev[0]] + done
+        E = max(args.engines, 1)        # steps complete in groups of E (one per handle): time per step over sliding groups of E completions
+        per = sorted(marks[i].elapsed_time(marks[i + E]) / E for i in range(0, K - E + 1))
         barrier()
         rec["clocks"] = sampler.window(tw0, tw1) if rank == 0 else None
-        rec["gpu_launches"] = eng.launches_total - l0
+        rec["gpu_launches"] = P.launches_total - l0
         ms = max_over_ranks(ms)
         rec["ms_per_step"] = ms / K
         rec["value"] = world * B * K / (ms / 1e3)
         rec["step_ms"] = {"min": per[0], "median": per[len(per) // 2], "max": per[-1]}
-        counts = P._out["counts"].clone()
+        counts = o_last["counts"].clone()
         # ---- metric all-reduce (the only collective of the path), outside the step loop like evaluate_model.py:177-187 --
         met = ysp.SegMetrics()
         met.update(counts)
@@ -396,14 +404,14 @@ def main_ours(args):
             barrier()
             t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             cur = torch.cuda.current_stream(dev)
-            for st in (hp.s_in, hp.s_run, hp.s_out):
+            for st in hp.streams():
                 st.wait_stream(cur)
             t_e0.record(cur)
-            for st in (hp.s_in, hp.s_run, hp.s_out):
+            for st in hp.streams():
                 st.wait_stream(cur)                      # every pipeline stream starts after the start event
             for i in range(K):
                 slot = hp.submit(hx[i % 2], htg)
-            for st in (hp.s_in, hp.s_run, hp.s_out):
+            for st in hp.streams():
                 cur.wait_stream(st)                      # the end event waits for the last D2H
             t_e1.record(cur)
             torch.cuda.synchronize()
@@ -418,7 +426,7 @@ def main_ours(args):
                 rec["e2e_with_mask"] = e
             else:
                 e["note"] = ("HostPipeline.submit: pinned u8 HWC host batch + u8 target masks -> H2D -> ysp_pipeline -> D2H of padded "
-                             "detections + Dice counters, every step, double-buffered over 3 streams")
+                             "detections + Dice counters, every step, double-buffered: upload / download streams + one compute stream per engine handle")
                 rec["e2e"] = e
             del hp
         # ---- in-run parity of THIS mode at THIS batch size ---------------------------------------------------------------
@@ -494,6 +502,7 @@ def main_ours(args):
                 "dtype": head["dtype"], "data": "synthetic",
                 "config": {"workload": WORKLOAD, "mode": head["mode"],
                            "batch_per_gpu": B, "global_batch": B * world, "H": H, "W": W, "parallelism": f"shard{world}",
+                           "engines": f"{args.engines} engine handle(s) per GPU over the same weights take alternate {B}-slice batches on their own streams",
                            "l2": f"inputs larger than L2: {nbuf} rotating fp32 input buffers of {B * 4 * H * W * 4 / 1e6:.0f} MB",
                            "weights": "random-init synthetic checkpoint (yolo_u_b200.synth, seed 0, calibrated heads)",
                            "env": {k: v for k, v in os.environ.items() if k.startswith("YSP_")}},
@@ -542,7 +551,7 @@ def main_eval(args):
     B, K, Wm = args.batch, args.steps, args.warmup
     sampler = ClockSampler(local).start() if rank == 0 else None
     det_sd, seg_sd = calibrate(*synth_state_dicts(0), device=dev)
-    P = ysp.Predictor(det_sd, seg_sd, device=dev, mode=args.mode)
+    P = ysp.Predictor(det_sd, seg_sd, device=dev, mode=args.mode, replicas=args.engines)
     lo, hi = ysp.shard_slices(NV, NS, world, rank)
     n_local = hi - lo
     # this rank's shard: decoded PNG bytes (u8 HWC4 slices + u8 masks), generated per VOLUME from the volume index so the
@@ -566,9 +575,9 @@ def main_eval(args):
         torch.cuda.synchronize()
 
     def evaluate_device():
-        for a, b in bl:
-            o = P.engine.pipeline(d_img[a:b], d_tgt[a:b], out=outs.setdefault(b - a, {}))
-            all_counts[a:b].copy_(o["counts"], non_blocking=True)
+        for a, b in bl:                                    # alternate engine handles; the counters are copied on the handle's stream
+            P.submit_raw(d_img[a:b], d_tgt[a:b], after=lambda o, a=a, b=b: all_counts[a:b].copy_(o["counts"], non_blocking=True))
+        P.join()
         met = ysp.SegMetrics()
         if n_local:
             met.update(all_counts[:n_local])              # ONE D2H of the integer counters per evaluation
@@ -608,10 +617,10 @@ def main_eval(args):
             ms, wall = (float(v) for v in t.tolist())
         return res, ms, wall
 
-    l0 = P.engine.launches_total
+    l0 = P.launches_total
     tw0 = time.time()
     res, ms, wall = timed(evaluate_device)
-    launches = (P.engine.launches_total - l0) * K // (K + Wm)
+    launches = (P.launches_total - l0) * K // (K + Wm)
     clocks = sampler.stop(tw0, time.time()) if rank == 0 else None
     res_h, ms_h, wall_h = timed(evaluate_host)
     total = NV * NS
@@ -622,7 +631,7 @@ def main_eval(args):
                 "wall_ms_per_step": wall / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": DTYPE_OF[args.mode], "data": "synthetic",
                 "config": {"workload": f"evaluate_model.py:134-187 over {NV} volumes x {NS} slices = {total} 4x{H}x{W} slices; u8 slices + u8 masks",
-                           "mode": args.mode, "batch": B, "batches_per_rank": [b - a for a, b in bl], "parallelism": f"shard{world} (contiguous by volume)",
+                           "mode": args.mode, "batch": B, "engines": args.engines, "batches_per_rank": [b - a for a, b in bl], "parallelism": f"shard{world} (contiguous by volume)",
                            "collective": "one all-reduce(SUM) of [sum Dice, n, TP, FP, FN] per evaluation (NCCL), inside the timed region",
                            "l2": f"inputs larger than L2: {n_local * H * W * 5 / 1e6:.0f} MB of device-resident slices + masks per rank"},
                 "e2e": {"value": total * K / (ms_h / 1e3), "unit": UNIT, "ms_per_step": ms_h / K, "wall_ms_per_step": wall_h / K,
@@ -845,6 +854,8 @@ def main():
                     help="headline mode: tc32 = the tensor-core mode that meets the 1e-3 / 1e-4 parity bar (default); "
                          "the other tensor-core mode is measured too and reported as a sub-record")
     ap.add_argument("--single-mode", action="store_true", help="measure only --mode")
+    ap.add_argument("--engines", type=int, default=2, help="engine handles per GPU that take alternate batches (Predictor(replicas=...)); "
+                                                             "1 = strictly one batch at a time")
     ap.add_argument("--parity-slices", type=int, default=32, help="slices of the timed batch checked against the CPU oracle in-run")
     ap.add_argument("--no-library", action="store_true", help="skip the stock-PyTorch (cuDNN) library baseline")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -77,6 +77,53 @@ def test_host_pipeline_matches_direct_call(ysp, predictor):
     assert hp.h2d_bytes == B * 240 * 240 * 4 + B * 240 * 240 * 4 and hp.d2h_bytes > 0
 
 
+@pytest.mark.parametrize("mode", ["tc32", "bf16"])
+def test_replicas_take_alternate_batches(ysp, models, mode):
+    """Predictor(replicas=2): consecutive batches run on alternate engine handles / streams (submit_raw, HostPipeline) and
+    every batch gets bit-identical results to the single-handle call, whatever overlaps with it."""
+    pred, seg = models
+    one = ysp.Predictor.from_modules(pred, seg, mode=mode)
+    two = ysp.Predictor.from_modules(pred, seg, mode=mode, replicas=2)
+    assert len(two.replicas) == 2 and two.replicas[0] is two
+    g = torch.Generator().manual_seed(23)
+    B, NB = 5, 6
+    u8 = [torch.randint(0, 256, (B, 240, 240, 4), dtype=torch.uint8, generator=g) for _ in range(NB)]
+    tg = (torch.rand(B, 240, 240, generator=g) > 0.5).to(torch.uint8) * 255
+    keys = ("mask_logits", "counts", "det_count", "det_idx", "det_boxes", "y")
+    want = []
+    for x in u8:
+        o = one.predict_raw(x.cuda(), tg.cuda())
+        torch.cuda.synchronize()
+        want.append({k: o[k].clone() for k in keys})
+    # device-resident round robin
+    d = [x.cuda() for x in u8]
+    dt = tg.cuda()
+    got = [None] * NB
+    for i in range(NB):
+        two.submit_raw(d[i], dt, after=lambda o, i=i: got.__setitem__(i, {k: o[k].clone() for k in keys}))
+    two.join()
+    torch.cuda.synchronize()
+    assert two.replicas[1].engine.launches_total > 0 and two.launches_total == 2 * two.replicas[1].engine.launches_total
+    for i in range(NB):
+        n = want[i]["det_count"].tolist()
+        for k in ("mask_logits", "counts", "det_count", "y"):
+            assert torch.equal(got[i][k], want[i][k]), (i, k)
+        for b in range(B):
+            assert torch.equal(got[i]["det_idx"][b, : n[b]], want[i]["det_idx"][b, : n[b]])
+            assert torch.equal(got[i]["det_boxes"][b, : n[b]], want[i]["det_boxes"][b, : n[b]])
+    # host pipeline: slot k computes on replica k
+    hp = ysp.HostPipeline(two, B, 240, 240)
+    assert len(hp.run_streams) == 2
+    hx, ht = [x.pin_memory() for x in u8], tg.pin_memory()
+    res = []
+    for i in range(NB):
+        slot = hp.submit(hx[i], ht)
+        res.append({k: v.clone() for k, v in hp.results(slot).items()})
+    hp.synchronize()
+    for i in range(NB):
+        assert torch.equal(res[i]["counts"], want[i]["counts"].cpu()) and torch.equal(res[i]["det_count"], want[i]["det_count"].cpu())
+
+
 @pytest.mark.parametrize("B,size", [(1, 240), (3, 160), (5, 96)])
 def test_odd_batches_and_sizes(ysp, models, predictor, B, size):
     g = torch.Generator().manual_seed(B * 1000 + size)

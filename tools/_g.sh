@@ -1,6 +1,16 @@
 mkdir -p gpurun_out/r8
-timeout 600 python bench.py --workload train --steps 20 --warmup 3 > gpurun_out/r8/train_n1.json 2> gpurun_out/r8/train_n1.err; echo "train bench rc=$?"
+timeout 900 python -m pytest tests/test_gpu_eval.py -x -q -m gpu > gpurun_out/r8/pytest_eval.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/r8/pytest_eval.log
+timeout 900 python bench.py --steps 40 --no-library --no-cpu > gpurun_out/r8/bench_e2.json 2> gpurun_out/r8/bench_e2.err; echo "bench rc=$?"; tail -3 gpurun_out/r8/bench_e2.err
 python -c "
-import json;d=json.load(open('gpurun_out/r8/train_n1.json'));print(d['value'],d['ms_per_step'],d['gpu_launches'],d['roofline'],d['cpu_baseline'])"
-timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r8/launches_train.csv python bench.py --workload train --steps 1 --warmup 2 --no-cpu > gpurun_out/r8/ncu_train.log 2>&1; echo "ncu rc=$?"
-python tools/train_step_table.py gpurun_out/r8/launches_train.csv > gpurun_out/r8/train_table.md; head -45 gpurun_out/r8/train_table.md
+import json;d=json.load(open('gpurun_out/r8/bench_e2.json'))
+for k in ('value','ms_per_step','e2e','e2e_with_mask','parity','step_ms','gpu_launches'): print(k, d.get(k))
+t=d['throughput_mode']; print('bf16', t['value'], t['e2e']['value'], t['parity']['logits_max_abs'])
+print(d['config']['engines'])
+"
+timeout 900 python bench.py --steps 40 --no-library --no-cpu --engines 1 --single-mode 2>/dev/null | python -c "
+import json,sys;d=json.loads(sys.stdin.read()); print('engines=1', d['value'], d['e2e']['value'])"
+timeout 900 python bench.py --workload eval 2>/dev/null | python -c "
+import json,sys;d=json.loads(sys.stdin.read()); print('eval', d['value'], d['ms_per_step'], d['e2e']['value'], d['metrics'], d['metrics_e2e_equal'])"
+timeout 900 python bench.py --workload eval --engines 1 2>/dev/null | python -c "
+import json,sys;d=json.loads(sys.stdin.read()); print('eval engines=1', d['value'], d['ms_per_step'], d['e2e']['value'], d['metrics'], d['metrics_e2e_equal'])"
