@@ -1,16 +1,12 @@
 mkdir -p gpurun_out/r8
-timeout 900 python -m pytest tests/test_gpu_eval.py -x -q -m gpu > gpurun_out/r8/pytest_eval.log 2>&1; echo "pytest rc=$?"
-tail -5 gpurun_out/r8/pytest_eval.log
-timeout 900 python bench.py --steps 40 --no-library --no-cpu > gpurun_out/r8/bench_e2.json 2> gpurun_out/r8/bench_e2.err; echo "bench rc=$?"; tail -3 gpurun_out/r8/bench_e2.err
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r8/pytest_all.log 2>&1; echo "pytest rc=$?"
+tail -4 gpurun_out/r8/pytest_all.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/r8/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/r8/smoke.log
+timeout 900 python bench.py > gpurun_out/r8/bench_n1.json 2> gpurun_out/r8/bench_n1.err; echo "bench rc=$?"
 python -c "
-import json;d=json.load(open('gpurun_out/r8/bench_e2.json'))
-for k in ('value','ms_per_step','e2e','e2e_with_mask','parity','step_ms','gpu_launches'): print(k, d.get(k))
-t=d['throughput_mode']; print('bf16', t['value'], t['e2e']['value'], t['parity']['logits_max_abs'])
-print(d['config']['engines'])
+import json;d=json.load(open('gpurun_out/r8/bench_n1.json'))
+for k in ('value','ms_per_step','step_ms','gpu_launches','clocks'): print(k, d.get(k))
+print('e2e', d['e2e']['value'], d['e2e_with_mask']['value'])
+t=d['throughput_mode']; print('bf16', t['value'], t['e2e']['value'])
+print(d['roofline']['frac'], d['roofline']['us_per_launch']); print(d['cpu_baseline'])
 "
-timeout 900 python bench.py --steps 40 --no-library --no-cpu --engines 1 --single-mode 2>/dev/null | python -c "
-import json,sys;d=json.loads(sys.stdin.read()); print('engines=1', d['value'], d['e2e']['value'])"
-timeout 900 python bench.py --workload eval 2>/dev/null | python -c "
-import json,sys;d=json.loads(sys.stdin.read()); print('eval', d['value'], d['ms_per_step'], d['e2e']['value'], d['metrics'], d['metrics_e2e_equal'])"
-timeout 900 python bench.py --workload eval --engines 1 2>/dev/null | python -c "
-import json,sys;d=json.loads(sys.stdin.read()); print('eval engines=1', d['value'], d['ms_per_step'], d['e2e']['value'], d['metrics'], d['metrics_e2e_equal'])"
