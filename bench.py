@@ -680,14 +680,15 @@ def main_train(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    ahead = args.lookahead               # opt-in: the next batch's frozen-encoder pass runs under this step's decoder kernels
     for i in range(Wm):
-        tr.step(xs[i % nbuf], tg, lgs[i % nbuf])
+        tr.step(xs[i % nbuf], tg, lgs[i % nbuf], next_img=xs[(i + 1) % nbuf] if ahead else None)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.time()
     e0.record()
     for i in range(K):
-        loss, _ = tr.step(xs[i % nbuf], tg, lgs[i % nbuf])
+        loss, _ = tr.step(xs[(Wm + i) % nbuf], tg, lgs[(Wm + i) % nbuf], next_img=xs[(Wm + i + 1) % nbuf] if ahead and i + 1 < K else None)
     e1.record()
     torch.cuda.synchronize()
     tw1 = time.time()
@@ -866,6 +867,8 @@ def main():
                          "nms = BASELINE cfg 5 (NMS stress)")
     ap.add_argument("--volumes", type=int, default=64, help="eval workload: number of 155-slice volumes")
     ap.add_argument("--loss", default="dice_bce", choices=["dice", "dice_bce"])
+    ap.add_argument("--lookahead", action="store_true", help="train workload: launch the next batch's frozen-encoder pass ahead, on a side stream "
+                                                             "(measured 15.16 -> 15.04 ms per step, but one run in three at 17 ms: off by default)")
     args = ap.parse_args()
     if args.workload == "train" and args.batch == 256:
         args.batch = 128

@@ -228,3 +228,30 @@ def test_mixed_precision_branch_grad_scaler():
     # and training goes on
     l3, _ = amp.step(xc, tgc, lgc)
     assert amp.step_count == 3 and torch.isfinite(l3).all()
+
+
+def test_encoder_lookahead_gives_identical_steps():
+    """step(..., next_img=...) launches the NEXT batch's frozen-encoder pass on a side stream; the training trajectory does
+    not change (same losses; parameters equal up to the summation order of the gradient atomics)."""
+    B, S = 2, 64
+    seg, a, x, lg, tg = _setup(B, S)
+    _, b, _, _, _ = _setup(B, S)
+    from oracle.model import synth_inputs
+    batches = [tuple(t.cuda() for t in synth_inputs(B, S, seed=40 + i)) for i in range(4)]
+    la, lb = [], []
+    for i, (xi, lgi, tgi) in enumerate(batches):
+        la.append(a.step(xi, tgi, lgi)[0].clone())
+        nxt = batches[i + 1][0] if i + 1 < len(batches) else None
+        lb.append(b.step(xi, tgi, lgi, next_img=nxt)[0].clone())
+    torch.cuda.synchronize()
+    assert b._ahead is None and b._enc_stream is not None
+    for u, v in zip(la, lb):
+        assert (u - v).abs().max().item() <= 2e-5
+    start = _setup(B, S)[1].params
+    rel = ((a.params - b.params).norm() / (a.params - start).norm()).item()
+    assert rel <= 2e-2, rel
+    # a batch that was not announced still works (encoder runs inline), and an announced batch that never arrives is dropped
+    b.step(batches[0][0], batches[0][2], batches[0][1], next_img=batches[1][0])
+    l = b.step(batches[2][0], batches[2][2], batches[2][1])[0]
+    torch.cuda.synchronize()
+    assert torch.isfinite(l).all()
