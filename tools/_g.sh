@@ -1,7 +1,4 @@
 mkdir -p gpurun_out/r8
-timeout 900 python -m pytest tests/test_gpu_train.py -x -q -m gpu > gpurun_out/r8/pytest_train.log 2>&1; echo "pytest rc=$?"
-tail -5 gpurun_out/r8/pytest_train.log
-for v in "" "--no-lookahead" ""; do
-  timeout 300 python bench.py --workload train --steps 20 --warmup 3 --no-cpu $v 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('$v', d['value'], d['ms_per_step'], d['loss'], d['gpu_launches'])"
-done
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/r8/launches_tc32.csv python bench.py --steps 2 --warmup 1 --single-mode --no-library --no-cpu --parity-slices 0 > gpurun_out/r8/ncu_bench.log 2>&1; echo "ncu rc=$?"
+tail -2 gpurun_out/r8/ncu_bench.log | cut -c1-300
+grep -c mask_dice gpurun_out/r8/launches_tc32.csv
