@@ -526,18 +526,22 @@ void launch_dlc32(const Dlc32P& p, cudaStream_t s) {
   // Measured at B = 256 (tools/profile_layers.py tc32, profiles/r7_*): with CTA-wide barriers between the phases, small CTAs win
   // where they fit -- stage 4 (C = 16): four 128-thread CTAs per SM on 14 x 14 tiles 1.09 ms, two 256-thread CTAs on 14 x 30
   // tiles 2.12 ms (ncu: 28 % of the stall samples were barrier waits); stage 3 (C = 32): two 256-thread CTAs 0.67 ms, three
-  // 128-thread CTAs with the c tile over the b tiles 0.75 ms; stage 1 (C = 64, one CTA per SM): 512 threads 0.55 ms, 256
-  // threads 0.67 ms.  YSP_DLC32_CFG=1 selects the alternative of each pair (A/B timing only).
+  // 128-thread CTAs with the c tile over the b tiles 0.75 ms, four 128-thread CTAs on 14 x 6 tiles 0.665 ms (YSP_DLC32_CFG=2);
+  // stage 1 (C = 64): 14 x 14 tiles need 157 KB = ONE CTA per SM, whose phases then run strictly one after the other (512
+  // threads 0.57 ms, 256 threads 0.67 ms); 14 x 6 tiles fit twice (102 KB) and the two CTAs cover each other's barriers:
+  // 0.43 ms although the halo overhead grows from 1.31x to 1.52x.  YSP_DLC32_CFG=1 / 3 select the alternatives (A/B timing only).
   static const int cfg = getenv("YSP_DLC32_CFG") ? atoi(getenv("YSP_DLC32_CFG")) : 0;
   if (p.C == 16) {
     if (cfg == 1) dlc32_launch<16, 32, 256, 2, false, true>(p, s);
     else dlc32_launch<16, 16, 128, 1, false, true>(p, s);
   } else if (p.C == 32) {
     if (cfg == 1) dlc32_launch<32, 16, 128, 1, true, false>(p, s);
+    else if (cfg == 2) dlc32_launch<32, 8, 128, 1, true, false>(p, s);      // 14 x 6 tiles: four CTAs per SM
     else dlc32_launch<32, 16, 256, 1, false, false>(p, s);
   } else {
     if (cfg == 1) dlc32_launch<64, 16, 256, 1, true, false>(p, s);
-    else dlc32_launch<64, 16, 512, 1, true, false>(p, s);
+    else if (cfg == 3) dlc32_launch<64, 16, 512, 1, true, false>(p, s);
+    else dlc32_launch<64, 8, 256, 1, true, false>(p, s);                    // 14 x 6 tiles: 102 KB -> TWO CTAs per SM
   }
 }
 
