@@ -1,17 +1,7 @@
 mkdir -p gpurun_out/r8
-for v in "A=1" "YSP_TC32_ONE_GROUP=1"; do
-  echo "== $v"
-  env $v timeout 300 python tools/profile_layers.py tc32 256 > gpurun_out/r8/layers_$v.md 2>&1
-  grep -E "sum of" gpurun_out/r8/layers_$v.md
-  python - <<PY
-import re
-k={}
-for l in open("gpurun_out/r8/layers_$v.md"):
-    m=l.split('|')
-    if len(m)>5:
-        try: k.setdefault(m[2].strip(),[0,0.]); k[m[2].strip()][0]+=1; k[m[2].strip()][1]+=float(m[3])
-        except: pass
-for a,b in sorted(k.items(),key=lambda x:-x[1][1])[:6]: print(a,b)
-PY
+timeout 900 python -m pytest tests/test_gpu_train.py -x -q -m gpu > gpurun_out/r8/pytest_train.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/r8/pytest_train.log
+for v in "A=0" "YSP_DWFUSE_CFG=1" "A=1"; do
+  env $v timeout 300 python bench.py --workload train --steps 20 --warmup 3 --no-cpu 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('$v', d['value'], d['ms_per_step'], d['loss'], d['gpu_launches'])"
 done
-timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_golden.py -x -q -m gpu 2>&1 | tail -2
