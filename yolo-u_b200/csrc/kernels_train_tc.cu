@@ -313,6 +313,8 @@ __global__ void __launch_bounds__(kGT, 512 / kGT) pw_gemm_tc_kernel(const GemmTc
   }
 }
 
+static bool launch_pw_gemm_tc2(GemmTcP p, int trans, cudaStream_t s);       // the warp-specialised version below
+
 // true when the launch was taken (tensor-core path); false -> the caller runs the FFMA kernel
 bool launch_pw_gemm_tc(const float* A, int lda, const float* W, int ldw, int trans, const float* bias, float* C, int ldc, long long M,
                        int I, int J, int beta, cudaStream_t s, double* sums, InTf tf, PwDual du) {
@@ -325,6 +327,9 @@ bool launch_pw_gemm_tc(const float* A, int lda, const float* W, int ldw, int tra
   p.N = (J + 15) / 16 * 16;
   if (p.N > 256 || p.Kt > 288 || J < 8) return false;                        // narrow outputs (the 16 -> 1 head) stay on CUDA cores
   if (du.Jsplit && (du.Jsplit & 15)) return false;                            // rider columns must start on a 16-column chunk
+  // large launches with N <= 64 go to the warp-specialised ring version below (15.14 -> 14.89 ms per step; YSP_TRAIN_GEMM_RING=0: A/B)
+  static const int ring = getenv("YSP_TRAIN_GEMM_RING") ? atoi(getenv("YSP_TRAIN_GEMM_RING")) : 1;
+  if (ring && M >= 128 * 296 && launch_pw_gemm_tc2(p, trans, s)) return true;
   // Rows per iteration: as many 128-row blocks (1, 2 or 4) as keep the A tiles within 64 KB and the 2 NB accumulators within 256
   // TMEM columns (two 256-thread CTAs per SM) -- the narrow GEMMs of the full-resolution stages move 16 KB per block and are
   // latency-bound one block at a time.  (Four 128-thread CTAs per SM, the shape that halved the inference decoder kernel,
@@ -354,6 +359,306 @@ bool launch_pw_gemm_tc(const float* A, int lda, const float* W, int ldw, int tra
   ensure_dyn_smem(pw_gemm_tc_kernel<false, 256>, 200 * 1024, attr_b, "pw_gemm_tc_kernel<bf16>");
   if (trans) pw_gemm_tc_kernel<false, 256><<<grid, 256, smem, s>>>(p);      // input gradient: bf16 hi/mid operands
   else pw_gemm_tc_kernel<true, 256><<<grid, 256, smem, s>>>(p);            // forward: fp16 hi/lo operands
+  return true;
+}
+
+// =====================================================================================================================
+// The same GEMM, warp-specialised (the kernel above runs load -> MMA -> epilogue -> statistics one after the other inside a CTA;
+// ncu: 25-35 % of its stall samples wait for the loads, 10-14 % at the CTA barriers, and every instruction added to its epilogue is
+// on the critical path).  Here a 128-row block travels through a ring:
+//   loader groups (NLG x 4 warps, thread = row): fp32 row -> [transform] -> split -> operand slot; group g takes the blocks with
+//                 (block index % NLG) == g, so NLG blocks are being loaded at once;                          full[s] / empty[s]
+//   MMA warp:     3 x Kt/16 MMAs per block into one of two accumulator pairs in TMEM;                          tfull[a] / tempty[a]
+//   epilogue (4 warps): tcgen05.ld -> un-scale, bias, beta -> store; BatchNorm statistics of the output by a reduce-scatter
+//                 butterfly over the warp's 32 rows (31 shuffles for 16 columns x {sum, sum of squares}) into per-warp double
+//                 accumulators.
+// Same arithmetic, operand layouts and weight prologue as pw_gemm_tc_kernel.
+// =====================================================================================================================
+namespace {
+constexpr int kG2LG = 2;                                  // loader groups (3 groups = 544 threads leave 56 registers: spills, 15.4 ms)
+constexpr int kG2Threads = 32 * (4 * kG2LG + 1 + 4);     // 13 warps
+constexpr int kG2MaxS = 6;
+__device__ __forceinline__ void mbar_arrive2(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
+}
+}  // namespace
+
+template <bool F16>
+__global__ void __launch_bounds__(kG2Threads, 2) pw_gemm_tc2_kernel(const GemmTcP p, const int S) {
+  extern __shared__ __align__(128) uint8_t gsm2[];
+  const int planes = p.Kt >> 3;
+  const int slot_bytes = 2 * planes * 2048;                  // hi then lo: [plane][128 rows] x 16 B
+  uint8_t* sB = gsm2;                                        // hi [Kt/8][N] x 16 B, then lo
+  uint8_t* sA = gsm2 + ((2 * p.b_half + 127) & ~127);        // S slots
+  float* sSc = reinterpret_cast<float*>(sA + (size_t)S * slot_bytes);
+  float* sSh = sSc + p.K0;
+  float* sBias = sSh + p.K0;
+  double* sAcc = reinterpret_cast<double*>(sBias + p.N + ((2 * p.K0 + p.N) & 1));   // [4 epilogue warps][2][N]
+  __shared__ __align__(8) uint64_t full_bar[kG2MaxS], empty_bar[kG2MaxS], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_s;
+  __shared__ float red[16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool tfon = p.tf.gamma != nullptr;
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(s32(&full_bar[i])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&empty_bar[i])));
+    }
+    for (int i = 0; i < 2; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&tfull_bar[i])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(s32(&tempty_bar[i])));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4 * kG2LG) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_s)), "r"((uint32_t)p.tcols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // ---- weights -> B operand (as in pw_gemm_tc_kernel) ----
+  float wmax = 0.f;
+  if (F16) {
+    for (int e = tid; e < p.Kt * p.N; e += kG2Threads) wmax = fmaxf(wmax, fabsf(weight_at(p, e % p.Kt, e / p.Kt)));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) red[warp] = wmax;
+  }
+  for (int i = tid; i < p.K0; i += kG2Threads) {
+    float sc = 1.f, sh = 0.f;
+    if (tfon && i < p.I0) { sc = p.tf.gamma[i] * p.tf.invstd[i]; sh = p.tf.beta[i] - p.tf.mean[i] * sc; }
+    sSc[i] = sc; sSh[i] = sh;
+  }
+  for (int j = tid; j < p.N; j += kG2Threads) {
+    float b = 0.f;
+    if (j < p.J) {
+      if (p.du.Jsplit && j >= p.du.Jsplit) b = p.du.biasb ? p.du.biasb[j - p.du.Jsplit] : 0.f;
+      else b = p.bias ? p.bias[j] : 0.f;
+    }
+    sBias[j] = b;
+  }
+  for (int i = tid; i < 8 * p.N; i += kG2Threads) sAcc[i] = 0.0;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  int e2 = 0;
+  if (F16) {
+    wmax = 0.f;
+    for (int w = 0; w < kG2Threads / 32; ++w) wmax = fmaxf(wmax, red[w]);
+    if (wmax > 0.f) { int ex; frexpf(wmax, &ex); e2 = 14 - ex; }
+  }
+  const float wsc = ldexpf(1.f, e2), unscale = ldexpf(1.f, -e2);
+  for (int e = tid; e < (p.Kt >> 1) * p.N; e += kG2Threads) {
+    const int kp = e % (p.Kt >> 1), j = e / (p.Kt >> 1), k = 2 * kp;
+    uint32_t hi, lo;
+    if (F16) split2_f16(weight_at(p, k, j) * wsc, weight_at(p, k + 1, j) * wsc, hi, lo);
+    else split2_bf16(weight_at(p, k, j), weight_at(p, k + 1, j), hi, lo);
+    const uint32_t off = (uint32_t)(k >> 3) * (uint32_t)(p.N * 16) + (uint32_t)j * 16u + (uint32_t)(k & 7) * 2u;
+    *reinterpret_cast<uint32_t*>(sB + off) = hi;
+    *reinterpret_cast<uint32_t*>(sB + p.b_half + off) = lo;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const uint32_t tmem = tmem_s;
+  const long long mtiles = (p.M + 127) / 128;
+  const int Jstat = p.du.Jsplit ? p.du.Jsplit : p.J;
+
+  if (warp < 4 * kG2LG) {
+    // ===== loaders: fp32 row -> [transform] -> split -> operand slot =====
+    const int grp = warp >> 2, row = (warp & 3) * 32 + lane;
+    const bool vecA0 = ((p.lda0 | p.I0) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.A0) & 15) == 0;
+    const bool vecA2 = p.du.A2 && ((p.du.lda2 | p.du.I2) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.du.A2) & 15) == 0;
+    int s = 0; uint32_t ph = 0; int gi = 0;
+    for (long long mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+      if (gi == grp) {
+        const long long m = mt * 128 + row;
+        uint32_t par = ph ^ 1u;
+        asm volatile("{\n\t.reg .pred q;\n\tWE2:\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t@q bra DE2;\n\tbra WE2;\n\tDE2:\n\t}"
+                     ::"r"(s32(&empty_bar[s])), "r"(par) : "memory");
+        uint8_t* slot = sA + (size_t)s * slot_bytes;
+        constexpr int UB = 4;
+#pragma unroll 1
+        for (int g0 = 0; g0 < planes; g0 += UB) {
+          float v[UB][8];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int g = g0 + u;
+            if (g < planes) {
+              const int k0 = g * 8;
+              const bool part2 = k0 >= p.K0;
+              const float* src = part2 ? p.du.A2 + m * p.du.lda2 + (k0 - p.K0) : p.A0 + m * p.lda0 + k0;
+              const int valid = part2 ? p.du.I2 - (k0 - p.K0) : p.I0 - k0;
+              if (m < p.M && valid >= 8 && (part2 ? vecA2 : vecA0)) {
+                const float4 a = *reinterpret_cast<const float4*>(src), bq = *reinterpret_cast<const float4*>(src + 4);
+                v[u][0] = a.x; v[u][1] = a.y; v[u][2] = a.z; v[u][3] = a.w; v[u][4] = bq.x; v[u][5] = bq.y; v[u][6] = bq.z; v[u][7] = bq.w;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[u][j] = (m < p.M && j < valid) ? src[j] : 0.f;
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int g = g0 + u;
+            if (g >= planes) break;
+            const int k0 = g * 8;
+            if (tfon && k0 < p.K0 && m < p.M) {
+              const float4 c0 = *reinterpret_cast<const float4*>(sSc + k0), c1 = *reinterpret_cast<const float4*>(sSc + k0 + 4);
+              const float4 h0 = *reinterpret_cast<const float4*>(sSh + k0), h1 = *reinterpret_cast<const float4*>(sSh + k0 + 4);
+              const float sc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                float2 x = __ffma2_rn(make_float2(v[u][j], v[u][j + 1]), make_float2(sc[j], sc[j + 1]), make_float2(sh[j], sh[j + 1]));
+                if (p.tf.act) x = silu2_f(x);
+                v[u][j] = k0 + j < p.I0 ? x.x : 0.f; v[u][j + 1] = k0 + j + 1 < p.I0 ? x.y : 0.f;
+              }
+            }
+            uint4 h, l;
+            if (F16) {
+              split2_f16(v[u][0], v[u][1], h.x, l.x); split2_f16(v[u][2], v[u][3], h.y, l.y);
+              split2_f16(v[u][4], v[u][5], h.z, l.z); split2_f16(v[u][6], v[u][7], h.w, l.w);
+            } else {
+              split2_bf16(v[u][0], v[u][1], h.x, l.x); split2_bf16(v[u][2], v[u][3], h.y, l.y);
+              split2_bf16(v[u][4], v[u][5], h.z, l.z); split2_bf16(v[u][6], v[u][7], h.w, l.w);
+            }
+            *reinterpret_cast<uint4*>(slot + g * 2048 + row * 16) = h;
+            *reinterpret_cast<uint4*>(slot + planes * 2048 + g * 2048 + row * 16) = l;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive2(&full_bar[s]);
+      }
+      if (++gi == kG2LG) gi = 0;
+      if (++s == S) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 4 * kG2LG) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t b0 = s32(sB);
+      int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
+      for (long long mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+        mbar_wait_parity(&tempty_bar[acc], aph ^ 1u);
+        mbar_wait_parity(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = s32(sA + (size_t)s * slot_bytes), al0 = a0 + planes * 2048;
+        const uint32_t d0 = tmem + (uint32_t)(acc * 2 * p.N);
+        for (int ks = 0; ks < (p.Kt >> 4); ++ks) {
+          const uint64_t bh = desc_nosw(b0 + ks * 2 * p.N * 16, (uint32_t)p.N * 16u, 128u);
+          const uint64_t bl = desc_nosw(b0 + p.b_half + ks * 2 * p.N * 16, (uint32_t)p.N * 16u, 128u);
+          const uint64_t ah = desc_nosw(a0 + ks * 4096, 2048u, 128u), am = desc_nosw(al0 + ks * 4096, 2048u, 128u);
+          umma_f16(d0, ah, bh, idesc, ks ? 1u : 0u);                  // hi . hi
+          umma_f16(d0 + p.N, am, bh, idesc, ks ? 1u : 0u);            // lo . hi
+          umma_f16(d0 + p.N, ah, bl, idesc, 1u);                      // hi . lo
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&empty_bar[s])) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&tfull_bar[acc])) : "memory");
+        if (++s == S) { s = 0; ph ^= 1u; }
+        if (++acc == 2) { acc = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue: warp w owns TMEM lanes [32q, 32q + 32), q = w & 3 =====
+    const int q = warp & 3, ew = warp - (4 * kG2LG + 1);
+    double* myAcc = sAcc + (size_t)ew * 2 * p.N;
+    const bool vecC = ((p.ldc | p.J | p.du.Jsplit | p.du.ldcb) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.du.Cb) & 15) == 0;
+    int acc = 0; uint32_t aph = 0;
+    for (long long mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+      const long long em = mt * 128 + q * 32 + lane;
+      mbar_wait_parity(&tfull_bar[acc], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * p.N);
+      for (int c0 = 0; c0 < p.N; c0 += 16) {
+        uint32_t v[16], w[16];
+        ld16(taddr + c0, v);
+        ld16(taddr + p.N + c0, w);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = (__uint_as_float(v[j]) + __uint_as_float(w[j])) * unscale;
+        if (p.sums && c0 < Jstat) {
+          // column sums of the bias-free product over this warp's 32 rows (rows >= M hold exact zeros)
+          float r[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { r[j] = f[j]; r[16 + j] = f[j] * f[j]; }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; ++i) {
+              const float send = up ? r[i] : r[i + o], keep = up ? r[i + o] : r[i];
+              r[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          myAcc[(lane >> 4) * p.N + c0 + (lane & 15)] += (double)r[0];
+        }
+        if (em < p.M && c0 < p.J) {
+          const bool second = p.du.Jsplit && c0 >= p.du.Jsplit;
+          float* crow = second ? p.du.Cb + em * p.du.ldcb + (c0 - p.du.Jsplit) : p.C + em * p.ldc + c0;
+          const int nvalid = (second ? p.J : (p.du.Jsplit ? p.du.Jsplit : p.J)) - c0;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + 4 * j4);
+            f[4 * j4] += b4.x; f[4 * j4 + 1] += b4.y; f[4 * j4 + 2] += b4.z; f[4 * j4 + 3] += b4.w;
+          }
+          if (vecC && nvalid >= 16) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              float4 o = make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+              float4* op = reinterpret_cast<float4*>(crow) + j4;
+              if (p.beta) { const float4 pv = *op; o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w; }
+              *op = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < nvalid) crow[j] = p.beta ? crow[j] + f[j] : f[j];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive2(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; aph ^= 1u; }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (p.sums) {
+    for (int e = tid; e < 2 * p.N; e += kG2Threads) {
+      const int h = e / p.N, col = e - h * p.N;
+      if (col >= Jstat) continue;
+      atomicAdd(&p.sums[h * Jstat + col], sAcc[e] + sAcc[2 * p.N + e] + sAcc[4 * p.N + e] + sAcc[6 * p.N + e]);
+    }
+  }
+  if (warp == 4 * kG2LG) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tcols) : "memory");
+  }
+}
+
+// false: shape outside the envelope (two accumulator pairs must fit 256 TMEM columns, at least three ring slots in ~100 KB)
+static bool launch_pw_gemm_tc2(GemmTcP p, int trans, cudaStream_t s) {
+  if (4 * p.N > 256) return false;
+  p.NB = 1;
+  p.tcols = 32;
+  while (p.tcols < 4 * p.N) p.tcols <<= 1;
+  p.b_half = (p.Kt / 8) * p.N * 16;
+  const size_t slot = 2 * (size_t)(p.Kt / 8) * 2048;
+  const size_t fixed = ((2 * (size_t)p.b_half + 127) & ~(size_t)127) + (size_t)(2 * p.K0 + p.N + 1) * 4 + (size_t)8 * p.N * 8 + 256;
+  int S = (int)((100 * 1024 - fixed) / slot);
+  if (S > kG2MaxS) S = kG2MaxS;
+  if (S < 3) return false;
+  const size_t smem = fixed + (size_t)S * slot;
+  static int sms = 0;
+  if (!sms) { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d); if (sms <= 0) sms = 148; }
+  const long long mtiles = (p.M + 127) / 128;
+  const int grid = (int)std::min<long long>(mtiles, (long long)sms * 2);
+  static unsigned long long attr_f = 0, attr_b = 0;
+  ensure_dyn_smem(pw_gemm_tc2_kernel<true>, 110 * 1024, attr_f, "pw_gemm_tc2_kernel<f16>");
+  ensure_dyn_smem(pw_gemm_tc2_kernel<false>, 110 * 1024, attr_b, "pw_gemm_tc2_kernel<bf16>");
+  if (trans) pw_gemm_tc2_kernel<false><<<grid, kG2Threads, smem, s>>>(p, S);
+  else pw_gemm_tc2_kernel<true><<<grid, kG2Threads, smem, s>>>(p, S);
   return true;
 }
 
