@@ -376,7 +376,9 @@ bool launch_pw_gemm_tc(const float* A, int lda, const float* W, int ldw, int tra
 // =====================================================================================================================
 namespace {
 constexpr int kG2LG = 2;                                  // loader groups (3 groups = 544 threads leave 56 registers: spills, 15.4 ms)
-constexpr int kG2Threads = 32 * (4 * kG2LG + 1 + 4);     // 13 warps
+constexpr int kG2EG = 1;                                  // epilogue groups of four warps (group g drains accumulator pair g of two);
+                                                          // one loader group + two epilogue groups measured 15.3 ms against 14.9
+constexpr int kG2Threads = 32 * (4 * kG2LG + 1 + 4 * kG2EG);
 constexpr int kG2MaxS = 6;
 __device__ __forceinline__ void mbar_arrive2(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(kG2Threads, 2) pw_gemm_tc2_kernel(const GemmTc
   float* sSc = reinterpret_cast<float*>(sA + (size_t)S * slot_bytes);
   float* sSh = sSc + p.K0;
   float* sBias = sSh + p.K0;
-  double* sAcc = reinterpret_cast<double*>(sBias + p.N + ((2 * p.K0 + p.N) & 1));   // [4 epilogue warps][2][N]
+  double* sAcc = reinterpret_cast<double*>(sBias + p.N + ((2 * p.K0 + p.N) & 1));   // [4 * kG2EG epilogue warps][2][N]
   __shared__ __align__(8) uint64_t full_bar[kG2MaxS], empty_bar[kG2MaxS], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_s;
   __shared__ float red[16];
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(kG2Threads, 2) pw_gemm_tc2_kernel(const GemmTc
     }
     sBias[j] = b;
   }
-  for (int i = tid; i < 8 * p.N; i += kG2Threads) sAcc[i] = 0.0;
+  for (int i = tid; i < 8 * kG2EG * p.N; i += kG2Threads) sAcc[i] = 0.0;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -562,8 +564,13 @@ __global__ void __launch_bounds__(kG2Threads, 2) pw_gemm_tc2_kernel(const GemmTc
     double* myAcc = sAcc + (size_t)ew * 2 * p.N;
     const bool vecC = ((p.ldc | p.J | p.du.Jsplit | p.du.ldcb) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(p.du.Cb) & 15) == 0;
+    const int egrp = ew >> 2;
     int acc = 0; uint32_t aph = 0;
     for (long long mt = blockIdx.x; mt < mtiles; mt += gridDim.x) {
+      if (kG2EG == 2 && acc != egrp) {                     // the other group's accumulator pair
+        if (++acc == 2) { acc = 0; aph ^= 1u; }
+        continue;
+      }
       const long long em = mt * 128 + q * 32 + lane;
       mbar_wait_parity(&tfull_bar[acc], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -628,7 +635,10 @@ __global__ void __launch_bounds__(kG2Threads, 2) pw_gemm_tc2_kernel(const GemmTc
     for (int e = tid; e < 2 * p.N; e += kG2Threads) {
       const int h = e / p.N, col = e - h * p.N;
       if (col >= Jstat) continue;
-      atomicAdd(&p.sums[h * Jstat + col], sAcc[e] + sAcc[2 * p.N + e] + sAcc[4 * p.N + e] + sAcc[6 * p.N + e]);
+      double a = 0.0;
+#pragma unroll
+      for (int w = 0; w < 4 * kG2EG; ++w) a += sAcc[(size_t)w * 2 * p.N + e];
+      atomicAdd(&p.sums[h * Jstat + col], a);
     }
   }
   if (warp == 4 * kG2LG) {
@@ -645,7 +655,7 @@ static bool launch_pw_gemm_tc2(GemmTcP p, int trans, cudaStream_t s) {
   while (p.tcols < 4 * p.N) p.tcols <<= 1;
   p.b_half = (p.Kt / 8) * p.N * 16;
   const size_t slot = 2 * (size_t)(p.Kt / 8) * 2048;
-  const size_t fixed = ((2 * (size_t)p.b_half + 127) & ~(size_t)127) + (size_t)(2 * p.K0 + p.N + 1) * 4 + (size_t)8 * p.N * 8 + 256;
+  const size_t fixed = ((2 * (size_t)p.b_half + 127) & ~(size_t)127) + (size_t)(2 * p.K0 + p.N + 1) * 4 + (size_t)8 * kG2EG * p.N * 8 + 256;
   int S = (int)((100 * 1024 - fixed) / slot);
   if (S > kG2MaxS) S = kG2MaxS;
   if (S < 3) return false;
