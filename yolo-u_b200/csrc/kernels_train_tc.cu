@@ -656,17 +656,20 @@ static bool launch_pw_gemm_tc2(GemmTcP p, int trans, cudaStream_t s) {
   p.b_half = (p.Kt / 8) * p.N * 16;
   const size_t slot = 2 * (size_t)(p.Kt / 8) * 2048;
   const size_t fixed = ((2 * (size_t)p.b_half + 127) & ~(size_t)127) + (size_t)(2 * p.K0 + p.N + 1) * 4 + (size_t)8 * kG2EG * p.N * 8 + 256;
-  int S = (int)((100 * 1024 - fixed) / slot);
+  // two CTAs per SM when three ring slots fit ~100 KB; wide reductions (K >= 96: 48 KB and more per slot) run one CTA per SM
+  int per_sm = 2;
+  int S = fixed < 100 * 1024 ? (int)((100 * 1024 - fixed) / slot) : 0;
+  if (S < 3) { per_sm = 1; S = fixed < 208 * 1024 ? (int)((208 * 1024 - fixed) / slot) : 0; }
   if (S > kG2MaxS) S = kG2MaxS;
   if (S < 3) return false;
   const size_t smem = fixed + (size_t)S * slot;
   static int sms = 0;
   if (!sms) { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d); if (sms <= 0) sms = 148; }
   const long long mtiles = (p.M + 127) / 128;
-  const int grid = (int)std::min<long long>(mtiles, (long long)sms * 2);
+  const int grid = (int)std::min<long long>(mtiles, (long long)sms * per_sm);
   static unsigned long long attr_f = 0, attr_b = 0;
-  ensure_dyn_smem(pw_gemm_tc2_kernel<true>, 110 * 1024, attr_f, "pw_gemm_tc2_kernel<f16>");
-  ensure_dyn_smem(pw_gemm_tc2_kernel<false>, 110 * 1024, attr_b, "pw_gemm_tc2_kernel<bf16>");
+  ensure_dyn_smem(pw_gemm_tc2_kernel<true>, 212 * 1024, attr_f, "pw_gemm_tc2_kernel<f16>");
+  ensure_dyn_smem(pw_gemm_tc2_kernel<false>, 212 * 1024, attr_b, "pw_gemm_tc2_kernel<bf16>");
   if (trans) pw_gemm_tc2_kernel<false><<<grid, kG2Threads, smem, s>>>(p, S);
   else pw_gemm_tc2_kernel<true><<<grid, kG2Threads, smem, s>>>(p, S);
   return true;
