@@ -208,6 +208,52 @@ void launch_pw_gemm(const float* A, int lda, const float* W, int ldw, int trans,
 }
 
 // =====================================================================================================================
+// The 1x1 mask head (C -> 1, YOLOSegPlusPlus.py:178) as two streaming kernels: as GEMMs its forward (N = 1) ran on the FFMA
+// kernel at 1.7 TB/s and its input gradient (K = 1, an outer product) on the tensor-core kernel at 2.6 TB/s, both bound by
+// instruction issue.   y[m] = b + sum_c x[m][c] * w[c];   dx[m][c] = dy[m] * w[c].   One thread per pixel, C % 4 == 0, C <= 64.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) lin1_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ w,
+                                                       const float* __restrict__ b, float* __restrict__ Y, int C, long long M) {
+  __shared__ __align__(16) float sw[64];
+  if (threadIdx.x < C) sw[threadIdx.x] = w[threadIdx.x];
+  __syncthreads();
+  const float bias = b ? b[0] : 0.f;
+  for (long long m = (long long)blockIdx.x * 256 + threadIdx.x; m < M; m += (long long)gridDim.x * 256) {
+    const float4* xp = reinterpret_cast<const float4*>(X + m * ldx);
+    float acc = bias;
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+      const float4 v = xp[c4], ww = *reinterpret_cast<const float4*>(sw + 4 * c4);
+      acc = fmaf(v.x, ww.x, acc); acc = fmaf(v.y, ww.y, acc); acc = fmaf(v.z, ww.z, acc); acc = fmaf(v.w, ww.w, acc);
+    }
+    Y[m] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) lin1_dgrad_kernel(const float* __restrict__ DY, const float* __restrict__ w,
+                                                         float* __restrict__ DX, int ldx, int C, long long M) {
+  __shared__ __align__(16) float sw[64];
+  if (threadIdx.x < C) sw[threadIdx.x] = w[threadIdx.x];
+  __syncthreads();
+  for (long long m = (long long)blockIdx.x * 256 + threadIdx.x; m < M; m += (long long)gridDim.x * 256) {
+    const float d = DY[m];
+    float4* op = reinterpret_cast<float4*>(DX + m * ldx);
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+      const float4 ww = *reinterpret_cast<const float4*>(sw + 4 * c4);
+      op[c4] = make_float4(d * ww.x, d * ww.y, d * ww.z, d * ww.w);
+    }
+  }
+}
+bool launch_lin1_fwd(const float* X, int ldx, const float* w, const float* b, float* Y, int C, long long M, cudaStream_t s) {
+  if ((C & 3) || C > 64 || (ldx & 3) || (reinterpret_cast<uintptr_t>(X) & 15)) return false;
+  lin1_fwd_kernel<<<(int)std::min<long long>(cdivl(M, 256), 148 * 16), 256, 0, s>>>(X, ldx, w, b, Y, C, M);
+  return true;
+}
+bool launch_lin1_dgrad(const float* DY, const float* w, float* DX, int ldx, int C, long long M, cudaStream_t s) {
+  if ((C & 3) || C > 64 || (ldx & 3) || (reinterpret_cast<uintptr_t>(DX) & 15)) return false;
+  lin1_dgrad_kernel<<<(int)std::min<long long>(cdivl(M, 256), 148 * 16), 256, 0, s>>>(DY, w, DX, ldx, C, M);
+  return true;
+}
+
+// =====================================================================================================================
 // dW[j][i] += sum_m D[m][j] * X[m][i]   (weight gradient of a 1x1 conv; dW in PyTorch layout, ld = I)
 // CTA = one (TJ x TI) tile of dW and one chunk of rows; the 256 threads form G = 256/((TJ/4)(TI/4)) row groups, each
 // with a 4x4 micro-tile; groups combine through shared-memory atomics, CTAs through global atomics (dW pre-zeroed).

@@ -27,6 +27,9 @@ bool launch_pw_gemm_tc(const float* A, int lda, const float* W, int ldw, int tra
                        long long M, int I, int J, int beta, cudaStream_t s, double* sums, InTf tf, PwDual du);
 bool launch_pw_wgrad_tc(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I, int J,
                         cudaStream_t s, InTf tf);
+// the C -> 1 mask head as streaming kernels (false: shape outside their envelope, the caller uses launch_pw_gemm)
+bool launch_lin1_fwd(const float* X, int ldx, const float* w, const float* b, float* Y, int C, long long M, cudaStream_t s);
+bool launch_lin1_dgrad(const float* DY, const float* w, float* DX, int ldx, int C, long long M, cudaStream_t s);
 void launch_pw_wgrad(const float* D, int ldd, const float* X, int ldx, float* dW, int ldw, long long M, int I, int J,
                      cudaStream_t s, InTf tf = InTf());
 void launch_dw_conv(const float* X, int ldx, const float* W, float* Y, int ldy, int N, int H, int Wd, int C, int k,

@@ -447,13 +447,15 @@ void run_step(ysp_trainer* t, Ctx& c, const StepIO& io) {
   float* dD0 = c.alloc((size_t)M0 * 96);
   if (!c.dry) {
     const Lin& o = t->out;
-    launch_pw_gemm(d4, 16, c.P + o.w, 16, 0, c.P + o.b, lg, 1, M3, 16, 1, 0, c.s);                 // self.output (:271)
+    if (!launch_lin1_fwd(d4, 16, c.P + o.w, c.P + o.b, lg, 16, M3, c.s))                           // self.output (:271)
+      launch_pw_gemm(d4, 16, c.P + o.w, 16, 0, c.P + o.b, lg, 1, M3, 16, 1, 0, c.s);
     launch_loss(lg, io.target, M3, lacc, io.loss_kind, io.grad_scale, dlg, io.loss3, c.s);
     BnRef none = {};
     launch_col_reduce(2, dlg, 4, nullptr, 0, none, 0, obs, 4, 1, M3 / 4, c.s);                     // d bias = sum dlogits
     launch_add_sums(obs, c.G + o.b, 1, 4, c.s);
     launch_pw_wgrad(dlg, 1, d4, 16, c.G + o.w, 16, M3, 16, 1, c.s);
-    launch_pw_gemm(dlg, 1, c.P + o.w, 16, 1, nullptr, dD4, 16, M3, 1, 16, 0, c.s);
+    if (!launch_lin1_dgrad(dlg, c.P + o.w, dD4, 16, 16, M3, c.s))
+      launch_pw_gemm(dlg, 1, c.P + o.w, 16, 1, nullptr, dD4, 16, M3, 1, 16, 0, c.s);
     c.launches += 7;
     c.acct((double)M3 * (17 + 2 + 3 + 1 + 17 + 17));
   }
