@@ -1194,7 +1194,25 @@ __global__ void __launch_bounds__(256) add_copy_kernel(const float* __restrict__
     O[m * ldo + c] = v;
   }
 }
+// 16-byte version: C, the row strides and the base addresses are multiples of four floats
+__global__ void __launch_bounds__(256) add_copy4_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B,
+                                                        int ldb, float* O, int ldo, int C4, long long M) {
+  const long long total = M * C4;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    const int c = (int)(e % C4) * 4;
+    const long long m = e / C4;
+    float4 v = *reinterpret_cast<const float4*>(A + m * lda + c);
+    if (B) { const float4 w = *reinterpret_cast<const float4*>(B + m * ldb + c); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+    *reinterpret_cast<float4*>(O + m * ldo + c) = v;
+  }
+}
 void launch_add_copy(const float* A, int lda, const float* B, int ldb, float* O, int ldo, int C, long long M, cudaStream_t s) {
+  const bool v4 = ((C | lda | ldo | (B ? ldb : 0)) & 3) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(O) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
+  if (v4) {
+    add_copy4_kernel<<<(int)std::min<long long>(cdivl(M * (C / 4), 256), 148 * 16), 256, 0, s>>>(A, lda, B, ldb, O, ldo, C / 4, M);
+    return;
+  }
   int grid = (int)std::min<long long>(cdivl(M * C, 256), 148 * 16);
   add_copy_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, O, ldo, C, M);
 }
@@ -1619,6 +1637,10 @@ __global__ void __launch_bounds__(256) export_view_kernel(const T* __restrict__ 
   }
 }
 void launch_export_view(const void* in, int in_cs, int dt, float* out, int C, long long M, cudaStream_t s) {
+  if (dt == DT_F32 && ((C | in_cs) & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    launch_add_copy(reinterpret_cast<const float*>(in), in_cs, nullptr, 0, out, C, C, M, s);      // a strided fp32 copy
+    return;
+  }
   int grid = (int)std::min<long long>(cdivl(M * C, 256), 148 * 16);
   if (dt == DT_F32) export_view_kernel<float><<<grid, 256, 0, s>>>((const float*)in, in_cs, out, C, M);
   else export_view_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, in_cs, out, C, M);
