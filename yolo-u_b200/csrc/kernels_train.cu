@@ -1286,42 +1286,55 @@ void launch_up2_bwd(const float* DY, int ldd, float* DX, int ldx, int N, int h, 
 // The DoubleLightConv form of up2 (train.cu: dlc_fwd runs both 1x1 convs on the upsampled tensor at LOW resolution).
 //   up2_split: X [N,h,w][C0 + C1] -> Y0 [N,2h,2w][C0] (= z of conv.0.conv1, with its BatchNorm statistics: column sum and sum
 //              of squares into `sums`) and Y1 [N,2h,2w][C1] (= the residual branch): one read of X, no separate statistics pass.
+// thread = one LOW-resolution pixel x channel quad: its 3 x 3 neighbourhood (clamped) gives the 2 x 2 output pixels it covers --
+// 9 loads for 4 outputs where the per-output form needs 16, and a third of the index arithmetic
 __global__ void __launch_bounds__(256) up2_split_kernel(const float* __restrict__ X, int ldx, float* Y0, int ldy0, int C0,
                                                         float* Y1, int ldy1, int N, int h, int w, int C, double* sums) {
   extern __shared__ double ssum[];      // [2][C0]
-  const int H = 2 * h, Wd = 2 * w, q = threadIdx.x;
+  const int Wd = 2 * w, q = threadIdx.x;
   const int nthr = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
   for (int e = tid; e < 2 * C0; e += nthr) ssum[e] = 0.0;
   __syncthreads();
-  const unsigned total = (unsigned)N * H * Wd;
+  const unsigned total = (unsigned)N * h * w;
   const bool first = q * 4 < C0;
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   for (unsigned pix = blockIdx.x * blockDim.y + threadIdx.y; pix < total; pix += gridDim.x * blockDim.y) {
-    const int ox = pix % (unsigned)Wd;
-    const unsigned t = pix / (unsigned)Wd;
-    const int oy = t % (unsigned)H;
-    const unsigned n = t / (unsigned)H;
-    int jy = oy >> 1, jx = ox >> 1;
-    int y0 = (oy & 1) ? jy : max(jy - 1, 0), y1 = (oy & 1) ? min(jy + 1, h - 1) : jy;
-    int x0 = (ox & 1) ? jx : max(jx - 1, 0), x1 = (ox & 1) ? min(jx + 1, w - 1) : jx;
-    float wy1 = (oy & 1) ? 0.25f : 0.75f, wx1 = (ox & 1) ? 0.25f : 0.75f;
+    const int jx = pix % (unsigned)w;
+    const unsigned t = pix / (unsigned)w;
+    const int jy = t % (unsigned)h;
+    const unsigned n = t / (unsigned)h;
+    const int ym = max(jy - 1, 0), yp = min(jy + 1, h - 1), xm = max(jx - 1, 0), xp = min(jx + 1, w - 1);
     const float* b = X + (size_t)n * h * w * ldx + q * 4;
-    float4 a00 = *reinterpret_cast<const float4*>(b + (size_t)(y0 * w + x0) * ldx);
-    float4 a01 = *reinterpret_cast<const float4*>(b + (size_t)(y0 * w + x1) * ldx);
-    float4 a10 = *reinterpret_cast<const float4*>(b + (size_t)(y1 * w + x0) * ldx);
-    float4 a11 = *reinterpret_cast<const float4*>(b + (size_t)(y1 * w + x1) * ldx);
-    float wy0 = 1.f - wy1, wx0 = 1.f - wx1;
-    float4 o;
-    o.x = wy0 * (wx0 * a00.x + wx1 * a01.x) + wy1 * (wx0 * a10.x + wx1 * a11.x);
-    o.y = wy0 * (wx0 * a00.y + wx1 * a01.y) + wy1 * (wx0 * a10.y + wx1 * a11.y);
-    o.z = wy0 * (wx0 * a00.z + wx1 * a01.z) + wy1 * (wx0 * a10.z + wx1 * a11.z);
-    o.w = wy0 * (wx0 * a00.w + wx1 * a01.w) + wy1 * (wx0 * a10.w + wx1 * a11.w);
-    if (first) {
-      *reinterpret_cast<float4*>(Y0 + (size_t)pix * ldy0 + q * 4) = o;
-      s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
-      s2[0] = fmaf(o.x, o.x, s2[0]); s2[1] = fmaf(o.y, o.y, s2[1]); s2[2] = fmaf(o.z, o.z, s2[2]); s2[3] = fmaf(o.w, o.w, s2[3]);
-    } else {
-      *reinterpret_cast<float4*>(Y1 + (size_t)pix * ldy1 + (q * 4 - C0)) = o;
+    float4 a[3][3];
+    const int ys[3] = {ym, jy, yp}, xs[3] = {xm, jx, xp};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a[r][c] = *reinterpret_cast<const float4*>(b + (size_t)(ys[r] * w + xs[c]) * ldx);
+    float* o0 = first ? Y0 + q * 4 : Y1 + (q * 4 - C0);
+    const int ld = first ? ldy0 : ldy1;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      // output row 2 jy + dy: rows (jy - 1, jy) with weights (.25, .75) for dy = 0, rows (jy, jy + 1) with (.75, .25) for dy = 1
+      const int r0 = dy, r1 = dy + 1;
+      const float wy0 = dy ? 0.75f : 0.25f, wy1 = 1.f - wy0;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int c0 = dx, c1 = dx + 1;
+        const float wx0 = dx ? 0.75f : 0.25f, wx1 = 1.f - wx0;
+        float4 o;
+        // same association as ATen's upsample_bilinear2d: w_y0*(w_x0*a00 + w_x1*a01) + w_y1*(w_x0*a10 + w_x1*a11)
+        o.x = wy0 * (wx0 * a[r0][c0].x + wx1 * a[r0][c1].x) + wy1 * (wx0 * a[r1][c0].x + wx1 * a[r1][c1].x);
+        o.y = wy0 * (wx0 * a[r0][c0].y + wx1 * a[r0][c1].y) + wy1 * (wx0 * a[r1][c0].y + wx1 * a[r1][c1].y);
+        o.z = wy0 * (wx0 * a[r0][c0].z + wx1 * a[r0][c1].z) + wy1 * (wx0 * a[r1][c0].z + wx1 * a[r1][c1].z);
+        o.w = wy0 * (wx0 * a[r0][c0].w + wx1 * a[r0][c1].w) + wy1 * (wx0 * a[r1][c0].w + wx1 * a[r1][c1].w);
+        const size_t opix = ((size_t)n * 2 * h + 2 * jy + dy) * Wd + 2 * jx + dx;
+        *reinterpret_cast<float4*>(o0 + opix * ld) = o;
+        if (first) {
+          s1[0] += o.x; s1[1] += o.y; s1[2] += o.z; s1[3] += o.w;
+          s2[0] = fmaf(o.x, o.x, s2[0]); s2[1] = fmaf(o.y, o.y, s2[1]); s2[2] = fmaf(o.z, o.z, s2[2]); s2[3] = fmaf(o.w, o.w, s2[3]);
+        }
+      }
     }
   }
   if (first) {
@@ -1334,7 +1347,7 @@ __global__ void __launch_bounds__(256) up2_split_kernel(const float* __restrict_
 void launch_up2_split(const float* X, int ldx, float* Y0, int ldy0, int C0, float* Y1, int ldy1, int C1, int N, int h, int w,
                       double* sums, cudaStream_t s) {
   const int C = C0 + C1;
-  up2_split_kernel<<<quad_grid((long long)N * 4 * h * w, C, 8), quad_block(C), (size_t)2 * C0 * sizeof(double), s>>>(
+  up2_split_kernel<<<quad_grid((long long)N * h * w, C, 8), quad_block(C), (size_t)2 * C0 * sizeof(double), s>>>(
       X, ldx, Y0, ldy0, C0, Y1, ldy1, N, h, w, C, sums);
 }
 
