@@ -661,7 +661,7 @@ static bool launch_pw_gemm_tc2(GemmTcP p, int trans, cudaStream_t s) {
   int S = fixed < 100 * 1024 ? (int)((100 * 1024 - fixed) / slot) : 0;
   if (S < 3) { per_sm = 1; S = fixed < 208 * 1024 ? (int)((208 * 1024 - fixed) / slot) : 0; }
   if (S > kG2MaxS) S = kG2MaxS;
-  if (S < 3) return false;
+  if (S < 2) return false;                                 // K = 144 (the 129-channel concat): two 74-KB slots, one per loader group
   const size_t smem = fixed + (size_t)S * slot;
   static int sms = 0;
   if (!sms) { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d); if (sms <= 0) sms = 148; }
