@@ -87,7 +87,7 @@ class YOLOSegPlusPlus(nn.Module):
     """`YOLOSegPlusPlus(predictor)(x, logits) -> mask logits [B,1,H,W]`.
 
     predictor: anything with `.model.model.model[0:5]` (the fused detector's first five modules, shared by
-    reference like YOLOSegPlusPlus.py:150).  `mode`: "fp32" (parity, default) or "bf16" (throughput).
+    reference like YOLOSegPlusPlus.py:150).  `mode`: "tc32" (tensor-core parity mode, default), "bf16" (throughput) or "fp32" (CUDA-core reference).
     """
 
     def __init__(self, predictor, verbose: bool = False, target_modules_indices: List[int] = [2, 4, 6],
@@ -111,7 +111,6 @@ class YOLOSegPlusPlus(nn.Module):
         self.param = nn.Parameter(torch.tensor([5.0]))
         self.verbose = verbose
         self.skip_connections = []
-        self._indices = {"upsample": {2, 5, 6}, "skip_connections_encoder": {2, 4}, "skip_connections_decoder": {0, 2}}
         self.mode = mode
         self.use_logits = use_logits
         self._engine: Optional[Engine] = None
