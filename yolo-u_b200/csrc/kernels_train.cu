@@ -1065,7 +1065,10 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict
 
 void launch_col_reduce(int mode, const float* A, int lda, const float* B, int ldb, const BnRef& bn, int act, double* sums,
                        int C, long long segs, long long rows_per_seg, cudaStream_t s) {
-  long long want = std::max<long long>(1, (148 * 8) / segs);
+  // CTAs per SM of the reduction grid, measured on the whole step (ms): 1: 13.74, 2: 13.32, 3: 13.56, 4: 13.48, 8: 13.87, 16: 14.52 --
+  // few CTAs with long contiguous row ranges and few double-precision atomics win
+  static const int per_sm = getenv("YSP_COLRED_PER_SM") ? atoi(getenv("YSP_COLRED_PER_SM")) : 2;
+  long long want = std::max<long long>(1, (148 * per_sm) / segs);
   long long per = std::max<long long>(cdivl(rows_per_seg, want), 64);
   dim3 grid(cdivl(rows_per_seg, per), (unsigned)segs);
   size_t sm = (size_t)2 * C * sizeof(double);
